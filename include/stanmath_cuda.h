@@ -1,0 +1,212 @@
+/* stanmath_cuda.h -- C ABI of libstanmath_cuda.so, the B200 (sm_100a) backend for
+ * Stan Math's GLM log-density + gradient hot path.
+ *
+ * This is the boundary a `stan/math/cuda` backend binds, the slot the
+ * reference's OpenCL backend occupies today:
+ *   - smc_matrix            <-> matrix_cl<T>        stan/math/opencl/matrix_cl.hpp L46-55
+ *   - smc_matrix_upload/... <-> to_matrix_cl / from_matrix_cl   stan/math/opencl/copy.hpp L45, L61-235
+ *   - smc_<family>_glm      <-> the matrix_cl overloads of the same names in
+ *                               stan/math/opencl/prim/<family>_glm_l{pdf,pmf}.hpp
+ *                               (value + partials of prim/prob/<family>_glm_*.hpp)
+ * The C++ header overloads that call it live in include/stan/math/cuda/.
+ *
+ * Conventions
+ *   - Plain C: opaque handles, pointers and sizes; no exceptions cross the ABI.
+ *   - Matrices are column-major (Eigen / matrix_cl default), dtype f64 or i32.
+ *   - Every call returns smc_status; smc_last_error() gives the thread-local text.
+ *     SMC_ERR_INVALID_ARGUMENT <-> std::invalid_argument (sizes),
+ *     SMC_ERR_DOMAIN           <-> std::domain_error (values),
+ *     SMC_ERR_CUDA             <-> std::system_error (backend failure).
+ *   - Re-entrant: each host thread owns its device, stream and workspace, so
+ *     several chains may evaluate against the same read-only device x.
+ *   - Caller owns host buffers; the library owns device buffers behind handles.
+ *   - There is no CPU fallback: without a CUDA device every compute call fails
+ *     with SMC_ERR_CUDA.
+ *
+ * `flags` mirror the reference's compile-time switches
+ * (include_summand<propto, ...>, is_constant_all<...>): a term or a partial is
+ * computed only when the reference would compute it.
+ */
+#ifndef STANMATH_CUDA_H
+#define STANMATH_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct smc_matrix smc_matrix;
+
+enum smc_status {
+  SMC_OK = 0,
+  SMC_ERR_INVALID_ARGUMENT = 1,
+  SMC_ERR_DOMAIN = 2,
+  SMC_ERR_CUDA = 3,
+  SMC_ERR_UNSUPPORTED = 4
+};
+
+enum smc_dtype { SMC_F64 = 0, SMC_I32 = 1 };
+
+/* flags */
+#define SMC_PROPTO 1u     /* propto = true                                   */
+#define SMC_VAR_X 2u      /* x is an autodiff variable -> d_x is produced    */
+#define SMC_VAR_ALPHA 4u  /* alpha is a var                                  */
+#define SMC_VAR_BETA 8u   /* beta is a var                                   */
+#define SMC_VAR_AUX 16u   /* sigma / phi / cuts is a var                     */
+#define SMC_VAR_Y 32u     /* y is a var (normal_id_glm only)                 */
+
+/* Layout of the packed result vector written by the *_device entry points
+ * (and all-reduced across GPUs by the row-sharded driver):
+ *   [0] log density   [1] sum_i d_i   [2] family aux sum   [3] #rows with a
+ *   non-finite linear predictor   [4] second aux sum   [5..7] reserved
+ *   [8 .. 8+K)            d_beta
+ *   [8+K .. 8+K+ncuts)    d_cuts (ordered_logistic only)                    */
+#define SMC_OUT_HEADER 8
+#define SMC_OUT_LOGP 0
+#define SMC_OUT_SUM_D 1
+#define SMC_OUT_AUX 2
+#define SMC_OUT_NONFINITE 3
+#define SMC_OUT_AUX2 4
+
+/* ---- runtime ------------------------------------------------------------- */
+int smc_device_count(int* count);
+int smc_set_device(int device);        /* for the calling thread               */
+int smc_get_device(int* device);
+/* Use an existing CUDA stream (cudaStream_t) for the calling thread's launches;
+ * NULL restores the library's own non-blocking stream. */
+int smc_set_stream(void* cuda_stream);
+int smc_synchronize(void);
+int smc_device_info(int* sm_count, int* cc_major, int* cc_minor,
+                    size_t* free_bytes, size_t* total_bytes);
+const char* smc_last_error(void);
+/* Number of GLM kernel launches issued by the calling thread since the last
+ * smc_reset_launch_count (bench.py's gpu_launches). */
+int64_t smc_launch_count(void);
+void smc_reset_launch_count(void);
+
+/* ---- device matrix (matrix_cl analogue) ---------------------------------- */
+/* rows x cols, column-major; the library pads the leading dimension so every
+ * column starts 128-byte aligned (TMA requirement and full-sector DRAM reads). */
+int smc_matrix_create(int64_t rows, int64_t cols, int dtype, smc_matrix** out);
+/* Wrap an existing device buffer (not owned), cf. matrix_cl.hpp L190-192. */
+int smc_matrix_wrap(void* device_ptr, int64_t rows, int64_t cols, int64_t ld,
+                    int dtype, smc_matrix** out);
+int smc_matrix_free(smc_matrix* m);
+int64_t smc_matrix_rows(const smc_matrix* m);
+int64_t smc_matrix_cols(const smc_matrix* m);
+int64_t smc_matrix_ld(const smc_matrix* m);
+int smc_matrix_dtype(const smc_matrix* m);
+void* smc_matrix_data(const smc_matrix* m);
+/* Host <-> device copies; ld_host is the host leading dimension in elements. */
+int smc_matrix_upload(smc_matrix* m, const void* host, int64_t ld_host);
+/* Upload the row block [row0, row0+nrows) from a host matrix whose element
+ * (row0, 0) is at `host` (row-sharding: one call per GPU, ld_host = N). */
+int smc_matrix_upload_rows(smc_matrix* m, int64_t row0, int64_t nrows,
+                           const void* host, int64_t ld_host);
+int smc_matrix_download(const smc_matrix* m, void* host, int64_t ld_host);
+int smc_matrix_download_rows(const smc_matrix* m, int64_t row0, int64_t nrows,
+                             void* host, int64_t ld_host);
+int smc_matrix_zero(smc_matrix* m);
+/* y += a * x on the device: update_adjoints for a device-resident operand
+ * (rev/functor/operands_and_partials.hpp L28-38). */
+int smc_matrix_axpy(smc_matrix* y, double a, const smc_matrix* x);
+/* Lazy value checks (cf. check_cl in opencl/prim/ *_glm_*.hpp). */
+int smc_matrix_all_finite(const smc_matrix* m, int* all_finite);
+int smc_matrix_int_range(const smc_matrix* m, int* min_out, int* max_out);
+/* Deterministic synthetic fill, identical on every GPU and reproducible on the
+ * host (counter-based hash of (seed, row0+i, k); exact integer arithmetic and a
+ * single correctly-rounded multiply, so host and device agree bit for bit):
+ *   kind 0: f64, zero mean, unit variance (sum of four 16-bit uniforms), *scale
+ *   kind 1: i32 uniform in [lo, hi]                                          */
+int smc_matrix_fill_synthetic(smc_matrix* m, uint64_t seed, int64_t row0,
+                              int kind, double scale, int lo, int hi);
+
+/* ---- GLM log density + gradient ------------------------------------------ */
+/* Common argument meaning (N = x rows, K = x cols):
+ *   y            N x 1 device vector (i32; f64 for normal_id) or NULL to
+ *                broadcast the scalar y_scalar
+ *   x            N x K f64 device matrix (uploaded once, reused every call)
+ *   alpha_vec    N x 1 f64 device vector, or NULL -> scalar `alpha`
+ *   beta         host pointer, K doubles
+ *   logp         host out: the log density the reference returns
+ *   d_alpha      host out (1 double): sum_i d_i, the partial of a scalar alpha
+ *   d_alpha_vec  device out N x 1: the partial of a vector alpha (or NULL)
+ *   d_beta       host out, K doubles
+ *   d_x          device out N x K (required when SMC_VAR_X is set)
+ * Outputs whose flag is not set are not written and may be NULL.             */
+
+/* prim/prob/bernoulli_logit_glm_lpmf.hpp L49-167 */
+int smc_bernoulli_logit_glm(const smc_matrix* y, int y_scalar,
+                            const smc_matrix* x, const smc_matrix* alpha_vec,
+                            double alpha, const double* beta, unsigned flags,
+                            double* logp, double* d_alpha,
+                            smc_matrix* d_alpha_vec, double* d_beta,
+                            smc_matrix* d_x);
+
+/* prim/prob/poisson_log_glm_lpmf.hpp L51-163 */
+int smc_poisson_log_glm(const smc_matrix* y, int y_scalar, const smc_matrix* x,
+                        const smc_matrix* alpha_vec, double alpha,
+                        const double* beta, unsigned flags, double* logp,
+                        double* d_alpha, smc_matrix* d_alpha_vec,
+                        double* d_beta, smc_matrix* d_x);
+
+/* prim/prob/normal_id_glm_lpdf.hpp L54-216
+ *   sigma_vec N x 1 device or NULL -> scalar sigma;  d_sigma host (scalar sigma)
+ *   or d_sigma_vec device (vector sigma);  d_y host (scalar y) / d_y_vec device */
+int smc_normal_id_glm(const smc_matrix* y, double y_scalar, const smc_matrix* x,
+                      const smc_matrix* alpha_vec, double alpha,
+                      const double* beta, const smc_matrix* sigma_vec,
+                      double sigma, unsigned flags, double* logp,
+                      double* d_alpha, smc_matrix* d_alpha_vec, double* d_beta,
+                      double* d_sigma, smc_matrix* d_sigma_vec, double* d_y,
+                      smc_matrix* d_y_vec, smc_matrix* d_x);
+
+/* prim/prob/neg_binomial_2_log_glm_lpmf.hpp L64-248 */
+int smc_neg_binomial_2_log_glm(const smc_matrix* y, int y_scalar,
+                               const smc_matrix* x, const smc_matrix* alpha_vec,
+                               double alpha, const double* beta,
+                               const smc_matrix* phi_vec, double phi,
+                               unsigned flags, double* logp, double* d_alpha,
+                               smc_matrix* d_alpha_vec, double* d_beta,
+                               double* d_phi, smc_matrix* d_phi_vec,
+                               smc_matrix* d_x);
+
+/* prim/prob/ordered_logistic_glm_lpmf.hpp L46-210; cuts host, ncuts = C-1 */
+int smc_ordered_logistic_glm(const smc_matrix* y, int y_scalar,
+                             const smc_matrix* x, const double* beta,
+                             const double* cuts, int64_t ncuts, unsigned flags,
+                             double* logp, double* d_beta, double* d_cuts,
+                             smc_matrix* d_x);
+
+/* prim/prob/categorical_logit_glm_lpmf.hpp L43-195
+ *   alpha host (C), beta host column-major K x C, d_alpha host (C),
+ *   d_beta host column-major K x C */
+int smc_categorical_logit_glm(const smc_matrix* y, int y_scalar,
+                              const smc_matrix* x, const double* alpha,
+                              const double* beta, int64_t n_classes,
+                              unsigned flags, double* logp, double* d_alpha,
+                              double* d_beta, smc_matrix* d_x);
+
+/* ---- device-resident results (pipelining / multi-GPU) -------------------- */
+/* Same evaluation, but asynchronous on the thread's stream: parameters are read
+ * from DEVICE memory (`params_dev`: beta[K], then cuts[ncuts] for ordered) and
+ * the packed result (layout above, SMC_OUT_HEADER + K (+ ncuts) doubles) is
+ * left in `out_dev` for an NCCL all-reduce; no host synchronisation and no
+ * value checks (the caller inspects out[SMC_OUT_NONFINITE]).  `family`:
+ * 0 normal_id, 1 bernoulli_logit, 2 poisson_log, 3 neg_binomial_2_log,
+ * 4 ordered_logistic.  Scalars alpha/aux are passed by value; out[0] already
+ * contains every term of the reference's logp for this rank's rows. */
+int smc_glm_eval_device(int family, const smc_matrix* y, double y_scalar,
+                        const smc_matrix* x, const smc_matrix* alpha_vec,
+                        double alpha, const smc_matrix* aux_vec, double aux,
+                        const double* params_dev, int64_t ncuts, unsigned flags,
+                        double* out_dev, smc_matrix* d_alpha_vec,
+                        smc_matrix* d_aux_vec, smc_matrix* d_y_vec,
+                        smc_matrix* d_x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STANMATH_CUDA_H */

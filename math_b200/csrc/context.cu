@@ -1,0 +1,423 @@
+// Per-thread runtime state and the device matrix type (matrix_cl analogue,
+// reference: stan/math/opencl/matrix_cl.hpp L46-55, opencl/copy.hpp).
+#include <cmath>
+#include <cstring>
+
+#include "smc_internal.h"
+
+namespace smc {
+
+static thread_local Context t_ctx;
+
+Context& ctx() { return t_ctx; }
+
+Context::~Context() {
+  // Runs at thread exit; the CUDA runtime may already be gone at process exit,
+  // so errors are ignored.
+  if (!inited) return;
+  if (cudaSetDevice(device) != cudaSuccess) return;
+  if (partials) cudaFree(partials);
+  if (counter) cudaFree(counter);
+  if (params_dev) cudaFree(params_dev);
+  if (scratch) cudaFree(scratch);
+  if (out_host) cudaFreeHost(out_host);
+  if (own_stream) cudaStreamDestroy(own_stream);
+}
+
+int fail(int status, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  t_ctx.last_error = buf;
+  return status;
+}
+
+static int bind_device(int device) {
+  Context& c = t_ctx;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(SMC_ERR_CUDA,
+                "no CUDA device available (%s); libstanmath_cuda has no CPU "
+                "fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n)
+    return fail(SMC_ERR_INVALID_ARGUMENT, "device %d out of range [0,%d)",
+                device, n);
+  if (c.inited && c.device == device) {
+    SMC_CUDA(cudaSetDevice(device));
+    return SMC_OK;
+  }
+  if (c.inited) {
+    // moving the thread to another device: drop the old workspace
+    c.~Context();
+    new (&c) Context();
+  }
+  SMC_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SMC_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(SMC_ERR_UNSUPPORTED,
+                "device %d is sm_%d%d; this library is built for sm_100a only",
+                device, prop.major, prop.minor);
+  c.device = device;
+  c.sm_count = prop.multiProcessorCount;
+  SMC_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+  c.stream = c.own_stream;
+  SMC_CUDA(cudaMalloc(&c.counter, 64));
+  SMC_CUDA(cudaMemset(c.counter, 0, 64));
+  c.inited = true;
+  return SMC_OK;
+}
+
+int ensure_ctx() {
+  if (t_ctx.inited) {
+    SMC_CUDA(cudaSetDevice(t_ctx.device));
+    return SMC_OK;
+  }
+  return bind_device(0);
+}
+
+static int grow(void** p, size_t* have, size_t want, bool pinned) {
+  if (*have >= want) return SMC_OK;
+  size_t n = want < 4096 ? 4096 : want;
+  if (*p) {
+    // make sure nothing in flight still uses the old buffer
+    SMC_CUDA(cudaStreamSynchronize(t_ctx.stream));
+    if (pinned)
+      SMC_CUDA(cudaFreeHost(*p));
+    else
+      SMC_CUDA(cudaFree(*p));
+    *p = nullptr;
+    *have = 0;
+  }
+  if (pinned)
+    SMC_CUDA(cudaHostAlloc(p, n, cudaHostAllocMapped | cudaHostAllocPortable));
+  else
+    SMC_CUDA(cudaMalloc(p, n));
+  *have = n;
+  return SMC_OK;
+}
+
+int ensure_partials(size_t bytes) {
+  return grow(reinterpret_cast<void**>(&t_ctx.partials), &t_ctx.partials_bytes,
+              bytes, false);
+}
+int ensure_params(size_t bytes) {
+  return grow(reinterpret_cast<void**>(&t_ctx.params_dev), &t_ctx.params_bytes,
+              bytes, false);
+}
+int ensure_out(size_t bytes) {
+  return grow(reinterpret_cast<void**>(&t_ctx.out_host), &t_ctx.out_bytes, bytes,
+              true);
+}
+int ensure_scratch(size_t bytes) {
+  return grow(reinterpret_cast<void**>(&t_ctx.scratch), &t_ctx.scratch_bytes,
+              bytes, false);
+}
+
+// ---------------------------------------------------------------- kernels
+__global__ void axpy_kernel(double* __restrict__ y, int64_t ldy,
+                            const double* __restrict__ x, int64_t ldx,
+                            int64_t rows, int64_t cols, double a) {
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = i / rows, r = i - c * rows;
+    y[c * ldy + r] += a * x[c * ldx + r];
+  }
+}
+
+__global__ void all_finite_kernel(const double* __restrict__ x, int64_t ld,
+                                  int64_t rows, int64_t cols, int* bad) {
+  const int64_t total = rows * cols;
+  int local = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = i / rows, r = i - c * rows;
+    if (!isfinite(x[c * ld + r])) local = 1;
+  }
+  if (__any_sync(0xffffffffu, local) && (threadIdx.x & 31) == 0) *bad = 1;
+}
+
+__host__ __device__ inline uint64_t synth_hash(uint64_t seed, uint64_t row,
+                                               uint64_t col) {
+  uint64_t z = seed + row * 0x9E3779B97F4A7C15ull + col * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+__global__ void fill_synth_kernel(void* data, int64_t ld, int64_t rows,
+                                  int64_t cols, int dtype, uint64_t seed,
+                                  int64_t row0, int kind, double c, int lo,
+                                  int hi) {
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t col = i / rows, r = i - col * rows;
+    const uint64_t z = synth_hash(seed, (uint64_t)(row0 + r), (uint64_t)col);
+    if (kind == 0) {
+      const uint32_t u = (uint32_t)(z & 0xffff) + (uint32_t)((z >> 16) & 0xffff)
+                         + (uint32_t)((z >> 32) & 0xffff) + (uint32_t)(z >> 48);
+      static_cast<double*>(data)[col * ld + r] = ((double)u - 131070.0) * c;
+    } else {
+      const uint64_t span = (uint64_t)((int64_t)hi - (int64_t)lo + 1);
+      const int v = (int)((int64_t)lo + (int64_t)(z % span));
+      if (dtype == SMC_I32)
+        static_cast<int*>(data)[col * ld + r] = v;
+      else
+        static_cast<double*>(data)[col * ld + r] = (double)v;
+    }
+  }
+}
+
+static inline int grid_for(int64_t total, int threads) {
+  int64_t b = (total + threads - 1) / threads;
+  const int64_t cap = (int64_t)t_ctx.sm_count * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+static inline size_t elem_size(int dtype) { return dtype == SMC_F64 ? 8 : 4; }
+
+}  // namespace smc
+
+using namespace smc;
+
+extern "C" {
+
+int smc_device_count(int* count) {
+  if (!count) return fail(SMC_ERR_INVALID_ARGUMENT, "count is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return fail(SMC_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  }
+  *count = n;
+  return SMC_OK;
+}
+
+int smc_set_device(int device) { return bind_device(device); }
+
+int smc_get_device(int* device) {
+  if (int rc = ensure_ctx()) return rc;
+  *device = ctx().device;
+  return SMC_OK;
+}
+
+int smc_set_stream(void* s) {
+  if (int rc = ensure_ctx()) return rc;
+  ctx().stream = s ? static_cast<cudaStream_t>(s) : ctx().own_stream;
+  return SMC_OK;
+}
+
+int smc_synchronize(void) {
+  if (int rc = ensure_ctx()) return rc;
+  SMC_CUDA(cudaStreamSynchronize(ctx().stream));
+  return SMC_OK;
+}
+
+int smc_device_info(int* sm_count, int* cc_major, int* cc_minor,
+                    size_t* free_bytes, size_t* total_bytes) {
+  if (int rc = ensure_ctx()) return rc;
+  cudaDeviceProp prop;
+  SMC_CUDA(cudaGetDeviceProperties(&prop, ctx().device));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  size_t f = 0, t = 0;
+  SMC_CUDA(cudaMemGetInfo(&f, &t));
+  if (free_bytes) *free_bytes = f;
+  if (total_bytes) *total_bytes = t;
+  return SMC_OK;
+}
+
+const char* smc_last_error(void) { return ctx().last_error.c_str(); }
+int64_t smc_launch_count(void) { return ctx().launches; }
+void smc_reset_launch_count(void) { ctx().launches = 0; }
+
+// ------------------------------------------------------------------ matrix
+int smc_matrix_create(int64_t rows, int64_t cols, int dtype, smc_matrix** out) {
+  if (!out) return fail(SMC_ERR_INVALID_ARGUMENT, "out is NULL");
+  if (rows < 0 || cols < 0 || (dtype != SMC_F64 && dtype != SMC_I32))
+    return fail(SMC_ERR_INVALID_ARGUMENT, "bad matrix shape/dtype %lld x %lld",
+                (long long)rows, (long long)cols);
+  if (int rc = ensure_ctx()) return rc;
+  smc_matrix* m = new smc_matrix();
+  m->rows = rows;
+  m->cols = cols;
+  m->dtype = dtype;
+  m->device = ctx().device;
+  const int64_t align = 128 / (int64_t)elem_size(dtype);
+  m->ld = cols > 1 ? (rows + align - 1) / align * align : rows;
+  if (m->ld < 1) m->ld = 1;
+  const size_t bytes = (size_t)m->ld * (size_t)(cols > 0 ? cols : 1) * elem_size(dtype);
+  cudaError_t e = cudaMalloc(&m->data, bytes < 256 ? 256 : bytes);
+  if (e != cudaSuccess) {
+    delete m;
+    return fail(SMC_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", bytes,
+                cudaGetErrorString(e));
+  }
+  m->owned = true;
+  *out = m;
+  return SMC_OK;
+}
+
+int smc_matrix_wrap(void* device_ptr, int64_t rows, int64_t cols, int64_t ld,
+                    int dtype, smc_matrix** out) {
+  if (!out || (!device_ptr && rows * cols > 0) || rows < 0 || cols < 0
+      || ld < rows || (dtype != SMC_F64 && dtype != SMC_I32))
+    return fail(SMC_ERR_INVALID_ARGUMENT, "bad arguments to smc_matrix_wrap");
+  if (int rc = ensure_ctx()) return rc;
+  smc_matrix* m = new smc_matrix();
+  m->data = device_ptr;
+  m->rows = rows;
+  m->cols = cols;
+  m->ld = ld < 1 ? 1 : ld;
+  m->dtype = dtype;
+  m->owned = false;
+  m->device = ctx().device;
+  *out = m;
+  return SMC_OK;
+}
+
+int smc_matrix_free(smc_matrix* m) {
+  if (!m) return SMC_OK;
+  if (m->owned && m->data) {
+    if (int rc = ensure_ctx()) return rc;
+    SMC_CUDA(cudaStreamSynchronize(ctx().stream));
+    SMC_CUDA(cudaFree(m->data));
+  }
+  delete m;
+  return SMC_OK;
+}
+
+int64_t smc_matrix_rows(const smc_matrix* m) { return m ? m->rows : 0; }
+int64_t smc_matrix_cols(const smc_matrix* m) { return m ? m->cols : 0; }
+int64_t smc_matrix_ld(const smc_matrix* m) { return m ? m->ld : 0; }
+int smc_matrix_dtype(const smc_matrix* m) { return m ? m->dtype : -1; }
+void* smc_matrix_data(const smc_matrix* m) { return m ? m->data : nullptr; }
+
+static int copy_rows(smc_matrix* m, int64_t row0, int64_t nrows, void* host,
+                     int64_t ld_host, bool to_device) {
+  if (!m || (!host && nrows * m->cols > 0))
+    return fail(SMC_ERR_INVALID_ARGUMENT, "NULL matrix or host pointer");
+  if (row0 < 0 || nrows < 0 || row0 + nrows > m->rows || ld_host < nrows)
+    return fail(SMC_ERR_INVALID_ARGUMENT,
+                "row block [%lld,%lld) outside matrix with %lld rows (ld_host "
+                "%lld)",
+                (long long)row0, (long long)(row0 + nrows), (long long)m->rows,
+                (long long)ld_host);
+  if (int rc = ensure_ctx()) return rc;
+  if (nrows == 0 || m->cols == 0) return SMC_OK;
+  const size_t es = elem_size(m->dtype);
+  char* dev = static_cast<char*>(m->data) + (size_t)row0 * es;
+  if (to_device) {
+    m->lgamma_valid = false;
+    m->range_valid = false;
+    SMC_CUDA(cudaMemcpy2DAsync(dev, (size_t)m->ld * es, host,
+                               (size_t)ld_host * es, (size_t)nrows * es,
+                               (size_t)m->cols, cudaMemcpyHostToDevice,
+                               ctx().stream));
+  } else {
+    SMC_CUDA(cudaMemcpy2DAsync(host, (size_t)ld_host * es, dev,
+                               (size_t)m->ld * es, (size_t)nrows * es,
+                               (size_t)m->cols, cudaMemcpyDeviceToHost,
+                               ctx().stream));
+  }
+  SMC_CUDA(cudaStreamSynchronize(ctx().stream));
+  return SMC_OK;
+}
+
+int smc_matrix_upload(smc_matrix* m, const void* host, int64_t ld_host) {
+  return copy_rows(m, 0, m ? m->rows : 0, const_cast<void*>(host), ld_host, true);
+}
+int smc_matrix_upload_rows(smc_matrix* m, int64_t row0, int64_t nrows,
+                           const void* host, int64_t ld_host) {
+  // `host` addresses element (row0, 0) of the host matrix; the device copy
+  // holds the block at rows [0, nrows) when the matrix is a shard, so row0
+  // here indexes the DEVICE matrix.
+  return copy_rows(m, row0, nrows, const_cast<void*>(host), ld_host, true);
+}
+int smc_matrix_download(const smc_matrix* m, void* host, int64_t ld_host) {
+  return copy_rows(const_cast<smc_matrix*>(m), 0, m ? m->rows : 0, host, ld_host,
+                   false);
+}
+int smc_matrix_download_rows(const smc_matrix* m, int64_t row0, int64_t nrows,
+                             void* host, int64_t ld_host) {
+  return copy_rows(const_cast<smc_matrix*>(m), row0, nrows, host, ld_host, false);
+}
+
+int smc_matrix_zero(smc_matrix* m) {
+  if (!m) return fail(SMC_ERR_INVALID_ARGUMENT, "NULL matrix");
+  if (int rc = ensure_ctx()) return rc;
+  if (m->rows == 0 || m->cols == 0) return SMC_OK;
+  m->lgamma_valid = false;
+  m->range_valid = false;
+  const size_t es = elem_size(m->dtype);
+  SMC_CUDA(cudaMemset2DAsync(m->data, (size_t)m->ld * es, 0, (size_t)m->rows * es,
+                             (size_t)m->cols, ctx().stream));
+  return SMC_OK;
+}
+
+int smc_matrix_axpy(smc_matrix* y, double a, const smc_matrix* x) {
+  if (!y || !x || y->rows != x->rows || y->cols != x->cols
+      || y->dtype != SMC_F64 || x->dtype != SMC_F64)
+    return fail(SMC_ERR_INVALID_ARGUMENT, "axpy: shape/dtype mismatch");
+  if (int rc = ensure_ctx()) return rc;
+  const int64_t total = y->rows * y->cols;
+  if (total == 0) return SMC_OK;
+  axpy_kernel<<<grid_for(total, 256), 256, 0, ctx().stream>>>(
+      static_cast<double*>(y->data), y->ld, static_cast<const double*>(x->data),
+      x->ld, y->rows, y->cols, a);
+  SMC_CUDA(cudaGetLastError());
+  return SMC_OK;
+}
+
+int smc_matrix_all_finite(const smc_matrix* m, int* all_finite) {
+  if (!m || !all_finite || m->dtype != SMC_F64)
+    return fail(SMC_ERR_INVALID_ARGUMENT, "all_finite: need an f64 matrix");
+  if (int rc = ensure_ctx()) return rc;
+  *all_finite = 1;
+  const int64_t total = m->rows * m->cols;
+  if (total == 0) return SMC_OK;
+  if (int rc = ensure_out(4096)) return rc;
+  int* flag = reinterpret_cast<int*>(ctx().out_host);
+  *flag = 0;
+  all_finite_kernel<<<grid_for(total, 256), 256, 0, ctx().stream>>>(
+      static_cast<const double*>(m->data), m->ld, m->rows, m->cols, flag);
+  SMC_CUDA(cudaGetLastError());
+  SMC_CUDA(cudaStreamSynchronize(ctx().stream));
+  *all_finite = (*flag == 0);
+  return SMC_OK;
+}
+
+int smc_matrix_int_range(const smc_matrix* m, int* min_out, int* max_out) {
+  if (!m || m->dtype != SMC_I32 || !min_out || !max_out)
+    return fail(SMC_ERR_INVALID_ARGUMENT, "int_range: need an i32 matrix");
+  return y_range(m, min_out, max_out);
+}
+
+int smc_matrix_fill_synthetic(smc_matrix* m, uint64_t seed, int64_t row0,
+                              int kind, double scale, int lo, int hi) {
+  if (!m || (kind != 0 && kind != 1) || (kind == 0 && m->dtype != SMC_F64)
+      || (kind == 1 && hi < lo))
+    return fail(SMC_ERR_INVALID_ARGUMENT, "fill_synthetic: bad arguments");
+  if (int rc = ensure_ctx()) return rc;
+  const int64_t total = m->rows * m->cols;
+  if (total == 0) return SMC_OK;
+  m->lgamma_valid = false;
+  m->range_valid = false;
+  const double c = scale / sqrt(4294967295.0 / 3.0);
+  fill_synth_kernel<<<grid_for(total, 256), 256, 0, ctx().stream>>>(
+      m->data, m->ld, m->rows, m->cols, m->dtype, seed, row0, kind, c, lo, hi);
+  SMC_CUDA(cudaGetLastError());
+  return SMC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,503 @@
+// Single-pass fused GLM kernel for sm_100a.
+//
+// One evaluation = ONE sweep over the column-major design matrix x (N x K):
+//   theta_i = sum_k x[i,k] beta[k]      (row reduction)
+//   link:   per-row log-density term and theta-derivative d_i
+//   d_beta[k] = sum_i x[i,k] d_i        (column reduction)   [+ d_x = beta (x) d]
+// fused so x is read from HBM exactly once (algorithmic bytes = N*K*8).
+//
+// Data path: a producer warp streams row tiles of x ({R rows} x {CW cols},
+// R = 32*G, CW = 32*S) into a 3-stage shared-memory ring with TMA
+// (cp.async.bulk.tensor.2d + mbarrier complete_tx).  Consumer warp (g, s) owns
+// row group g (32 rows, lane = row) and column slab s (32 columns): it pulls its
+// 32 x values from shared memory into registers ONCE, releases the stage,
+// forms its partial dot product, exchanges partials through shared memory,
+// evaluates the link, and accumulates d_beta for its 32 columns in registers.
+// Column-major tiles make every shared-memory access lane-contiguous
+// (conflict-free) and every global access coalesced.
+//
+// Reductions are deterministic: fixed static tile->CTA schedule, per-thread
+// sequential accumulation, xor-butterfly across lanes, fixed-order sum over row
+// groups, per-CTA partials in global memory, and a fixed-order final sum by the
+// last CTA to finish (ticket counter; order of summation does not depend on
+// arrival order).  No floating-point atomics anywhere.
+//
+// Reference semantics (value + partials): stan/math/prim/prob/
+//   normal_id_glm_lpdf.hpp L122-213, bernoulli_logit_glm_lpmf.hpp L105-164,
+//   poisson_log_glm_lpmf.hpp L107-161, neg_binomial_2_log_glm_lpmf.hpp L143-244,
+//   ordered_logistic_glm_lpmf.hpp L108-207.
+#include <cmath>
+#include <cstring>
+
+#include "glm_link.cuh"
+
+namespace smc {
+
+constexpr int kStages = 3;
+constexpr int kCutsPerThread = 4;
+
+// ------------------------------------------------------------------ PTX glue
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// TMA: 2-D tiled bulk tensor load global -> shared, completion on an mbarrier.
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map,
+                                            int c0, int c1, uint64_t* bar,
+                                            uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::"
+      "bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1),
+      "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void group_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void st_stream(double* p, double v) {
+  asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+// ------------------------------------------------------------------- the kernel
+template <int FAM>
+__global__ void __launch_bounds__(256, 1)
+    glm_fused_kernel(const __grid_constant__ CUtensorMap tmap,
+                     const __grid_constant__ FusedArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const int S = a.S, G = a.G;
+  const int R = 32 * G, CW = 32 * S;
+  const int n_cons_warps = S * G;
+  const uint32_t stage_bytes = (uint32_t)R * CW * 8u;
+
+  // shared-memory carve-up
+  double* tiles = reinterpret_cast<double*>(smem_raw);
+  unsigned char* p = smem_raw + (size_t)kStages * stage_bytes;
+  double* beta_s = reinterpret_cast<double*>(p);  // CW doubles
+  p += (size_t)CW * 8;
+  double* cuts_s = reinterpret_cast<double*>(p);  // ncuts (padded) doubles
+  p += (size_t)((a.ncuts + 1) & ~1) * 8;
+  double* partial_s = reinterpret_cast<double*>(p);  // [2][S][R]
+  p += (size_t)2 * S * R * 8;
+  double* d1_s = reinterpret_cast<double*>(p);  // [2][R] (ordered)
+  double* d2_s = d1_s + 2 * R;
+  int* yc_s = reinterpret_cast<int*>(d2_s + 2 * R);  // [2][R]
+  p += (size_t)(4 * R) * 8 + (size_t)2 * R * 4;
+  p = reinterpret_cast<unsigned char*>(((uintptr_t)p + 7) & ~(uintptr_t)7);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(p);
+  uint64_t* empty_bar = full_bar + kStages;
+  __shared__ int s_last;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+
+  // parameters -> shared memory
+  const double* params = a.params_dev ? a.params_dev : a.inline_params;
+  for (int j = tid; j < CW; j += blockDim.x) beta_s[j] = j < a.K ? params[j] : 0.0;
+  for (int j = tid; j < a.ncuts; j += blockDim.x) cuts_s[j] = params[a.K + j];
+  if (tid == 0) {
+    for (int st = 0; st < kStages; ++st) {
+      mbar_init(&full_bar[st], 1);
+      mbar_init(&empty_bar[st], n_cons_warps);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  // consumer identity: slab-major so the lead warps (s == 0) of different row
+  // groups sit on different SM sub-partitions
+  const int s = warp / G, g = warp - s * G;
+  const bool lead = s == 0;
+  double acc[kColsPerThread];
+#pragma unroll
+  for (int kk = 0; kk < kColsPerThread; ++kk) acc[kk] = 0.0;
+  double cacc[kCutsPerThread] = {0, 0, 0, 0};
+  RowAcc racc;
+  const bool need_beta = a.flags & SMC_VAR_BETA;
+  const bool need_dx = (a.flags & SMC_VAR_X) && a.d_x;
+  const bool need_cuts = FAM == kOrdered && (a.flags & SMC_VAR_AUX);
+
+  // Thread 0 doubles as the TMA producer (a ninth warp would put three warps
+  // on one SM sub-partition and cap every thread at 168 registers).  Prologue:
+  // fill the ring.
+  uint64_t pol = 0;
+  if (tid == 0) {
+    pol = policy_evict_first();
+    for (int j = 0; j < kStages; ++j) {
+      const int64_t tile = (int64_t)blockIdx.x + (int64_t)j * gridDim.x;
+      if (tile < a.ntiles) {
+        mbar_expect_tx(&full_bar[j], stage_bytes);
+        tma_load_2d(tiles + (size_t)j * (stage_bytes / 8), &tmap, (int)tile * R, 0,
+                    &full_bar[j], pol);
+      }
+    }
+  }
+  {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+      const int st = it % kStages;
+      const uint32_t ph = (uint32_t)(it / kStages) & 1u;
+      const int par = it & 1;
+      if (tid == 0 && it >= 1) {
+        // refill the stage tile it-1 occupied, once every warp has released it
+        const int64_t nt = (int64_t)tile + (int64_t)(kStages - 1) * gridDim.x;
+        if (nt < a.ntiles) {
+          const int rs = (it - 1) % kStages;
+          mbar_wait(&empty_bar[rs], (uint32_t)((it - 1) / kStages) & 1u);
+          mbar_expect_tx(&full_bar[rs], stage_bytes);
+          tma_load_2d(tiles + (size_t)rs * (stage_bytes / 8), &tmap, (int)nt * R, 0,
+                      &full_bar[rs], pol);
+        }
+      }
+      const int rloc = 32 * g + lane;
+      const int64_t row = (int64_t)tile * R + rloc;
+      const bool valid = row < a.N;
+
+      // per-row inputs: issue the global loads before blocking on the tile
+      RowIn<FAM> in;
+      if constexpr (FAM == kNormal)
+        in.y = (a.y && valid) ? static_cast<const double*>(a.y)[row] : a.y_scalar;
+      else
+        in.y = (a.y && valid) ? (double)static_cast<const int*>(a.y)[row]
+                              : a.y_scalar;
+      in.alpha = (a.alpha_vec && valid) ? a.alpha_vec[row] : a.alpha;
+      in.aux = (a.aux_vec && valid) ? a.aux_vec[row] : a.aux;
+
+      mbar_wait(&full_bar[st], ph);
+      const double* xs
+          = tiles + (size_t)st * (stage_bytes / 8) + (size_t)(32 * s) * R + rloc;
+      double xv[kColsPerThread];
+#pragma unroll
+      for (int kk = 0; kk < kColsPerThread; ++kk) xv[kk] = xs[kk * R];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[st]);  // stage is free again
+
+      const double* bs = beta_s + 32 * s;
+      double part = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < kColsPerThread; ++kk) part = fma(xv[kk], bs[kk], part);
+
+      double xb = part;
+      if (S > 1) {
+        partial_s[(par * S + s) * R + rloc] = part;
+        group_bar(1 + g, 32 * S);
+        xb = 0.0;
+        for (int ss = 0; ss < S; ++ss) xb += partial_s[(par * S + ss) * R + rloc];
+      }
+
+      double d1 = 0, d2 = 0;
+      const double d
+          = link_row<FAM>(a, xb, in, valid, lead, row, racc, cuts_s, d1, d2);
+
+      if (need_beta) {
+#pragma unroll
+        for (int kk = 0; kk < kColsPerThread; ++kk) acc[kk] = fma(xv[kk], d, acc[kk]);
+      }
+      if (need_dx && valid) {
+        double* dx = a.d_x + (size_t)(32 * s) * a.ld_dx + row;
+#pragma unroll
+        for (int kk = 0; kk < kColsPerThread; ++kk)
+          if (32 * s + kk < a.K) st_stream(dx + (size_t)kk * a.ld_dx, bs[kk] * d);
+      }
+      if constexpr (FAM == kOrdered) {
+        if (need_cuts) {
+          // ordered_logistic_glm_lpmf.hpp L197-207: scatter d2 / -d1 into the
+          // cut of each row's class -- done as an owner-computes loop so the
+          // order of additions is fixed.
+          if (lead) {
+            d1_s[par * R + rloc] = d1;
+            d2_s[par * R + rloc] = d2;
+            yc_s[par * R + rloc] = valid ? (int)in.y : 0;
+          }
+          if (S > 1)
+            group_bar(1 + g, 32 * S);
+          else
+            __syncwarp();
+          const int tg = s * 32 + lane;
+#pragma unroll
+          for (int j = 0; j < kCutsPerThread; ++j) {
+            const int c = tg + j * 32 * S;
+            if (c < a.ncuts) {
+              double v = cacc[j];
+              for (int r = 0; r < 32; ++r) {
+                const int yy = yc_s[par * R + 32 * g + r];
+                if (yy - 1 == c) v += d2_s[par * R + 32 * g + r];
+                if (yy - 2 == c) v -= d1_s[par * R + 32 * g + r];
+              }
+              cacc[j] = v;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ------------------------------------------------ CTA-level reduction
+  __syncthreads();  // every tile consumed; the ring is reusable as scratch
+  double* red = tiles;  // [G][pstride]
+  const int ps = a.pstride;
+  for (int j = tid; j < G * ps; j += blockDim.x) red[j] = 0.0;
+  __syncthreads();
+  {
+#pragma unroll
+    for (int kk = 0; kk < kColsPerThread; ++kk) {
+      const double v = warp_sum(acc[kk]);
+      if (lane == kk) red[g * ps + kHdr + 32 * s + kk] = v;
+    }
+    if (lead) {
+      const double v0 = warp_sum(racc.lp), v1 = warp_sum(racc.sd),
+                   v2 = warp_sum(racc.s2), v3 = warp_sum(racc.s3),
+                   vb = warp_sum((double)racc.bad);
+      if (lane == 0) {
+        red[g * ps + SMC_OUT_LOGP] = v0;
+        red[g * ps + SMC_OUT_SUM_D] = v1;
+        red[g * ps + SMC_OUT_AUX] = v2;
+        red[g * ps + SMC_OUT_NONFINITE] = vb;
+        red[g * ps + SMC_OUT_AUX2] = v3;
+      }
+    }
+    if (need_cuts) {
+      const int tg = s * 32 + lane;
+#pragma unroll
+      for (int j = 0; j < kCutsPerThread; ++j) {
+        const int c = tg + j * 32 * S;
+        if (c < a.ncuts) red[g * ps + kHdr + CW + c] = cacc[j];
+      }
+    }
+  }
+  __syncthreads();
+  double* my_partial = a.partials + (size_t)blockIdx.x * ps;
+  for (int j = tid; j < ps; j += blockDim.x) {
+    double v = 0.0;
+    for (int gg = 0; gg < G; ++gg) v += red[gg * ps + j];
+    my_partial[j] = v;
+  }
+
+  // ------------------------------------------------ grid-level reduction
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int ticket = atomicAdd(a.counter, 1u);
+    s_last = ticket == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    const int nb = gridDim.x;
+    for (int j = tid; j < ps; j += blockDim.x) {
+      // fixed order over CTAs, four interleaved chains to shorten the
+      // dependency (still a fixed association)
+      double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+      int b = 0;
+      for (; b + 3 < nb; b += 4) {
+        v0 += __ldcg(a.partials + (size_t)(b + 0) * ps + j);
+        v1 += __ldcg(a.partials + (size_t)(b + 1) * ps + j);
+        v2 += __ldcg(a.partials + (size_t)(b + 2) * ps + j);
+        v3 += __ldcg(a.partials + (size_t)(b + 3) * ps + j);
+      }
+      for (; b < nb; ++b) v0 += __ldcg(a.partials + (size_t)b * ps + j);
+      double v = (v0 + v1) + (v2 + v3);
+      if (j == SMC_OUT_LOGP) v += a.c0;
+      // packed output: header, d_beta[K], d_cuts[ncuts]
+      if (j < kHdr)
+        a.out[j] = v;
+      else if (j < kHdr + CW) {
+        if (j - kHdr < a.K) a.out[j] = v;
+      } else if (j - kHdr - CW < a.ncuts)
+        a.out[kHdr + a.K + (j - kHdr - CW)] = v;
+    }
+    if (tid == 0) *a.counter = 0;  // ready for the next launch on this stream
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
+                                  void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault,
+                                &q)
+            == cudaSuccess
+        && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static void tile_shape(int64_t K, int* S, int* G) {
+  int s = (int)((K + kColsPerThread - 1) / kColsPerThread);
+  if (s < 1) s = 1;
+  int g = 1;
+  while (g * 2 * s <= 8) g *= 2;
+  *S = s;
+  *G = g;
+}
+
+bool fused_supported(const smc_matrix* x) {
+  if (!x || x->dtype != SMC_F64) return false;
+  if (x->cols < 1 || x->cols > kMaxFusedK) return false;
+  if (x->rows < 1 || x->rows > 0x7fffff00ll) return false;
+  if ((reinterpret_cast<uintptr_t>(x->data) & 15) != 0) return false;
+  if (x->cols > 1 && (x->ld & 1)) return false;  // TMA: 16-byte global strides
+  return get_encode() != nullptr;
+}
+
+static int get_tmap(const smc_matrix* xc, int R, int CW, CUtensorMap* out) {
+  smc_matrix* x = const_cast<smc_matrix*>(xc);
+  if (x->tmap_rows == R && x->tmap_cols == CW) {
+    *out = x->tmap;
+    return SMC_OK;
+  }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(SMC_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t gdim[2] = {(cuuint64_t)x->rows, (cuuint64_t)x->cols};
+  cuuint64_t gstr[1] = {(cuuint64_t)x->ld * 8};
+  if (x->cols == 1) gstr[0] = (cuuint64_t)((x->rows + 1) & ~1ll) * 8;
+  cuuint32_t box[2] = {(cuuint32_t)R, (cuuint32_t)CW};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(&x->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, x->data, gdim,
+                   gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(SMC_ERR_CUDA,
+                "cuTensorMapEncodeTiled failed (%d) for %lld x %lld ld %lld box "
+                "%d x %d",
+                (int)r, (long long)x->rows, (long long)x->cols, (long long)x->ld,
+                R, CW);
+  x->tmap_rows = R;
+  x->tmap_cols = CW;
+  *out = x->tmap;
+  return SMC_OK;
+}
+
+template <int FAM>
+static int launch_t(const CUtensorMap& tmap, const FusedArgs& a, int grid,
+                    int threads, size_t smem) {
+  static size_t attr_smem[16] = {};
+  Context& c = ctx();
+  if (attr_smem[c.device & 15] < smem) {
+    SMC_CUDA(cudaFuncSetAttribute(glm_fused_kernel<FAM>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    attr_smem[c.device & 15] = smem;
+  }
+  glm_fused_kernel<FAM><<<grid, threads, smem, c.stream>>>(tmap, a);
+  SMC_CUDA(cudaGetLastError());
+  c.launches += 1;
+  return SMC_OK;
+}
+
+int launch_glm_fused(const GlmCall& c) {
+  Context& cx = ctx();
+  const smc_matrix* x = c.x;
+  FusedArgs a;
+  if (int rc = prepare_args(c, &a)) return rc;
+  tile_shape(a.K, &a.S, &a.G);
+  const int R = 32 * a.G, CW = 32 * a.S;
+  a.ntiles = (int)((a.N + R - 1) / R);
+  if (a.ncuts > kCutsPerThread * 32 * a.S || a.ncuts > kMaxCuts)
+    return fail(SMC_ERR_UNSUPPORTED, "too many cut points for the fused kernel");
+
+  // parameters: by value when they fit, else staged through device memory
+  const int nparam = a.K + a.ncuts;
+  if (c.params_dev) {
+    a.params_dev = c.params_dev;
+  } else if (nparam <= kMaxParamDoubles) {
+    memcpy(a.inline_params, c.beta_host, sizeof(double) * a.K);
+    if (a.ncuts) memcpy(a.inline_params + a.K, c.cuts_host, sizeof(double) * a.ncuts);
+  } else {
+    if (int rc = ensure_params(sizeof(double) * nparam)) return rc;
+    // pageable source: the copy is staged by the driver before returning
+    SMC_CUDA(cudaMemcpyAsync(cx.params_dev, c.beta_host, sizeof(double) * a.K,
+                             cudaMemcpyHostToDevice, cx.stream));
+    if (a.ncuts)
+      SMC_CUDA(cudaMemcpyAsync(cx.params_dev + a.K, c.cuts_host,
+                               sizeof(double) * a.ncuts, cudaMemcpyHostToDevice,
+                               cx.stream));
+    a.params_dev = cx.params_dev;
+  }
+
+  a.pstride = kHdr + CW + ((a.ncuts + 3) & ~3);
+  int grid = cx.sm_count;
+  if (grid > a.ntiles) grid = a.ntiles;
+  if (int rc = ensure_partials(sizeof(double) * (size_t)grid * a.pstride)) return rc;
+  a.partials = cx.partials;
+  a.counter = cx.counter;
+  a.out = c.out;
+
+  CUtensorMap tmap;
+  if (int rc = get_tmap(x, R, CW, &tmap)) return rc;
+
+  const size_t stage_bytes = (size_t)R * CW * 8;
+  size_t smem = kStages * stage_bytes + (size_t)CW * 8
+                + (size_t)((a.ncuts + 1) & ~1) * 8 + (size_t)2 * a.S * R * 8
+                + (size_t)4 * R * 8 + (size_t)2 * R * 4 + 8 + 2 * kStages * 8;
+  const size_t red_bytes = (size_t)a.G * a.pstride * 8;
+  if (red_bytes > kStages * stage_bytes)
+    return fail(SMC_ERR_UNSUPPORTED, "reduction scratch exceeds the tile ring");
+  const int threads = 32 * a.S * a.G;
+
+  switch (c.family) {
+    case kNormal:
+      return launch_t<kNormal>(tmap, a, grid, threads, smem);
+    case kBernoulli:
+      return launch_t<kBernoulli>(tmap, a, grid, threads, smem);
+    case kPoisson:
+      return launch_t<kPoisson>(tmap, a, grid, threads, smem);
+    case kNegBinomial:
+      return launch_t<kNegBinomial>(tmap, a, grid, threads, smem);
+    case kOrdered:
+      return launch_t<kOrdered>(tmap, a, grid, threads, smem);
+  }
+  return fail(SMC_ERR_INVALID_ARGUMENT, "unknown family %d", c.family);
+}
+
+}  // namespace smc

@@ -1,0 +1,265 @@
+// General two-pass path for the memory-bound GLM families: any K (including 0
+// and K > 256), any leading dimension / alignment.  It reads x twice (row pass
+// for theta + link, column pass for x^T d), so it runs at half the roofline of
+// the fused kernel; launch_glm() only selects it when the fused single-pass
+// kernel cannot take the matrix.  Same link code (glm_link.cuh), same packed
+// output, same deterministic fixed-order reductions.
+#include <cmath>
+#include <cstring>
+
+#include "glm_link.cuh"
+
+namespace smc {
+
+constexpr int kGenThreads = 256;
+
+int prepare_args(const GlmCall& c, FusedArgs* ap) {
+  FusedArgs& a = *ap;
+  memset(&a, 0, sizeof(a));
+  const smc_matrix* x = c.x;
+  a.N = x->rows;
+  a.K = (int)x->cols;
+  a.x = static_cast<const double*>(x->data);
+  a.ldx = x->ld;
+  a.flags = c.flags;
+  a.ncuts = (int)c.ncuts;
+  a.y = c.y ? c.y->data : nullptr;
+  a.y_scalar = c.y_scalar;
+  a.alpha_vec = c.alpha_vec ? static_cast<const double*>(c.alpha_vec->data) : nullptr;
+  a.alpha = c.alpha;
+  a.aux_vec = c.aux_vec ? static_cast<const double*>(c.aux_vec->data) : nullptr;
+  a.aux = c.aux;
+  a.d_alpha_vec = c.d_alpha_vec ? static_cast<double*>(c.d_alpha_vec->data) : nullptr;
+  a.d_aux_vec = c.d_aux_vec ? static_cast<double*>(c.d_aux_vec->data) : nullptr;
+  a.d_y_vec = c.d_y_vec ? static_cast<double*>(c.d_y_vec->data) : nullptr;
+  a.d_x = c.d_x ? static_cast<double*>(c.d_x->data) : nullptr;
+  a.ld_dx = c.d_x ? c.d_x->ld : 0;
+  a.out = c.out;
+
+  // row-independent terms of the log density, evaluated once on the host
+  const double Nd = (double)a.N;
+  const bool propto = c.flags & SMC_PROPTO;
+  a.c0 = 0.0;
+  switch (c.family) {
+    case kNormal:
+      // normal_id_glm_lpdf.hpp L201-212
+      if (!propto) a.c0 += -0.91893853320467274178032973640561764 * Nd;
+      if (!c.aux_vec && (!propto || (c.flags & SMC_VAR_AUX)))
+        a.c0 -= Nd * std::log(c.aux);
+      break;
+    case kPoisson:
+    case kNegBinomial: {
+      // -sum lgamma(y + 1): poisson L126-128, neg-binomial L163-169
+      if (!propto) {
+        double lg = 0.0;
+        if (c.y) {
+          if (int rc = y_lgamma_sum(c.y, &lg)) return rc;
+        } else {
+          lg = Nd * std::lgamma(c.y_scalar + 1.0);
+        }
+        a.c0 -= lg;
+      }
+      if (c.family == kNegBinomial && !c.aux_vec) {
+        a.log_aux = std::log(c.aux);
+        a.digamma_aux = digamma(c.aux);
+        // N (phi log phi - lgamma phi), L177-182 (multiply_log(0,0) = 0)
+        if (!propto || (c.flags & SMC_VAR_AUX)) {
+          const double ml = (c.aux == 0.0) ? 0.0 : c.aux * std::log(c.aux);
+          a.c0 += Nd * (ml - std::lgamma(c.aux));
+        }
+      }
+      break;
+    }
+    default:
+      break;
+  }
+  return SMC_OK;
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  // fixed-order block reduction: butterfly inside the warp, then warp 0 adds
+  // the warp totals in index order
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < kGenThreads / 32; ++w) t += sh[w];
+  return t;
+}
+
+template <int FAM>
+__global__ void __launch_bounds__(kGenThreads)
+    generic_rows_kernel(const __grid_constant__ FusedArgs a,
+                        const double* __restrict__ params, double* __restrict__ dvec,
+                        double* __restrict__ d1v, double* __restrict__ d2v,
+                        double* __restrict__ block_partials) {
+  __shared__ double sh[kGenThreads / 32];
+  RowAcc racc;
+  const double* cuts = params + a.K;
+  for (int64_t row = blockIdx.x * (int64_t)kGenThreads + threadIdx.x; row < a.N;
+       row += (int64_t)gridDim.x * kGenThreads) {
+    double xb = 0.0;
+    const double* xr = a.x + row;
+    for (int k = 0; k < a.K; ++k) xb = fma(xr[(size_t)k * a.ldx], __ldg(params + k), xb);
+    RowIn<FAM> in;
+    if constexpr (FAM == kNormal)
+      in.y = a.y ? static_cast<const double*>(a.y)[row] : a.y_scalar;
+    else
+      in.y = a.y ? (double)static_cast<const int*>(a.y)[row] : a.y_scalar;
+    in.alpha = a.alpha_vec ? a.alpha_vec[row] : a.alpha;
+    in.aux = a.aux_vec ? a.aux_vec[row] : a.aux;
+    double d1 = 0, d2 = 0;
+    const double d = link_row<FAM>(a, xb, in, true, true, row, racc, cuts, d1, d2);
+    dvec[row] = d;
+    if constexpr (FAM == kOrdered) {
+      d1v[row] = d1;
+      d2v[row] = d2;
+    }
+  }
+  const double v0 = block_sum(racc.lp, sh), v1 = block_sum(racc.sd, sh),
+               v2 = block_sum(racc.s2, sh), v3 = block_sum(racc.s3, sh),
+               vb = block_sum((double)racc.bad, sh);
+  if (threadIdx.x == 0) {
+    double* bp = block_partials + (size_t)blockIdx.x * kHdr;
+    bp[SMC_OUT_LOGP] = v0;
+    bp[SMC_OUT_SUM_D] = v1;
+    bp[SMC_OUT_AUX] = v2;
+    bp[SMC_OUT_NONFINITE] = vb;
+    bp[SMC_OUT_AUX2] = v3;
+    bp[5] = bp[6] = bp[7] = 0.0;
+  }
+}
+
+// One CTA per column k: d_beta[k] = sum_i x[i,k] d[i]; optionally d_x[:,k].
+__global__ void __launch_bounds__(kGenThreads)
+    generic_cols_kernel(const __grid_constant__ FusedArgs a,
+                        const double* __restrict__ params,
+                        const double* __restrict__ dvec) {
+  __shared__ double sh[kGenThreads / 32];
+  const int k = blockIdx.x;
+  const double* col = a.x + (size_t)k * a.ldx;
+  const bool need_dx = (a.flags & SMC_VAR_X) && a.d_x;
+  const double bk = params[k];
+  double v = 0.0;
+  for (int64_t i = threadIdx.x; i < a.N; i += kGenThreads) {
+    const double di = dvec[i];
+    v = fma(col[i], di, v);
+    if (need_dx) a.d_x[(size_t)k * a.ld_dx + i] = bk * di;
+  }
+  v = block_sum(v, sh);
+  if (threadIdx.x == 0) a.out[kHdr + k] = v;
+}
+
+// One CTA per cut point c (ordered_logistic_glm_lpmf.hpp L197-207).
+__global__ void __launch_bounds__(kGenThreads)
+    generic_cuts_kernel(const __grid_constant__ FusedArgs a,
+                        const double* __restrict__ d1v,
+                        const double* __restrict__ d2v) {
+  __shared__ double sh[kGenThreads / 32];
+  const int c = blockIdx.x;
+  double v = 0.0;
+  for (int64_t i = threadIdx.x; i < a.N; i += kGenThreads) {
+    const int yy = a.y ? static_cast<const int*>(a.y)[i] : (int)a.y_scalar;
+    if (yy - 1 == c) v += d2v[i];
+    if (yy - 2 == c) v -= d1v[i];
+  }
+  v = block_sum(v, sh);
+  if (threadIdx.x == 0) a.out[kHdr + a.K + c] = v;
+}
+
+__global__ void generic_finalize_kernel(const double* __restrict__ block_partials,
+                                        int nblocks, double c0,
+                                        double* __restrict__ out) {
+  const int j = threadIdx.x;
+  if (j >= kHdr) return;
+  double v = 0.0;
+  for (int b = 0; b < nblocks; ++b) v += block_partials[(size_t)b * kHdr + j];
+  if (j == SMC_OUT_LOGP) v += c0;
+  out[j] = v;
+}
+
+template <int FAM>
+static int run_rows(const FusedArgs& a, const double* params, double* dvec,
+                    double* d1v, double* d2v, double* bp, int grid) {
+  generic_rows_kernel<FAM><<<grid, kGenThreads, 0, ctx().stream>>>(a, params, dvec,
+                                                                  d1v, d2v, bp);
+  SMC_CUDA(cudaGetLastError());
+  return SMC_OK;
+}
+
+int launch_glm_generic(const GlmCall& c) {
+  Context& cx = ctx();
+  FusedArgs a;
+  if (int rc = prepare_args(c, &a)) return rc;
+  const int nparam = a.K + a.ncuts;
+  const double* params = c.params_dev;
+  if (!params) {
+    if (int rc = ensure_params(sizeof(double) * (nparam > 0 ? nparam : 1))) return rc;
+    if (a.K)
+      SMC_CUDA(cudaMemcpyAsync(cx.params_dev, c.beta_host, sizeof(double) * a.K,
+                               cudaMemcpyHostToDevice, cx.stream));
+    if (a.ncuts)
+      SMC_CUDA(cudaMemcpyAsync(cx.params_dev + a.K, c.cuts_host,
+                               sizeof(double) * a.ncuts, cudaMemcpyHostToDevice,
+                               cx.stream));
+    params = cx.params_dev;
+  }
+  int grid = (int)((a.N + kGenThreads - 1) / kGenThreads);
+  if (grid > cx.sm_count * 4) grid = cx.sm_count * 4;
+  if (grid < 1) grid = 1;
+  const size_t nvec = c.family == kOrdered ? 3 : 1;
+  const size_t bytes = sizeof(double) * ((size_t)a.N * nvec + (size_t)grid * kHdr);
+  if (int rc = ensure_scratch(bytes)) return rc;
+  double* dvec = cx.scratch;
+  double* d1v = dvec + (nvec == 3 ? a.N : 0);
+  double* d2v = dvec + (nvec == 3 ? 2 * a.N : 0);
+  double* bp = dvec + (size_t)a.N * nvec;
+  int rc = SMC_OK;
+  switch (c.family) {
+    case kNormal:
+      rc = run_rows<kNormal>(a, params, dvec, d1v, d2v, bp, grid);
+      break;
+    case kBernoulli:
+      rc = run_rows<kBernoulli>(a, params, dvec, d1v, d2v, bp, grid);
+      break;
+    case kPoisson:
+      rc = run_rows<kPoisson>(a, params, dvec, d1v, d2v, bp, grid);
+      break;
+    case kNegBinomial:
+      rc = run_rows<kNegBinomial>(a, params, dvec, d1v, d2v, bp, grid);
+      break;
+    case kOrdered:
+      rc = run_rows<kOrdered>(a, params, dvec, d1v, d2v, bp, grid);
+      break;
+    default:
+      return fail(SMC_ERR_INVALID_ARGUMENT, "unknown family %d", c.family);
+  }
+  if (rc) return rc;
+  cx.launches += 1;
+  if (a.K > 0 && (a.flags & (SMC_VAR_BETA | SMC_VAR_X))) {
+    generic_cols_kernel<<<a.K, kGenThreads, 0, cx.stream>>>(a, params, dvec);
+    SMC_CUDA(cudaGetLastError());
+    cx.launches += 1;
+  }
+  if (c.family == kOrdered && a.ncuts > 0 && (a.flags & SMC_VAR_AUX)) {
+    generic_cuts_kernel<<<a.ncuts, kGenThreads, 0, cx.stream>>>(a, d1v, d2v);
+    SMC_CUDA(cudaGetLastError());
+    cx.launches += 1;
+  }
+  generic_finalize_kernel<<<1, 32, 0, cx.stream>>>(bp, grid, a.c0, a.out);
+  SMC_CUDA(cudaGetLastError());
+  cx.launches += 1;
+  return SMC_OK;
+}
+
+int launch_glm(const GlmCall& c) {
+  const char* force = getenv("SMC_FORCE_GENERIC");
+  if (fused_supported(c.x) && !(force && force[0] == '1')
+      && c.ncuts <= 4 * 32 * ((c.x->cols + 31) / 32))
+    return launch_glm_fused(c);
+  return launch_glm_generic(c);
+}
+
+}  // namespace smc

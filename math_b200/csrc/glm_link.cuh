@@ -1,0 +1,177 @@
+// Link functions of the five memory-bound GLM families, shared by the fused
+// single-pass kernel (glm_fused.cu) and the general two-pass path
+// (glm_generic.cu).  Each follows the reference's branches line by line:
+//   normal_id_glm_lpdf.hpp L122-213, bernoulli_logit_glm_lpmf.hpp L105-164,
+//   poisson_log_glm_lpmf.hpp L107-161, neg_binomial_2_log_glm_lpmf.hpp L143-244,
+//   ordered_logistic_glm_lpmf.hpp L108-207.
+#pragma once
+#include "device_math.cuh"
+#include "smc_internal.h"
+
+namespace smc {
+
+constexpr int kHdr = SMC_OUT_HEADER;
+
+struct FusedArgs {
+  int64_t N;
+  int K, S, G, ntiles;
+  const double* x;  // general path only (the fused kernel goes through TMA)
+  int64_t ldx;
+  unsigned flags;
+  int ncuts;
+  const void* y;
+  double y_scalar;
+  const double* alpha_vec;
+  double alpha;
+  const double* aux_vec;
+  double aux, log_aux, digamma_aux;
+  const double* params_dev;  // beta[K] then cuts[ncuts]; NULL -> inline_params
+  double* d_alpha_vec;
+  double* d_aux_vec;
+  double* d_y_vec;
+  double* d_x;
+  int64_t ld_dx;
+  double* partials;
+  int pstride;
+  unsigned int* counter;
+  double* out;
+  double c0;
+  double inline_params[kMaxParamDoubles];
+};
+
+// Fills everything in `a` that does not depend on the kernel variant: shapes,
+// pointers, flags, host-side constants of the log density (c0, log phi, ...).
+int prepare_args(const GlmCall& c, FusedArgs* a);
+
+// --------------------------------------------------------------- link functions
+// Per-row result of a link: theta-derivative d, log-density term lp, two aux
+// sums and the non-finite flag.  `lead` marks the one warp per row group that
+// owns the scalar sums and the N-vector outputs.
+struct RowAcc {
+  double lp = 0, sd = 0, s2 = 0, s3 = 0;
+  int bad = 0;
+};
+
+template <int FAM>
+struct RowIn {
+  double y;      // response (int families: exact small integer in a double)
+  double alpha;  // intercept for this row
+  double aux;    // sigma / phi for this row
+};
+
+template <int FAM>
+__device__ __forceinline__ double link_row(const FusedArgs& a, double xb,
+                                           const RowIn<FAM>& in, bool valid,
+                                           bool lead, int64_t row, RowAcc& acc,
+                                           const double* cuts_s, double& d1o,
+                                           double& d2o) {
+  double d = 0, lp = 0, s2 = 0, s3 = 0;
+  int bad = 0;
+  if constexpr (FAM == kBernoulli) {
+    const double sgn = 2.0 * in.y - 1.0;
+    const double t = sgn * (xb + in.alpha);
+    const double e = exp(-t);
+    // bernoulli_logit_glm_lpmf.hpp L120-126 / L137-142 (the t > 20 derivative
+    // branch is -e whatever the sign: reproduced for parity)
+    lp = t > 20.0 ? -e : (t < -20.0 ? t : -log1p(e));
+    d = t > 20.0 ? -e : (t < -20.0 ? sgn : sgn * e / (e + 1.0));
+    bad = !isfinite(t);
+    if (lead && valid && a.d_alpha_vec) a.d_alpha_vec[row] = d;
+  } else if constexpr (FAM == kPoisson) {
+    const double th = xb + in.alpha;
+    const double e = exp(th);
+    d = in.y - e;          // poisson_log_glm_lpmf.hpp L117-118
+    lp = in.y * th - e;    // L130-131
+    bad = !isfinite(th);
+    if (lead && valid && a.d_alpha_vec) a.d_alpha_vec[row] = d;
+  } else if constexpr (FAM == kNormal) {
+    const double inv = 1.0 / in.aux;
+    const double r = (in.y - xb - in.alpha) * inv;  // normal_id_glm_lpdf.hpp L130-133
+    d = inv * r;                                    // mu_derivative L140
+    const double r2 = r * r;
+    lp = -0.5 * r2;
+    if (a.aux_vec && (!(a.flags & SMC_PROPTO) || (a.flags & SMC_VAR_AUX)))
+      lp -= log(in.aux);  // L204-206
+    s3 = r2;
+    // check_positive_finite(sigma) L93 for a vector sigma is folded into the sweep
+    if (a.aux_vec) bad = !(in.aux > 0.0) || !isfinite(in.aux);
+    if (lead && valid) {
+      if (a.d_alpha_vec) a.d_alpha_vec[row] = d;
+      if (a.d_y_vec) a.d_y_vec[row] = -d;
+      if (a.d_aux_vec) a.d_aux_vec[row] = (r2 - 1.0) * inv;  // L177-178
+    }
+  } else if constexpr (FAM == kNegBinomial) {
+    const double th = xb + in.alpha;
+    const double ph = in.aux;
+    // check_finite(theta) L152; check_positive_finite(phi) L130 for vector phi
+    bad = !isfinite(th) || (a.aux_vec && (!(ph > 0.0) || !isfinite(ph)));
+    const double log_phi = a.aux_vec ? log(ph) : a.log_aux;
+    // neg_binomial_2_log_glm_lpmf.hpp L154-157
+    const double lse = th > log_phi ? th + log1p_exp(log_phi - th)
+                                    : log_phi + log1p_exp(th - log_phi);
+    const double ypp = in.y + ph;
+    const bool propto = a.flags & SMC_PROPTO;
+    const bool inc_phi = !propto || (a.flags & SMC_VAR_AUX);
+    const bool inc_lin
+        = !propto || (a.flags & (SMC_VAR_X | SMC_VAR_ALPHA | SMC_VAR_BETA));
+    lp = -ypp * lse;              // L184
+    if (inc_lin) lp += in.y * th;  // L186-188
+    const double te = exp(th);
+    d = in.y - te * ypp / (te + ph);  // L203-204
+    if (lead && valid) {
+      if (inc_phi) {
+        lp += lgamma(ypp);  // L189-195
+        if (a.aux_vec) lp += multiply_log(ph, ph) - lgamma(ph);  // L171-176
+      }
+      if (!propto && a.y == nullptr) {
+        // scalar y broadcast: host adds N * lgamma(y+1); nothing here
+      }
+      if (a.flags & SMC_VAR_AUX) {
+        const double dg_phi = a.aux_vec ? digamma(ph) : a.digamma_aux;
+        const double dp = 1.0 - ypp / (te + ph) + log_phi - lse + digamma(ypp)
+                          - dg_phi;  // L235-244
+        if (a.d_aux_vec)
+          a.d_aux_vec[row] = dp;
+        else
+          s2 = dp;
+      }
+      if (a.d_alpha_vec) a.d_alpha_vec[row] = d;
+    }
+  } else if constexpr (FAM == kOrdered) {
+    const int C = a.ncuts + 1;
+    const int c = valid ? (int)in.y : 1;
+    // ordered_logistic_glm_lpmf.hpp L108-121
+    const double c1 = c != C ? cuts_s[c - 1] : __longlong_as_double(0x7ff0000000000000ll);
+    const double c2 = c != 1 ? cuts_s[c - 2] : __longlong_as_double(0xfff0000000000000ll);
+    const double cut2 = xb - c2, cut1 = xb - c1;  // L129-132
+    const double A = (cut1 > 0.0 ? -cut1 : 0.0) - log1p(exp(-fabs(cut1)));
+    const double B = (cut2 <= 0.0 ? cut2 : 0.0) - log1p(exp(-fabs(cut2)));
+    if (c == 1)
+      lp = A;
+    else if (c == C)
+      lp = B;
+    else
+      lp = B + log1m_exp(cut1 - cut2) + A;  // L141-161
+    const double em1 = exp(-cut1), em2 = exp(-cut2), ed = exp(c2 - c1);
+    const double d1 = (cut2 > 0.0 ? em2 / (1.0 + em2) : 1.0 / (1.0 + exp(cut2)))
+                      - ed / (ed - 1.0);  // L168-170
+    const double d2 = 1.0 / (1.0 - ed)
+                      - (cut1 > 0.0 ? em1 / (1.0 + em1)
+                                    : 1.0 / (1.0 + exp(cut1)));  // L171-174
+    d = d1 - d2;
+    d1o = d1;
+    d2o = d2;
+    s3 = xb;  // sum(location) for the lazy finiteness check, L124
+  }
+  if (!valid) return 0.0;
+  if (lead) {
+    acc.lp += lp;
+    acc.sd += d;
+    acc.s2 += s2;
+    acc.s3 += s3;
+    acc.bad += bad;
+  }
+  return d;
+}
+
+}  // namespace smc

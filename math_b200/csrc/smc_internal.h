@@ -1,0 +1,123 @@
+// Internal declarations shared by the translation units of libstanmath_cuda.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/stanmath_cuda.h"
+
+namespace smc {
+
+constexpr int kMaxFusedK = 256;   // columns one fused CTA tile can hold
+constexpr int kColsPerThread = 32;
+constexpr int kMaxParamDoubles = 256;  // by-value parameter block (beta)
+constexpr int kMaxCuts = 512;
+
+enum Family {
+  kNormal = 0,
+  kBernoulli = 1,
+  kPoisson = 2,
+  kNegBinomial = 3,
+  kOrdered = 4
+};
+
+// Per-host-thread state: device, stream, reusable workspace.
+struct Context {
+  int device = -1;
+  bool inited = false;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;  // own_stream or the user's
+  int sm_count = 0;
+  // workspace
+  double* partials = nullptr;  // [grid][stride] per-CTA partial sums
+  size_t partials_bytes = 0;
+  unsigned int* counter = nullptr;  // last-block-done ticket (zero between launches)
+  double* params_dev = nullptr;     // small device parameter staging
+  size_t params_bytes = 0;
+  double* out_host = nullptr;  // pinned + mapped result buffer
+  size_t out_bytes = 0;
+  double* scratch = nullptr;   // generic device scratch (N-vectors for fallbacks)
+  size_t scratch_bytes = 0;
+  int64_t launches = 0;
+  std::string last_error;
+  ~Context();
+};
+
+Context& ctx();
+int ensure_ctx();  // lazily binds device 0 / creates the stream; returns smc_status
+int fail(int status, const char* fmt, ...);
+int ensure_partials(size_t bytes);
+int ensure_params(size_t bytes);
+int ensure_out(size_t bytes);
+int ensure_scratch(size_t bytes);
+
+#define SMC_CUDA(expr)                                                        \
+  do {                                                                        \
+    cudaError_t e__ = (expr);                                                 \
+    if (e__ != cudaSuccess)                                                   \
+      return ::smc::fail(SMC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,        \
+                         cudaGetErrorString(e__), __FILE__, __LINE__);        \
+  } while (0)
+
+// Arguments of one evaluation of a memory-bound GLM family; filled by the C API.
+struct GlmCall {
+  int family = 0;
+  const smc_matrix* x = nullptr;
+  const smc_matrix* y = nullptr;
+  double y_scalar = 0;
+  const smc_matrix* alpha_vec = nullptr;
+  double alpha = 0;
+  const smc_matrix* aux_vec = nullptr;  // sigma / phi vector
+  double aux = 0;                       // sigma / phi scalar
+  const double* beta_host = nullptr;    // K (by-value path)
+  const double* cuts_host = nullptr;    // ncuts
+  const double* params_dev = nullptr;   // beta[K] (+cuts) already on device
+  int64_t ncuts = 0;
+  unsigned flags = 0;
+  double* out = nullptr;  // packed result, device-accessible
+  smc_matrix* d_alpha_vec = nullptr;
+  smc_matrix* d_aux_vec = nullptr;
+  smc_matrix* d_y_vec = nullptr;
+  smc_matrix* d_x = nullptr;
+};
+
+// Launches the evaluation on ctx().stream; does not synchronise.
+int launch_glm(const GlmCall& c);
+// True when the single-pass TMA kernel can take this x.
+bool fused_supported(const smc_matrix* x);
+int launch_glm_fused(const GlmCall& c);
+int launch_glm_generic(const GlmCall& c);
+
+// sum_i lgamma(y_i + 1) over an i32 device vector (cached on the matrix).
+int y_lgamma_sum(const smc_matrix* y, double* sum);
+// min / max of an i32 device vector (cached on the matrix).
+int y_range(const smc_matrix* y, int* lo, int* hi);
+
+int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
+                       const double* alpha_host, const double* beta_host,
+                       int64_t C, unsigned flags, double* out_host_logp,
+                       double* d_alpha, double* d_beta, smc_matrix* d_x);
+
+}  // namespace smc
+
+struct smc_matrix {
+  void* data = nullptr;
+  int64_t rows = 0, cols = 0, ld = 0;
+  int dtype = SMC_F64;
+  bool owned = false;
+  int device = 0;
+  // cached TMA descriptor for the fused kernel (depends on the tile shape)
+  CUtensorMap tmap;
+  int tmap_rows = 0, tmap_cols = 0;
+  // cached sum_i lgamma(y_i + 1) for integer data vectors (y is data: the
+  // value only changes on upload)
+  bool lgamma_valid = false;
+  double lgamma_sum = 0;
+  // cached min / max of an integer data vector (eager y-range checks)
+  bool range_valid = false;
+  int imin = 0, imax = 0;
+};

@@ -1,0 +1,41 @@
+"""Thin runtime helpers over the C ABI: device selection, stream binding, sync."""
+import ctypes as C
+
+from ._lib import check, lib
+
+
+def device_count():
+    n = C.c_int()
+    check(lib().smc_device_count(C.byref(n)))
+    return n.value
+
+
+def set_device(i):
+    check(lib().smc_set_device(int(i)))
+
+
+def set_stream(cuda_stream_ptr):
+    """Bind this thread's launches to an existing cudaStream_t (e.g.
+    ``torch.cuda.current_stream().cuda_stream``); 0/None -> library stream."""
+    check(lib().smc_set_stream(C.c_void_p(cuda_stream_ptr or 0)))
+
+
+def synchronize():
+    check(lib().smc_synchronize())
+
+
+def device_info():
+    sm, maj, mnr = C.c_int(), C.c_int(), C.c_int()
+    fr, tot = C.c_size_t(), C.c_size_t()
+    check(lib().smc_device_info(C.byref(sm), C.byref(maj), C.byref(mnr),
+                                C.byref(fr), C.byref(tot)))
+    return {"sm_count": sm.value, "cc": (maj.value, mnr.value),
+            "free_bytes": fr.value, "total_bytes": tot.value}
+
+
+def launch_count():
+    return lib().smc_launch_count()
+
+
+def reset_launch_count():
+    lib().smc_reset_launch_count()
