@@ -99,13 +99,41 @@ __device__ __forceinline__ void st_stream(double* p, double v) {
 }
 
 // ------------------------------------------------------------------- the kernel
+// Raw per-row inputs, loaded one tile ahead so their DRAM latency overlaps the
+// current tile's arithmetic.
+struct RowRaw {
+  double y, alpha, aux;
+  int yi;
+};
+
 template <int FAM>
+__device__ __forceinline__ RowRaw load_row(const FusedArgs& a, int64_t row) {
+  RowRaw r;
+  r.y = a.y_scalar;
+  r.yi = 0;
+  r.alpha = a.alpha;
+  r.aux = a.aux;
+  if (row < a.N) {
+    if (a.y) {
+      if constexpr (FAM == kNormal)
+        r.y = static_cast<const double*>(a.y)[row];
+      else
+        r.yi = static_cast<const int*>(a.y)[row];
+    }
+    if (a.alpha_vec) r.alpha = a.alpha_vec[row];
+    if (a.aux_vec) r.aux = a.aux_vec[row];
+  }
+  return r;
+}
+
+template <int FAM, int G>
 __global__ void __launch_bounds__(256, 1)
     glm_fused_kernel(const __grid_constant__ CUtensorMap tmap,
                      const __grid_constant__ FusedArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  const int S = a.S, G = a.G;
-  const int R = 32 * G, CW = 32 * S;
+  const int S = a.S;
+  constexpr int R = 32 * G;
+  const int CW = 32 * S;
   const int n_cons_warps = S * G;
   const uint32_t stage_bytes = (uint32_t)R * CW * 8u;
 
@@ -173,6 +201,8 @@ __global__ void __launch_bounds__(256, 1)
   }
   {
     int it = 0;
+    const int rloc = 32 * g + lane;
+    RowRaw nxt = load_row<FAM>(a, (int64_t)blockIdx.x * R + rloc);
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
       const int st = it % kStages;
       const uint32_t ph = (uint32_t)(it / kStages) & 1u;
@@ -188,19 +218,20 @@ __global__ void __launch_bounds__(256, 1)
                       &full_bar[rs], pol);
         }
       }
-      const int rloc = 32 * g + lane;
       const int64_t row = (int64_t)tile * R + rloc;
       const bool valid = row < a.N;
 
-      // per-row inputs: issue the global loads before blocking on the tile
+      // per-row inputs of THIS tile were loaded during the previous iteration;
+      // issue the loads for the next tile now
+      const RowRaw cur = nxt;
+      nxt = load_row<FAM>(a, row + (int64_t)gridDim.x * R);
       RowIn<FAM> in;
       if constexpr (FAM == kNormal)
-        in.y = (a.y && valid) ? static_cast<const double*>(a.y)[row] : a.y_scalar;
+        in.y = cur.y;
       else
-        in.y = (a.y && valid) ? (double)static_cast<const int*>(a.y)[row]
-                              : a.y_scalar;
-      in.alpha = (a.alpha_vec && valid) ? a.alpha_vec[row] : a.alpha;
-      in.aux = (a.aux_vec && valid) ? a.aux_vec[row] : a.aux;
+        in.y = a.y ? (double)cur.yi : cur.y;
+      in.alpha = cur.alpha;
+      in.aux = cur.aux;
 
       mbar_wait(&full_bar[st], ph);
       const double* xs
@@ -211,17 +242,29 @@ __global__ void __launch_bounds__(256, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[st]);  // stage is free again
 
+      // partial dot product: four independent FMA chains (fixed association)
       const double* bs = beta_s + 32 * s;
-      double part = 0.0;
+      double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
 #pragma unroll
-      for (int kk = 0; kk < kColsPerThread; ++kk) part = fma(xv[kk], bs[kk], part);
+      for (int kk = 0; kk < kColsPerThread; kk += 4) {
+        p0 = fma(xv[kk + 0], bs[kk + 0], p0);
+        p1 = fma(xv[kk + 1], bs[kk + 1], p1);
+        p2 = fma(xv[kk + 2], bs[kk + 2], p2);
+        p3 = fma(xv[kk + 3], bs[kk + 3], p3);
+      }
+      const double part = (p0 + p1) + (p2 + p3);
 
       double xb = part;
       if (S > 1) {
         partial_s[(par * S + s) * R + rloc] = part;
         group_bar(1 + g, 32 * S);
-        xb = 0.0;
-        for (int ss = 0; ss < S; ++ss) xb += partial_s[(par * S + ss) * R + rloc];
+        // every warp of the row group adds the S partials in the same fixed
+        // tree, so all of them hold the identical theta
+        double q[8];
+#pragma unroll
+        for (int ss = 0; ss < 8; ++ss)
+          q[ss] = ss < S ? partial_s[(par * S + ss) * R + rloc] : 0.0;
+        xb = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
       }
 
       double d1 = 0, d2 = 0;
@@ -418,21 +461,36 @@ static int get_tmap(const smc_matrix* xc, int R, int CW, CUtensorMap* out) {
   return SMC_OK;
 }
 
-template <int FAM>
-static int launch_t(const CUtensorMap& tmap, const FusedArgs& a, int grid,
-                    int threads, size_t smem) {
+template <int FAM, int G>
+static int launch_tg(const CUtensorMap& tmap, const FusedArgs& a, int grid,
+                     int threads, size_t smem) {
   static size_t attr_smem[16] = {};
   Context& c = ctx();
   if (attr_smem[c.device & 15] < smem) {
-    SMC_CUDA(cudaFuncSetAttribute(glm_fused_kernel<FAM>,
+    SMC_CUDA(cudaFuncSetAttribute(glm_fused_kernel<FAM, G>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     attr_smem[c.device & 15] = smem;
   }
-  glm_fused_kernel<FAM><<<grid, threads, smem, c.stream>>>(tmap, a);
+  glm_fused_kernel<FAM, G><<<grid, threads, smem, c.stream>>>(tmap, a);
   SMC_CUDA(cudaGetLastError());
   c.launches += 1;
   return SMC_OK;
+}
+
+template <int FAM>
+static int launch_t(const CUtensorMap& tmap, const FusedArgs& a, int grid,
+                    int threads, size_t smem) {
+  switch (a.G) {
+    case 1:
+      return launch_tg<FAM, 1>(tmap, a, grid, threads, smem);
+    case 2:
+      return launch_tg<FAM, 2>(tmap, a, grid, threads, smem);
+    case 4:
+      return launch_tg<FAM, 4>(tmap, a, grid, threads, smem);
+    default:
+      return launch_tg<FAM, 8>(tmap, a, grid, threads, smem);
+  }
 }
 
 int launch_glm_fused(const GlmCall& c) {
