@@ -55,7 +55,10 @@ int prepare_args(const GlmCall& c, FusedArgs* ap) {
         if (c.y) {
           if (int rc = y_lgamma_sum(c.y, &lg)) return rc;
         } else {
-          lg = Nd * std::lgamma(c.y_scalar + 1.0);
+          // a broadcast scalar y: the poisson GLM sums lgamma(y + 1) over the
+          // elements of y as passed (once), the neg-binomial GLM scales by N
+          // (L165-168) -- both reproduced as the reference has them
+          lg = std::lgamma(c.y_scalar + 1.0) * (c.family == kPoisson ? 1.0 : Nd);
         }
         a.c0 -= lg;
       }

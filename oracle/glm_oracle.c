@@ -285,7 +285,11 @@ int oracle_poisson_log_glm(long N, long K, const int* y, long ny,
     d[i] = yi - e; /* L117-118 */
     acc_add(&sd, d[i]);
     acc_add(&lp, yi * th[i] - e); /* L130-131 */
-    if (!(flags & F_PROPTO)) acc_add(&lg, oracle_lgamma(yi + 1)); /* L126-128 */
+    /* L126-128: sum(lgamma(y + 1)) over the elements of y AS PASSED -- a
+     * broadcast scalar y contributes the term once, not N times (reference
+     * behaviour, reproduced for parity; the neg-binomial GLM does scale by N) */
+    if (!(flags & F_PROPTO) && (ny != 1 || i == 0))
+      acc_add(&lg, oracle_lgamma(yi + 1));
   }
   double sdv = acc_get(&sd);
   if (!isfinite(sdv)) { /* L120-124 */
