@@ -1,9 +1,578 @@
-// categorical_logit_glm_lpmf on the device (placeholder until the DMMA kernels land).
+// categorical_logit_glm_lpmf on sm_100a: the one GEMM-shaped GLM.
+//
+// reference: stan/math/prim/prob/categorical_logit_glm_lpmf.hpp L43-195
+//   lin = x beta + alpha^T                 (N x K . K x C)           L95-96
+//   softmax with row-max subtraction, logp                           L97-117
+//   T   = -softmax(lin) + onehot(y)                                  L158-159, L165-185
+//   d_alpha = colsum(T)                                              L160-169
+//   d_beta  = x^T T                        (K x N . N x C)           L171-190
+//   d_x     = T beta^T                     (N x C . C x K)           L142-150
+// (the reference's "+1 at column y_i" scatters are folded into T).
+//
+// 4 N K C flops against 2 N K 8 bytes puts this family above the FP64 ridge for
+// C >= ~16, so both contractions run on the FP64 tensor pipe (DMMA,
+// mma.sync.m8n8k4.f64 -- tcgen05 has no FP64 kind) and x is swept twice:
+//   pass 1  cat_lin_kernel   lin tiles (32 rows x C per warp) accumulated in
+//           registers, softmax / logp / T fused into the epilogue
+//   pass 2  cat_dbeta_kernel K x C accumulators of a CTA live in registers while it
+//           streams its row slice; per-CTA partials, fixed-order final sum
+// Operand fragments are loaded straight from global memory in the DMMA lane
+// layout (a column-major 32-row tile cannot be read conflict-free from shared
+// memory in that layout: the k stride is a multiple of all 32 banks); beta sits
+// in shared memory with a +4 padded stride, which makes its fragment reads
+// conflict-free.  All reductions are fixed-order (no floating-point atomics).
+#include <cmath>
+#include <cstring>
+#include <vector>
+
 #include "smc_internal.h"
+
+namespace smc {
+
+constexpr int kCatThreads = 256;
+constexpr int kCatWarps = 8;
+constexpr size_t kCatSmemBudget = 200 * 1024;
+
+struct CatArgs {
+  int64_t N;
+  int K, C, C8;
+  const double* x;
+  int64_t ldx;
+  const int* y;
+  int y_scalar;
+  const double* beta;   // device, column-major K x C
+  const double* alpha;  // device, C
+  double* T;            // device, column-major N x C8 (ld = ldT)
+  int64_t ldT;
+  double* partials;  // pass 1: [grid][1 + 1 + C8]; pass 2: [grid][K*C8]
+  double* out;       // pass 1 finalize: [0]=logp, [1]=nonfinite, [2..2+C) d_alpha
+  double* d_beta;    // pass 2 finalize: device K x C
+  double* d_x;
+  int64_t ld_dx;
+  int kchunk;   // k columns of beta resident in shared memory at a time (mult of 4)
+  int kstride;  // kchunk + 4
+  int rows_per_cta;  // pass 2 row slice (multiple of 4)
+};
+
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+  asm volatile(
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(d0), "+d"(d1)
+      : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double quad_max(double v) {
+  v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  return v;
+}
+__device__ __forceinline__ double quad_sum(double v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+
+// ----------------------------------------------------------------- pass 1
+template <int NT>
+__global__ void __launch_bounds__(kCatThreads, 1)
+    cat_lin_kernel(const __grid_constant__ CatArgs a) {
+  extern __shared__ __align__(16) unsigned char cat_smem[];
+  double* beta_s = reinterpret_cast<double*>(cat_smem);  // [C8][kstride]
+  double* alpha_s = beta_s + (size_t)a.C8 * a.kstride;    // [C8]
+  double* red_s = alpha_s + a.C8;                         // [kCatWarps][2 + C8]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = lane >> 2, tig = lane & 3;
+  const int nchunks = (a.K + a.kchunk - 1) / a.kchunk;
+  const int64_t ntiles = (a.N + 31) / 32;
+  const int64_t tiles_per_round = (int64_t)gridDim.x * kCatWarps;
+  const int64_t nrounds = (ntiles + tiles_per_round - 1) / tiles_per_round;
+
+  for (int c = tid; c < a.C8; c += kCatThreads) alpha_s[c] = c < a.C ? a.alpha[c] : 0.0;
+
+  double lp_acc = 0.0, bad_acc = 0.0;
+  double dal[NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) dal[nt][0] = dal[nt][1] = 0.0;
+
+  for (int64_t round = 0; round < nrounds; ++round) {
+    const int64_t tile = round * tiles_per_round + (int64_t)blockIdx.x * kCatWarps + warp;
+    const int64_t r0 = tile * 32;
+    double acc[4][NT][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int kb = ch * a.kchunk;
+      const int kc = min(a.kchunk, ((a.K - kb) + 3) & ~3);
+      if (nchunks > 1 || round == 0) {
+        // (re)load the beta chunk: beta_s[c][k - kb], zero padded
+        __syncthreads();
+        for (int idx = tid; idx < a.C8 * kc; idx += kCatThreads) {
+          const int c = idx / kc, k = idx - c * kc;
+          beta_s[(size_t)c * a.kstride + k]
+              = (c < a.C && kb + k < a.K) ? a.beta[(size_t)c * a.K + kb + k] : 0.0;
+        }
+        __syncthreads();
+      }
+      if (r0 < a.N) {
+        // A fragment addresses: lane holds x[r0 + 8 mt + grp][k + tig]
+        const double* xa = a.x + (size_t)(kb + tig) * a.ldx + r0 + grp;
+        bool rok[4];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) rok[mt] = r0 + 8 * mt + grp < a.N;
+        const double* bfrag = beta_s + (size_t)grp * a.kstride + tig;
+#pragma unroll 4
+        for (int k = 0; k < kc; k += 4) {
+          const bool kok = kb + k + tig < a.K;
+          double af[4];
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt)
+            af[mt] = (rok[mt] && kok) ? __ldg(xa + (size_t)k * a.ldx + 8 * mt) : 0.0;
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            const double bf = bfrag[(size_t)(8 * nt) * a.kstride + k];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+              dmma(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf);
+          }
+        }
+      }
+    }
+    if (r0 >= a.N) continue;
+
+    // ---- epilogue: softmax over the C classes of each row (held by a quad)
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      const int64_t row = r0 + 8 * mt + grp;
+      const bool valid = row < a.N;
+      const int yc = valid ? (a.y ? a.y[row] : a.y_scalar) - 1 : 0;
+      double m = -INFINITY;
+      double lin_y = 0.0;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int c = 8 * nt + 2 * tig + j;
+          double v = acc[mt][nt][j] + alpha_s[c];
+          acc[mt][nt][j] = v;
+          if (c < a.C) {
+            m = fmax(m, v);
+            if (c == yc) lin_y = v;
+          }
+        }
+      m = quad_max(m);
+      double se = 0.0;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int c = 8 * nt + 2 * tig + j;
+          const double e = c < a.C ? exp(acc[mt][nt][j] - m) : 0.0;
+          acc[mt][nt][j] = e;
+          se += e;
+        }
+      se = quad_sum(se);
+      lin_y = quad_sum(lin_y);
+      const double inv = 1.0 / se;
+      if (valid) {
+        if (tig == 0) {
+          const double t = (log(inv) - m) + lin_y;  // L106, L110-116
+          lp_acc += t;
+          bad_acc += isfinite(t) ? 0.0 : 1.0;
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int c = 8 * nt + 2 * tig + j;
+            if (c < a.C8) {
+              double t = acc[mt][nt][j] * -inv;  // neg_softmax_lin, L158-159
+              if (c == yc) t += 1.0;             // the "+1 at class y_i" scatters
+              if (c >= a.C) t = 0.0;
+              a.T[(size_t)c * a.ldT + row] = t;
+              dal[nt][j] += t;
+            }
+          }
+      }
+    }
+  }
+
+  // ---- CTA reduction of logp / nonfinite / d_alpha partials (fixed order)
+  // lanes sharing tig hold the same columns: add over grp (xor 4, 8, 16)
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      double v = dal[nt][j];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      dal[nt][j] = v;
+    }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    lp_acc += __shfl_xor_sync(0xffffffffu, lp_acc, o);
+    bad_acc += __shfl_xor_sync(0xffffffffu, bad_acc, o);
+  }
+  __syncthreads();
+  const int rs = 2 + a.C8;
+  if (lane == 0) {
+    red_s[warp * rs + 0] = lp_acc;
+    red_s[warp * rs + 1] = bad_acc;
+  }
+  if (grp == 0) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) red_s[warp * rs + 2 + 8 * nt + 2 * tig + j] = dal[nt][j];
+  }
+  __syncthreads();
+  for (int j = tid; j < rs; j += kCatThreads) {
+    double v = 0.0;
+    for (int w = 0; w < kCatWarps; ++w) v += red_s[w * rs + j];
+    a.partials[(size_t)blockIdx.x * rs + j] = v;
+  }
+}
+
+__global__ void cat_lin_finalize_kernel(const double* __restrict__ partials, int nb,
+                                        int rs, int C, double* __restrict__ out) {
+  for (int j = threadIdx.x; j < rs; j += blockDim.x) {
+    double v = 0.0;
+    for (int b = 0; b < nb; ++b) v += partials[(size_t)b * rs + j];
+    if (j < 2 || j - 2 < C) out[j] = v;
+  }
+}
+
+// ----------------------------------------------------------------- pass 2
+// CTA (bx, by): K-chunk by (MT*8*8 attributes), row slice bx.  Warp w owns the
+// attributes [kbase + 64 w', ...): MT blocks of 8.  D[k][c] += x[i][k] T[i][c].
+template <int NT, int MT>
+__global__ void __launch_bounds__(kCatThreads, 1)
+    cat_dbeta_kernel(const __grid_constant__ CatArgs a) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = lane >> 2, tig = lane & 3;
+  const int kbase = blockIdx.y * (kCatWarps * MT * 8) + warp * (MT * 8);
+  const int64_t i_begin = (int64_t)blockIdx.x * a.rows_per_cta;
+  const int64_t i_end = min(a.N, i_begin + a.rows_per_cta);
+  double acc[MT][NT][2];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+
+  if (kbase < a.K) {
+    bool kok[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) kok[mt] = kbase + 8 * mt + grp < a.K;
+    // A[m = attribute][kk = row]: lane holds x[i + tig][kbase + 8 mt + grp]
+    const double* xa = a.x + (size_t)(kbase + grp) * a.ldx + tig;
+    // B[kk = row][n = class]: lane holds T[i + tig][8 nt + grp]
+    const double* tb = a.T + (size_t)grp * a.ldT + tig;
+#pragma unroll 2
+    for (int64_t i = i_begin; i < i_end; i += 4) {
+      const bool iok = i + tig < a.N;
+      double af[MT], bf[NT];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+        af[mt] = (kok[mt] && iok) ? __ldg(xa + (size_t)(8 * mt) * a.ldx + i) : 0.0;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+        bf[nt] = iok ? __ldg(tb + (size_t)(8 * nt) * a.ldT + i) : 0.0;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+          dmma(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+    }
+  }
+  // per-CTA partial, layout [k][c8] of this K chunk; every element written
+  double* part = a.partials
+                 + ((size_t)blockIdx.y * gridDim.x + blockIdx.x)
+                       * ((size_t)kCatWarps * MT * 8 * a.C8);
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int kl = warp * (MT * 8) + 8 * mt + grp;
+        const int c = 8 * nt + 2 * tig + j;
+        if (c < a.C8) part[(size_t)kl * a.C8 + c] = acc[mt][nt][j];
+      }
+}
+
+__global__ void cat_dbeta_finalize_kernel(const double* __restrict__ partials,
+                                          int nbx, int kchunk_sz, int K, int C,
+                                          int C8, double* __restrict__ d_beta) {
+  const int64_t total = (int64_t)K * C;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx / K), k = (int)(idx - (int64_t)c * K);
+    const int by = k / kchunk_sz, kl = k - by * kchunk_sz;
+    const double* p = partials + (size_t)by * nbx * ((size_t)kchunk_sz * C8)
+                      + (size_t)kl * C8 + c;
+    double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+    int b = 0;
+    const size_t stride = (size_t)kchunk_sz * C8;
+    for (; b + 3 < nbx; b += 4) {
+      v0 += p[(size_t)(b + 0) * stride];
+      v1 += p[(size_t)(b + 1) * stride];
+      v2 += p[(size_t)(b + 2) * stride];
+      v3 += p[(size_t)(b + 3) * stride];
+    }
+    for (; b < nbx; ++b) v0 += p[(size_t)b * stride];
+    d_beta[(size_t)c * K + k] = (v0 + v1) + (v2 + v3);
+  }
+}
+
+// ----------------------------------------------------------------- d_x = T beta^T
+// One thread per row, T row in registers, beta broadcast from global (L1).
+template <int CMAX>
+__global__ void __launch_bounds__(256)
+    cat_dx_kernel(const __grid_constant__ CatArgs a) {
+  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (row >= a.N) return;
+  double t[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) t[c] = c < a.C ? a.T[(size_t)c * a.ldT + row] : 0.0;
+  for (int k = 0; k < a.K; ++k) {
+    double v = 0.0;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < a.C) v = fma(t[c], __ldg(a.beta + (size_t)c * a.K + k), v);
+    a.d_x[(size_t)k * a.ld_dx + row] = v;
+  }
+}
+
+template <int NT>
+static int run_lin(const CatArgs& a, int grid, size_t smem) {
+  static size_t attr[16] = {};
+  Context& c = ctx();
+  if (attr[c.device & 15] < smem) {
+    SMC_CUDA(cudaFuncSetAttribute(cat_lin_kernel<NT>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    attr[c.device & 15] = smem;
+  }
+  cat_lin_kernel<NT><<<grid, kCatThreads, smem, c.stream>>>(a);
+  SMC_CUDA(cudaGetLastError());
+  return SMC_OK;
+}
+
+template <int NT, int MT>
+static int run_dbeta(const CatArgs& a, dim3 grid) {
+  cat_dbeta_kernel<NT, MT><<<grid, kCatThreads, 0, ctx().stream>>>(a);
+  SMC_CUDA(cudaGetLastError());
+  return SMC_OK;
+}
+
+int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
+                       const double* alpha_host, const double* beta_host,
+                       int64_t C, unsigned flags, double* logp, double* d_alpha,
+                       double* d_beta, smc_matrix* d_x) {
+  Context& cx = ctx();
+  CatArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = x->rows;
+  a.K = (int)x->cols;
+  a.C = (int)C;
+  a.C8 = (a.C + 7) & ~7;
+  if (a.C8 > 64)
+    return fail(SMC_ERR_UNSUPPORTED,
+                "categorical_logit_glm_lpmf: more than 64 classes not supported yet");
+  a.x = static_cast<const double*>(x->data);
+  a.ldx = x->ld;
+  a.y = y ? static_cast<const int*>(y->data) : nullptr;
+  a.y_scalar = y_scalar;
+  const int NT = a.C8 / 8;
+
+  // device staging: beta (K*C), alpha (C), out (2 + C8)
+  const size_t nparam = (size_t)a.K * a.C + a.C;
+  if (int rc = ensure_params(sizeof(double) * (nparam + 8))) return rc;
+  if (a.K)
+    SMC_CUDA(cudaMemcpyAsync(cx.params_dev, beta_host, sizeof(double) * a.K * a.C,
+                             cudaMemcpyHostToDevice, cx.stream));
+  SMC_CUDA(cudaMemcpyAsync(cx.params_dev + (size_t)a.K * a.C, alpha_host,
+                           sizeof(double) * a.C, cudaMemcpyHostToDevice, cx.stream));
+  a.beta = cx.params_dev;
+  a.alpha = cx.params_dev + (size_t)a.K * a.C;
+
+  // shared-memory plan for beta: whole K if it fits, else chunks
+  const size_t fixed = (size_t)a.C8 * 8 + (size_t)kCatWarps * (2 + a.C8) * 8 + 64;
+  // kchunk is a multiple of 8 so that kstride = kchunk + 4 is 4 mod 8: the 16
+  // lanes of a half-warp (grp 0..3 x tig 0..3) then read 16 distinct banks pairs
+  int kchunk = (a.K + 7) & ~7;
+  if (kchunk < 8) kchunk = 8;
+  while ((size_t)a.C8 * (kchunk + 4) * 8 + fixed > kCatSmemBudget && kchunk > 8)
+    kchunk = ((kchunk / 2) + 7) & ~7;
+  a.kchunk = kchunk;
+  a.kstride = kchunk + 4;
+  const size_t smem1 = (size_t)a.C8 * a.kstride * 8 + fixed;
+
+  const bool need_beta = flags & SMC_VAR_BETA;
+  const bool need_dx = (flags & SMC_VAR_X) && d_x;
+  // pass-2 geometry
+  const int MT = NT <= 4 ? 8 : 4;
+  const int kchunk2 = kCatWarps * MT * 8;
+  const int nby = need_beta ? (a.K + kchunk2 - 1) / kchunk2 : 0;
+  int nbx = cx.sm_count / (nby > 0 ? nby : 1);
+  if (nbx < 1) nbx = 1;
+  int64_t rpc = (a.N + nbx - 1) / nbx;
+  rpc = (rpc + 3) & ~3ll;
+  if (rpc < 4) rpc = 4;
+  nbx = (int)((a.N + rpc - 1) / rpc);
+  a.rows_per_cta = (int)rpc;
+
+  const int64_t ntiles = (a.N + 31) / 32;
+  int grid1 = (int)((ntiles + kCatWarps - 1) / kCatWarps);
+  if (grid1 > cx.sm_count) grid1 = cx.sm_count;
+  const int rs = 2 + a.C8;
+
+  // scratch: T (ldT x C8), out (rs), d_beta_dev (K*C), partials
+  a.ldT = (a.N + 3) & ~3ll;
+  const size_t nT = (size_t)a.ldT * a.C8;
+  const size_t npart1 = (size_t)grid1 * rs;
+  const size_t npart2 = need_beta ? (size_t)nby * nbx * kchunk2 * a.C8 : 0;
+  const size_t npart = npart1 > npart2 ? npart1 : npart2;
+  const size_t ndb = (size_t)a.K * a.C;
+  if (int rc = ensure_scratch(sizeof(double) * (nT + rs + ndb + 8))) return rc;
+  if (int rc = ensure_partials(sizeof(double) * (npart + 8))) return rc;
+  a.T = cx.scratch;
+  double* out_dev = cx.scratch + nT;
+  double* d_beta_dev = out_dev + rs;
+  a.partials = cx.partials;
+  a.out = out_dev;
+  a.d_beta = d_beta_dev;
+  a.d_x = need_dx ? static_cast<double*>(d_x->data) : nullptr;
+  a.ld_dx = need_dx ? d_x->ld : 0;
+
+  int rc = SMC_OK;
+  switch (NT) {
+    case 1: rc = run_lin<1>(a, grid1, smem1); break;
+    case 2: rc = run_lin<2>(a, grid1, smem1); break;
+    case 3: rc = run_lin<3>(a, grid1, smem1); break;
+    case 4: rc = run_lin<4>(a, grid1, smem1); break;
+    case 5: rc = run_lin<5>(a, grid1, smem1); break;
+    case 6: rc = run_lin<6>(a, grid1, smem1); break;
+    case 7: rc = run_lin<7>(a, grid1, smem1); break;
+    default: rc = run_lin<8>(a, grid1, smem1); break;
+  }
+  if (rc) return rc;
+  cx.launches += 1;
+  cat_lin_finalize_kernel<<<1, 128, 0, cx.stream>>>(cx.partials, grid1, rs, a.C,
+                                                    out_dev);
+  SMC_CUDA(cudaGetLastError());
+  cx.launches += 1;
+
+  if (need_beta && a.K > 0) {
+    dim3 g2(nbx, nby);
+    switch (NT) {
+      case 1: rc = run_dbeta<1, 8>(a, g2); break;
+      case 2: rc = run_dbeta<2, 8>(a, g2); break;
+      case 3: rc = run_dbeta<3, 8>(a, g2); break;
+      case 4: rc = run_dbeta<4, 8>(a, g2); break;
+      case 5: rc = run_dbeta<5, 4>(a, g2); break;
+      case 6: rc = run_dbeta<6, 4>(a, g2); break;
+      case 7: rc = run_dbeta<7, 4>(a, g2); break;
+      default: rc = run_dbeta<8, 4>(a, g2); break;
+    }
+    if (rc) return rc;
+    cx.launches += 1;
+    int gf = (int)((ndb + 255) / 256);
+    if (gf > cx.sm_count * 4) gf = cx.sm_count * 4;
+    cat_dbeta_finalize_kernel<<<gf, 256, 0, cx.stream>>>(cx.partials, nbx, kchunk2,
+                                                        a.K, a.C, a.C8, d_beta_dev);
+    SMC_CUDA(cudaGetLastError());
+    cx.launches += 1;
+  }
+  if (need_dx && a.K > 0) {
+    const int g3 = (int)((a.N + 255) / 256);
+    if (a.C <= 8)
+      cat_dx_kernel<8><<<g3, 256, 0, cx.stream>>>(a);
+    else if (a.C <= 16)
+      cat_dx_kernel<16><<<g3, 256, 0, cx.stream>>>(a);
+    else if (a.C <= 32)
+      cat_dx_kernel<32><<<g3, 256, 0, cx.stream>>>(a);
+    else
+      cat_dx_kernel<64><<<g3, 256, 0, cx.stream>>>(a);
+    SMC_CUDA(cudaGetLastError());
+    cx.launches += 1;
+  }
+
+  // results -> host
+  if (int rc2 = ensure_out(sizeof(double) * (rs + ndb + 8))) return rc2;
+  SMC_CUDA(cudaMemcpyAsync(cx.out_host, out_dev, sizeof(double) * rs,
+                           cudaMemcpyDeviceToHost, cx.stream));
+  if (need_beta && a.K > 0)
+    SMC_CUDA(cudaMemcpyAsync(cx.out_host + rs, d_beta_dev, sizeof(double) * ndb,
+                             cudaMemcpyDeviceToHost, cx.stream));
+  SMC_CUDA(cudaStreamSynchronize(cx.stream));
+  *logp = cx.out_host[0];
+  if (d_alpha && (flags & SMC_VAR_ALPHA))
+    memcpy(d_alpha, cx.out_host + 2, sizeof(double) * a.C);
+  if (d_beta && need_beta) {
+    if (a.K > 0)
+      memcpy(d_beta, cx.out_host + rs, sizeof(double) * ndb);
+  }
+  return SMC_OK;
+}
+
+}  // namespace smc
+
 using namespace smc;
-extern "C" int smc_categorical_logit_glm(const smc_matrix*, int, const smc_matrix*,
-                                         const double*, const double*, int64_t,
-                                         unsigned, double*, double*, double*,
-                                         smc_matrix*) {
-  return fail(SMC_ERR_UNSUPPORTED, "categorical_logit_glm_lpmf: not built yet");
+
+extern "C" int smc_categorical_logit_glm(const smc_matrix* y, int y_scalar,
+                                         const smc_matrix* x, const double* alpha,
+                                         const double* beta, int64_t n_classes,
+                                         unsigned flags, double* logp,
+                                         double* d_alpha, double* d_beta,
+                                         smc_matrix* d_x) {
+  static const char* fn = "categorical_logit_glm_lpmf";
+  if (int rc = ensure_ctx()) return rc;
+  if (!x || x->dtype != SMC_F64)
+    return fail(SMC_ERR_INVALID_ARGUMENT, "%s: x must be an f64 device matrix", fn);
+  const int64_t N = x->rows, K = x->cols, C = n_classes;
+  if (y && (y->dtype != SMC_I32 || y->rows * y->cols != N))
+    return fail(SMC_ERR_INVALID_ARGUMENT,
+                "%s: size of y does not match rows of x", fn);  // L68-72
+  if (C < 1 || !alpha || (K > 0 && !beta) || !logp)
+    return fail(SMC_ERR_INVALID_ARGUMENT, "%s: NULL or empty alpha / beta / logp", fn);
+  if ((flags & SMC_VAR_X)
+      && (!d_x || d_x->dtype != SMC_F64 || d_x->rows != N || d_x->cols != K))
+    return fail(SMC_ERR_INVALID_ARGUMENT, "%s: SMC_VAR_X needs d_x shaped like x", fn);
+  *logp = 0.0;
+  if (N == 0 || C == 1) return SMC_OK;  // L73-75
+  {
+    int mn, mx;  // check_bounded(y, 1, C), L77
+    if (y) {
+      if (int rc = y_range(y, &mn, &mx)) return rc;
+    } else {
+      mn = mx = y_scalar;
+    }
+    if (mn < 1 || mx > C)
+      return fail(SMC_ERR_DOMAIN, "%s: categorical outcome out of support", fn);
+  }
+  if ((flags & SMC_PROPTO) && !(flags & (SMC_VAR_X | SMC_VAR_ALPHA | SMC_VAR_BETA)))
+    return SMC_OK;  // L80-82
+  double lp = 0.0;
+  if (int rc = launch_categorical(y, y_scalar, x, alpha, beta, C, flags, &lp, d_alpha,
+                                  d_beta, d_x))
+    return rc;
+  if (!std::isfinite(lp)) {  // lazy checks, L122-126
+    for (int64_t i = 0; i < K * C; ++i)
+      if (!std::isfinite(beta[i]))
+        return fail(SMC_ERR_DOMAIN, "%s: Weight vector is not finite", fn);
+    for (int64_t i = 0; i < C; ++i)
+      if (!std::isfinite(alpha[i]))
+        return fail(SMC_ERR_DOMAIN, "%s: Intercept is not finite", fn);
+    int ok = 1;
+    if (int rc = smc_matrix_all_finite(x, &ok)) return rc;
+    if (!ok)
+      return fail(SMC_ERR_DOMAIN,
+                  "%s: Matrix of independent variables is not finite", fn);
+  }
+  *logp = lp;
+  return SMC_OK;
 }

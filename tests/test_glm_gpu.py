@@ -242,3 +242,29 @@ def test_determinism(gpu):
     for _ in range(5):
         r = gpu.bernoulli_logit_glm_lpmf(y, x, 0.1, d["beta"])
         assert r.logp == r0.logp and np.array_equal(r.d_beta, r0.d_beta)
+
+
+@pytest.mark.parametrize("N,K,C", [(5, 2, 3), (153, 71, 43), (1000, 1, 2), (4099, 64, 8),
+                                   (3000, 512, 32), (2000, 100, 64), (50, 600, 5),
+                                   (700, 40, 17)])
+def test_categorical(gpu, N, K, C):
+    d = make_inputs("categorical", N, K, seed=N + 5 * C, C=C)
+    x = gpu.to_matrix_cuda(d["x"])
+    y = gpu.to_matrix_cuda(d["y"])
+    for propto in (False, True):
+        r = gpu.categorical_logit_glm_lpmf(y, x, d["alpha"], d["beta"], propto=propto,
+                                           var=("x", "alpha", "beta"))
+        o = po.categorical_logit_glm(d["y"], d["x"], d["alpha"], d["beta"],
+                                     flags=_flags(propto, ["x", "alpha", "beta"]))
+        assert o["rc"] == 0
+        assert_logp(r.logp, o["logp"])
+        sc = np.abs(o["d_beta"]).max()
+        assert_grad(r.d_alpha, o["d_alpha"], "d_alpha", scale=sc * 1e-2)
+        assert_grad(r.d_beta, o["d_beta"], "d_beta")
+        assert_grad(r.d_x.to_host(), o["d_x"], "d_x")
+    # C == 1 returns 0 (L73-75); y out of support -> domain_error
+    assert gpu.categorical_logit_glm_lpmf(y, x, [0.1], np.zeros((K, 1))).logp == 0.0
+    ybad = d["y"].copy()
+    ybad[0] = C + 1
+    with pytest.raises(gpu.DomainError):
+        gpu.categorical_logit_glm_lpmf(gpu.to_matrix_cuda(ybad), x, d["alpha"], d["beta"])
