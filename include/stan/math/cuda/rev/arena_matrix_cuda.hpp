@@ -1,0 +1,81 @@
+#ifndef STAN_MATH_CUDA_REV_ARENA_MATRIX_CUDA_HPP
+#define STAN_MATH_CUDA_REV_ARENA_MATRIX_CUDA_HPP
+// arena_matrix_cuda<T>: a device matrix whose lifetime is that of the autodiff
+// arena, the analogue of arena_matrix_cl (stan/math/opencl/rev/arena_matrix_cl.hpp
+// L15-22).  The object itself is a trivially destructible handle (it is captured
+// by value in reverse_pass_callback lambdas, which are never destroyed:
+// rev/core/callback_vari.hpp L32-33); the device buffer is owned by a
+// chainable_alloc on var_alloc_stack_ (rev/core/chainable_alloc.hpp L16-22) and
+// is released by recover_memory() (rev/core/recover_memory.hpp).
+#include <stan/math/cuda/matrix_cuda.hpp>
+#include <stan/math/rev/core/chainable_alloc.hpp>
+
+#include <utility>
+
+namespace stan {
+namespace math {
+
+namespace internal {
+class cuda_arena_owner : public chainable_alloc {
+ public:
+  explicit cuda_arena_owner(smc_matrix* h) : h_(h) {}
+  ~cuda_arena_owner() override {
+    if (h_) {
+      smc_matrix_free(h_);
+    }
+  }
+
+ private:
+  smc_matrix* h_;
+};
+}  // namespace internal
+
+template <typename T>
+class arena_matrix_cuda : public matrix_cuda_base {
+ public:
+  using Scalar = T;
+  arena_matrix_cuda() = default;
+
+  /** rows x cols of zeros owned by the arena. */
+  arena_matrix_cuda(int64_t rows, int64_t cols) {
+    matrix_cuda<T> m(rows, cols);
+    m.zero();
+    take(std::move(m));
+  }
+  /** Moves an owning matrix into the arena. */
+  explicit arena_matrix_cuda(matrix_cuda<T>&& m) { take(std::move(m)); }
+  /** Arena-owned view: `m` must outlive the reverse sweep (data matrices do). */
+  static arena_matrix_cuda view(const matrix_cuda<T>& m) {
+    arena_matrix_cuda a;
+    a.take(matrix_cuda<T>::view(m));
+    return a;
+  }
+
+  int64_t rows() const noexcept { return h_ ? smc_matrix_rows(h_) : 0; }
+  int64_t cols() const noexcept { return h_ ? smc_matrix_cols(h_) : 0; }
+  int64_t size() const noexcept { return rows() * cols(); }
+  smc_matrix* handle() const noexcept { return h_; }
+
+  /** Copy to an owning matrix (device-to-device). */
+  matrix_cuda<T> to_matrix_cuda() const {
+    matrix_cuda<T> out(rows(), cols());
+    if (h_) {
+      check_cuda_status("arena_matrix_cuda::to_matrix_cuda",
+                        smc_matrix_copy(out.handle(), h_));
+    }
+    return out;
+  }
+
+ private:
+  void take(matrix_cuda<T>&& m) {
+    h_ = m.release_handle();
+    if (h_) {
+      new internal::cuda_arena_owner(h_);  // registered on var_alloc_stack_
+    }
+  }
+  smc_matrix* h_{nullptr};
+};
+
+}  // namespace math
+}  // namespace stan
+#endif

@@ -109,6 +109,9 @@ int smc_matrix_download(const smc_matrix* m, void* host, int64_t ld_host);
 int smc_matrix_download_rows(const smc_matrix* m, int64_t row0, int64_t nrows,
                              void* host, int64_t ld_host);
 int smc_matrix_zero(smc_matrix* m);
+/* Device-to-device copy of a same-shaped matrix (matrix_cl copy construction,
+ * matrix_cl.hpp L198-210); asynchronous on the thread's stream. */
+int smc_matrix_copy(smc_matrix* dst, const smc_matrix* src);
 /* y += a * x on the device: update_adjoints for a device-resident operand
  * (rev/functor/operands_and_partials.hpp L28-38). */
 int smc_matrix_axpy(smc_matrix* y, double a, const smc_matrix* x);

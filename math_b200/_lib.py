@@ -56,6 +56,7 @@ SIGNATURES = {
     "smc_matrix_download": (_I, [_P, _P, _I64]),
     "smc_matrix_download_rows": (_I, [_P, _I64, _I64, _P, _I64]),
     "smc_matrix_zero": (_I, [_P]),
+    "smc_matrix_copy": (_I, [_P, _P]),
     "smc_matrix_axpy": (_I, [_P, _D, _P]),
     "smc_matrix_all_finite": (_I, [_P, C.POINTER(_I)]),
     "smc_matrix_int_range": (_I, [_P, C.POINTER(_I), C.POINTER(_I)]),

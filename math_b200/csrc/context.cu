@@ -365,6 +365,22 @@ int smc_matrix_zero(smc_matrix* m) {
   return SMC_OK;
 }
 
+int smc_matrix_copy(smc_matrix* dst, const smc_matrix* src) {
+  if (!dst || !src || dst->rows != src->rows || dst->cols != src->cols
+      || dst->dtype != src->dtype)
+    return fail(SMC_ERR_INVALID_ARGUMENT, "copy: shape/dtype mismatch");
+  if (int rc = ensure_ctx()) return rc;
+  if (dst->rows == 0 || dst->cols == 0) return SMC_OK;
+  dst->lgamma_valid = false;
+  dst->range_valid = false;
+  const size_t es = elem_size(dst->dtype);
+  SMC_CUDA(cudaMemcpy2DAsync(dst->data, (size_t)dst->ld * es, src->data,
+                             (size_t)src->ld * es, (size_t)src->rows * es,
+                             (size_t)src->cols, cudaMemcpyDeviceToDevice,
+                             ctx().stream));
+  return SMC_OK;
+}
+
 int smc_matrix_axpy(smc_matrix* y, double a, const smc_matrix* x) {
   if (!y || !x || y->rows != x->rows || y->cols != x->cols
       || y->dtype != SMC_F64 || x->dtype != SMC_F64)
