@@ -69,7 +69,9 @@ inline T_dst from_matrix_cuda(const matrix_cuda<T>& src) {
   return dst;
 }
 
-template <typename T>
+// (the leading non-type parameter keeps from_matrix_cuda<double>(m) from matching
+// this overload)
+template <int Unused = 0, typename T>
 inline Eigen::Matrix<T, Eigen::Dynamic, Eigen::Dynamic> from_matrix_cuda(
     const matrix_cuda<T>& src) {
   return from_matrix_cuda<Eigen::Matrix<T, Eigen::Dynamic, Eigen::Dynamic>>(src);

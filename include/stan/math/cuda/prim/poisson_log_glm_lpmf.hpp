@@ -1,0 +1,89 @@
+#ifndef STAN_MATH_CUDA_PRIM_POISSON_LOG_GLM_LPMF_HPP
+#define STAN_MATH_CUDA_PRIM_POISSON_LOG_GLM_LPMF_HPP
+// poisson_log_glm_lpmf for a device-resident design matrix: the B200
+// overload of stan/math/prim/prob/poisson_log_glm_lpmf.hpp L51-163 (same
+// name, template order and <propto> convention; selected by the type of x the
+// way the OpenCL overload is, opencl/prim/poisson_log_glm_lpmf.hpp L50-56).
+// Value and partials come from ONE fused pass over x on the GPU
+// (smc_poisson_log_glm); they are attached to the tape through the
+// reference's own make_partials_propagator(...).build(logp).
+#include <stan/math/cuda/prim/glm_common.hpp>
+
+namespace stan {
+namespace math {
+
+template <bool propto, typename T_y, typename T_x, typename T_alpha,
+          typename T_beta, require_cuda_design_matrix_t<T_x>* = nullptr>
+return_type_t<T_x, T_alpha, T_beta> poisson_log_glm_lpmf(
+    const T_y& y, const T_x& x, const T_alpha& alpha, const T_beta& beta) {
+  using namespace cuda_internal;  // NOLINT
+  static constexpr const char* function = "poisson_log_glm_lpmf(CUDA)";
+  const int64_t N = x.rows();
+  const int64_t K = x.cols();
+
+  // prim L79-82
+  if (!is_stan_scalar<T_y>::value) {
+    check_size_match(function, "Rows of ", "x", N, "rows of ", "y", operand_size(y));
+  }
+  check_size_match(function, "Columns of ", "x", K, "size of ", "beta",
+                   operand_size(beta));
+  if (!is_stan_scalar<T_alpha>::value) {
+    check_size_match(function, "Rows of ", "x", N, "size of ", "alpha",
+                     operand_size(alpha));
+  }
+  if (N == 0) {  // nothing to check in an empty y (L84); size_zero(y), L86-88
+    return 0;
+  }
+  row_operand<int, T_y> y_op(y);
+  if (y_op.handle() == nullptr) {  // scalar y: check_nonnegative(y), L84
+    check_nonnegative(function, "Vector of dependent variables", y_op.scalar());
+  }
+  if (!include_summand<propto, T_x, T_alpha, T_beta>::value) {  // L89-91
+    // the range check on a device y is part of the call; run it for parity
+    int lo = 0, hi = 0;
+    if (y_op.handle()) {
+      check_cuda_status(function, smc_matrix_int_range(y_op.handle(), &lo, &hi));
+      check_nonnegative(function, "Vector of dependent variables", lo);
+    }
+    return 0;
+  }
+
+  row_operand<double, T_alpha> alpha_op(alpha);
+  const Eigen::VectorXd beta_val = host_values(beta);
+
+  auto ops_partials = make_partials_propagator(x, alpha, beta);
+  row_partial<T_alpha> d_alpha_vec(partials<1>(ops_partials), N);
+
+  const unsigned flags = (propto ? SMC_PROPTO : 0u) | var_flag<T_x>(SMC_VAR_X)
+                         | var_flag<T_alpha>(SMC_VAR_ALPHA)
+                         | var_flag<T_beta>(SMC_VAR_BETA);
+  double logp = 0, d_alpha = 0;
+  Eigen::VectorXd d_beta(K);
+  check_cuda_status(
+      function,
+      smc_poisson_log_glm(y_op.handle(), y_op.scalar(), x_handle(x),
+                              alpha_op.handle(), alpha_op.scalar(), beta_val.data(),
+                              flags, &logp, &d_alpha, d_alpha_vec.handle(),
+                              d_beta.data(), dx_handle<T_x>(partials<0>(ops_partials))));
+
+  // partials: d_x was written into the edge by the kernel (L151-152)
+  if constexpr (!is_constant_all<T_alpha>::value) {  // L155-161
+    if constexpr (is_stan_scalar<T_alpha>::value) {
+      store_host_partial<double>(partials<1>(ops_partials), &d_alpha, 1);
+    } else {
+      d_alpha_vec.store(partials<1>(ops_partials));
+    }
+  }
+  if constexpr (!is_constant_all<T_beta>::value) {  // L142
+    store_host_partial<T_beta>(partials<2>(ops_partials), d_beta.data(), K);
+  }
+  return ops_partials.build(logp);
+}
+
+// The propto = false forwarding overload is the reference's own
+// (prim/prob/poisson_log_glm_lpmf.hpp L165-170): its call to
+// poisson_log_glm_lpmf<false>(...) resolves to the overload above.
+
+}  // namespace math
+}  // namespace stan
+#endif

@@ -1,0 +1,33 @@
+"""Runs the C++ parity tests of the CUDA backend (tests/cpp/*.cpp) on the GPU.
+
+The binaries are built HERE against the reference's own headers
+(`make -C tests/cpp`, done by __graft_entry__.build() where /root/reference
+exists) and travel to the GPU box in tests/cpp/_build/.  Each one compares the
+`stan::math::<family>_glm_*` overloads taking device matrices with the
+reference's prim (Eigen) implementation -- linked into the same binary -- for
+every prim/var combination of the arguments (see tests/cpp/cuda_test_util.hpp).
+"""
+import os
+import re
+import subprocess
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+BUILD = os.path.join(HERE, "cpp", "_build")
+TESTS = ["matrix_cuda_test", "bernoulli_logit_glm_test", "poisson_log_glm_test",
+         "normal_id_glm_test", "neg_binomial_2_log_glm_test",
+         "ordered_logistic_glm_test", "categorical_logit_glm_test"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", TESTS)
+def test_cpp_backend(gpu, name):
+    exe = os.path.join(BUILD, name)
+    if not os.path.exists(exe):
+        pytest.fail(f"{exe} missing: run `make -C tests/cpp` where /root/reference exists")
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    tail = "\n".join((p.stdout + p.stderr).splitlines()[-40:])
+    assert p.returncode == 0, tail
+    m = re.search(r"\[  PASSED  \] (\d+) tests?", p.stdout)
+    assert m and int(m.group(1)) > 0, tail
