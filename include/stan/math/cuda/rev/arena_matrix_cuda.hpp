@@ -42,6 +42,13 @@ class arena_matrix_cuda : public matrix_cuda_base {
     m.zero();
     take(std::move(m));
   }
+  /** rows x cols owned by the arena, contents unspecified (the producer
+   * overwrites every element). */
+  static arena_matrix_cuda uninitialized(int64_t rows, int64_t cols) {
+    arena_matrix_cuda a;
+    a.take(matrix_cuda<T>(rows, cols));
+    return a;
+  }
   /** Moves an owning matrix into the arena. */
   explicit arena_matrix_cuda(matrix_cuda<T>&& m) { take(std::move(m)); }
   /** Arena-owned view: `m` must outlive the reverse sweep (data matrices do). */

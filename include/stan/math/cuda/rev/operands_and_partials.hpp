@@ -5,10 +5,12 @@
 // (stan/math/opencl/rev/operands_and_partials.hpp L16-31) and of the OpenCL
 // update_adjoints overload (rev/functor/operands_and_partials.hpp L28-38).
 //
-// The partial is a zero-initialised arena-owned device matrix with the shape of
-// the operand (as every host edge is, rev/functor/operands_and_partials.hpp
-// L100-184); the GLM kernel writes into it directly, and the reverse sweep runs
-// one device axpy:  x.adj() += ret.adj() * partial.
+// The partial is an arena-owned device matrix with the shape of the operand (as
+// every host edge is, rev/functor/operands_and_partials.hpp L100-184); the GLM
+// kernel writes EVERY element of it directly (so, unlike the host edges, it is
+// not zero-filled first: at N x K = 1e7 x 128 that memset alone would cost a
+// quarter of the evaluation), and the reverse sweep runs one device axpy:
+//   x.adj() += ret.adj() * partial.
 #include <stan/math/cuda/rev/vari.hpp>
 #include <stan/math/prim/functor/partials_propagator.hpp>
 #include <stan/math/rev/functor/operands_and_partials.hpp>
@@ -38,7 +40,7 @@ class ops_partials_edge<double, var_value<matrix_cuda<double>>, void> {
   partials_t partials_;
   broadcast_array<partials_t> partials_vec_;
   explicit ops_partials_edge(const var_value<matrix_cuda<double>>& ops)
-      : partials_(ops.rows(), ops.cols()),
+      : partials_(arena_matrix_cuda<double>::uninitialized(ops.rows(), ops.cols())),
         partials_vec_(partials_),
         operands_(ops) {}
   inline auto& partial() noexcept { return partials_; }

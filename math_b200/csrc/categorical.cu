@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "smc_internal.h"
+#include "tma_utils.cuh"
 
 namespace smc {
 
@@ -327,6 +328,313 @@ __global__ void cat_dbeta_finalize_kernel(const double* __restrict__ partials,
   }
 }
 
+// ======================================================================= TMA path
+// The two kernels above load DMMA fragments straight from global memory and
+// stall on those loads (ncu r01: DMMA pipe 59 % / 29 % busy).  The kernels below
+// keep the same fragment / accumulator layout but stage x (and T) tiles in a
+// shared-memory ring filled by TMA, so the consumer warps only ever wait on an
+// mbarrier and read fragments with LDS.  Out-of-range rows / columns of a box
+// are zero-filled by TMA and contribute nothing.
+//
+// pass 1  cat_lin_tma_kernel<NT>   CTA row block = 256 rows (8 warps x 32 rows);
+//         ring of {256 rows x 8 cols} x tiles (16 KB, 2 KB contiguous per column);
+//         the whole beta (C8 x (K + 4) doubles) resident in shared memory.
+// pass 2  cat_dbeta_tma_kernel<NT, MT>   CTA = contiguous row range x one chunk of
+//         64 MT attributes; ring of {16 rows x 64 MT cols} x tiles + {16 rows x C8}
+//         T tiles; rows of an 8-row block are paired (2 tig, 2 tig + 1) so each
+//         lane feeds two DMMAs from one 16-byte LDS.
+constexpr int kLinRows = 256;   // rows per CTA row block in pass 1
+constexpr int kLinCols = 8;     // columns per stage in pass 1
+constexpr int kLinStages = 4;
+constexpr int kDbRows = 16;     // rows per stage in pass 2
+constexpr int kDbStages = 3;
+
+template <int NT>
+__global__ void __launch_bounds__(kCatThreads, 1)
+    cat_lin_tma_kernel(const __grid_constant__ CUtensorMap tmx,
+                       const __grid_constant__ CatArgs a) {
+  extern __shared__ __align__(1024) unsigned char cat_smem[];
+  double* xs = reinterpret_cast<double*>(cat_smem);  // [stages][8 cols][256 rows]
+  double* beta_s = xs + (size_t)kLinStages * kLinCols * kLinRows;  // [C8][kstride]
+  double* alpha_s = beta_s + (size_t)a.C8 * a.kstride;            // [C8]
+  double* red_s = alpha_s + a.C8;                                 // [warps][2 + C8]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(red_s + kCatWarps * (2 + a.C8));
+  uint64_t* empty_bar = full_bar + kLinStages;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = lane >> 2, tig = lane & 3;
+  constexpr uint32_t stage_bytes = kLinCols * kLinRows * 8;
+
+  const int64_t nblocks = (a.N + kLinRows - 1) / kLinRows;
+  const int ksteps = (a.K + kLinCols - 1) / kLinCols;  // stages per row block
+  // this CTA's row blocks: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const int64_t my_blocks
+      = nblocks > blockIdx.x ? (nblocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t total = my_blocks * ksteps;  // stage loads of this CTA
+
+  // beta -> shared memory, zero padded: beta_s[c][k]
+  const int kpad = (a.K + 7) & ~7;
+  for (int idx = tid; idx < a.C8 * kpad; idx += kCatThreads) {
+    const int c = idx / kpad, k = idx - c * kpad;
+    beta_s[(size_t)c * a.kstride + k]
+        = (c < a.C && k < a.K) ? a.beta[(size_t)c * a.K + k] : 0.0;
+  }
+  for (int c = tid; c < a.C8; c += kCatThreads) alpha_s[c] = c < a.C ? a.alpha[c] : 0.0;
+  if (tid == 0) {
+    for (int st = 0; st < kLinStages; ++st) {
+      mbar_init(&full_bar[st], 1);
+      mbar_init(&empty_bar[st], kCatWarps);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  uint64_t pol = 0;
+  auto issue = [&](int64_t q) {  // q-th stage load of this CTA
+    const int st = (int)(q % kLinStages);
+    const int64_t blk = blockIdx.x + (q / ksteps) * gridDim.x;
+    const int ks = (int)(q % ksteps);
+    mbar_expect_tx(&full_bar[st], stage_bytes);
+    tma_load_2d(xs + (size_t)st * (stage_bytes / 8), &tmx, (int)(blk * kLinRows),
+                ks * kLinCols, &full_bar[st], pol);
+  };
+  if (tid == 0) {
+    pol = policy_evict_first();
+    for (int64_t q = 0; q < kLinStages && q < total; ++q) issue(q);
+  }
+
+  double lp_acc = 0.0, bad_acc = 0.0;
+  double dal[NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) dal[nt][0] = dal[nt][1] = 0.0;
+
+  int64_t q = 0;
+  for (int64_t b = 0; b < my_blocks; ++b) {
+    const int64_t r0 = (blockIdx.x + b * gridDim.x) * kLinRows + 32 * warp;
+    double acc[4][NT][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+
+    for (int ks = 0; ks < ksteps; ++ks, ++q) {
+      const int st = (int)(q % kLinStages);
+      const uint32_t ph = (uint32_t)(q / kLinStages) & 1u;
+      if (tid == 0 && q >= 1 && q - 1 + kLinStages < total) {
+        // refill the stage load q-1 used, once every warp has released it
+        mbar_wait(&empty_bar[(q - 1) % kLinStages],
+                  (uint32_t)((q - 1) / kLinStages) & 1u);
+        issue(q - 1 + kLinStages);
+      }
+      mbar_wait(&full_bar[st], ph);
+      // A fragments: x[r0 + 8 mt + grp][8 ks + 4 h + tig], h = 0, 1
+      const double* xa = xs + (size_t)st * (stage_bytes / 8) + (size_t)tig * kLinRows
+                         + 32 * warp + grp;
+      double af[2][4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) af[h][mt] = xa[(size_t)(4 * h) * kLinRows + 8 * mt];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[st]);
+      const double* bfrag = beta_s + (size_t)grp * a.kstride + ks * kLinCols + tig;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const double bf = bfrag[(size_t)(8 * nt) * a.kstride + 4 * h];
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) dmma(acc[mt][nt][0], acc[mt][nt][1], af[h][mt], bf);
+        }
+    }
+    if (r0 >= a.N) continue;
+
+    // ---- epilogue: softmax over the C classes of each row (held by a quad)
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      const int64_t row = r0 + 8 * mt + grp;
+      const bool valid = row < a.N;
+      const int yc = valid ? (a.y ? a.y[row] : a.y_scalar) - 1 : 0;
+      double m = -INFINITY;
+      double lin_y = 0.0;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int c = 8 * nt + 2 * tig + j;
+          double v = acc[mt][nt][j] + alpha_s[c];
+          acc[mt][nt][j] = v;
+          if (c < a.C) {
+            m = fmax(m, v);
+            if (c == yc) lin_y = v;
+          }
+        }
+      m = quad_max(m);
+      double se = 0.0;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int c = 8 * nt + 2 * tig + j;
+          const double e = c < a.C ? exp(acc[mt][nt][j] - m) : 0.0;
+          acc[mt][nt][j] = e;
+          se += e;
+        }
+      se = quad_sum(se);
+      lin_y = quad_sum(lin_y);
+      const double inv = 1.0 / se;
+      if (valid) {
+        if (tig == 0) {
+          const double t = (log(inv) - m) + lin_y;  // L106, L110-116
+          lp_acc += t;
+          bad_acc += isfinite(t) ? 0.0 : 1.0;
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int c = 8 * nt + 2 * tig + j;
+            double t = acc[mt][nt][j] * -inv;  // neg_softmax_lin, L158-159
+            if (c == yc) t += 1.0;             // the "+1 at class y_i" scatters
+            if (c >= a.C) t = 0.0;
+            a.T[(size_t)c * a.ldT + row] = t;
+            dal[nt][j] += t;
+          }
+      }
+    }
+  }
+
+  // ---- CTA reduction of logp / nonfinite / d_alpha partials (fixed order)
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      double v = dal[nt][j];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      dal[nt][j] = v;
+    }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    lp_acc += __shfl_xor_sync(0xffffffffu, lp_acc, o);
+    bad_acc += __shfl_xor_sync(0xffffffffu, bad_acc, o);
+  }
+  __syncthreads();
+  const int rs = 2 + a.C8;
+  if (lane == 0) {
+    red_s[warp * rs + 0] = lp_acc;
+    red_s[warp * rs + 1] = bad_acc;
+  }
+  if (grp == 0) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) red_s[warp * rs + 2 + 8 * nt + 2 * tig + j] = dal[nt][j];
+  }
+  __syncthreads();
+  for (int j = tid; j < rs; j += kCatThreads) {
+    double v = 0.0;
+    for (int w = 0; w < kCatWarps; ++w) v += red_s[w * rs + j];
+    a.partials[(size_t)blockIdx.x * rs + j] = v;
+  }
+}
+
+// pass 2: D[k][c] += x[i][k] T[i][c] over this CTA's rows.
+template <int NT, int MT>
+__global__ void __launch_bounds__(kCatThreads, 1)
+    cat_dbeta_tma_kernel(const __grid_constant__ CUtensorMap tmx,
+                         const __grid_constant__ CUtensorMap tmt,
+                         const __grid_constant__ CatArgs a) {
+  extern __shared__ __align__(1024) unsigned char cat_smem[];
+  constexpr int KC = kCatWarps * MT * 8;  // attributes per CTA
+  constexpr int XBOX = KC > 256 ? 256 : KC;
+  double* xs = reinterpret_cast<double*>(cat_smem);         // [stages][KC][16]
+  double* ts = xs + (size_t)kDbStages * KC * kDbRows;         // [stages][C8][16]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ts + (size_t)kDbStages * a.C8 * kDbRows);
+  uint64_t* empty_bar = full_bar + kDbStages;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = lane >> 2, tig = lane & 3;
+  const int kbase = blockIdx.y * KC;
+  const int64_t i_begin = (int64_t)blockIdx.x * a.rows_per_cta;
+  const int64_t i_end = min(a.N, i_begin + a.rows_per_cta);
+  const int ntiles = i_end > i_begin ? (int)((i_end - i_begin + kDbRows - 1) / kDbRows) : 0;
+  const uint32_t stage_bytes = (uint32_t)(KC + a.C8) * kDbRows * 8u;
+
+  if (tid == 0) {
+    for (int st = 0; st < kDbStages; ++st) {
+      mbar_init(&full_bar[st], 1);
+      mbar_init(&empty_bar[st], kCatWarps);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  uint64_t pol = 0;
+  auto issue = [&](int t) {
+    const int st = t % kDbStages;
+    const int row = (int)(i_begin + (int64_t)t * kDbRows);
+    mbar_expect_tx(&full_bar[st], stage_bytes);
+#pragma unroll
+    for (int c0 = 0; c0 < KC; c0 += XBOX)
+      tma_load_2d(xs + ((size_t)st * KC + c0) * kDbRows, &tmx, row, kbase + c0,
+                  &full_bar[st], pol);
+    tma_load_2d(ts + (size_t)st * a.C8 * kDbRows, &tmt, row, 0, &full_bar[st], pol);
+  };
+  if (tid == 0) {
+    pol = policy_evict_first();
+    for (int t = 0; t < kDbStages && t < ntiles; ++t) issue(t);
+  }
+
+  double acc[MT][NT][2];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+
+  for (int t = 0; t < ntiles; ++t) {
+    const int st = t % kDbStages;
+    if (tid == 0 && t >= 1 && t - 1 + kDbStages < ntiles) {
+      mbar_wait(&empty_bar[(t - 1) % kDbStages], (uint32_t)((t - 1) / kDbStages) & 1u);
+      issue(t - 1 + kDbStages);
+    }
+    mbar_wait(&full_bar[st], (uint32_t)(t / kDbStages) & 1u);
+    // rows of an 8-row block are consumed as {0,2,4,6} then {1,3,5,7}: lane tig
+    // holds rows 2 tig, 2 tig + 1 in one double2 (A and B use the same order)
+    const double* xa = xs + ((size_t)st * KC + warp * (MT * 8) + grp) * kDbRows + 2 * tig;
+    const double* tb = ts + ((size_t)st * a.C8 + grp) * kDbRows + 2 * tig;
+#pragma unroll
+    for (int h = 0; h < kDbRows / 8; ++h) {
+      double2 af[MT], bf[NT];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+        af[mt] = *reinterpret_cast<const double2*>(xa + (size_t)(8 * mt) * kDbRows + 8 * h);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+        bf[nt] = *reinterpret_cast<const double2*>(tb + (size_t)(8 * nt) * kDbRows + 8 * h);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          dmma(acc[mt][nt][0], acc[mt][nt][1], af[mt].x, bf[nt].x);
+          dmma(acc[mt][nt][0], acc[mt][nt][1], af[mt].y, bf[nt].y);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[st]);
+  }
+  double* part = a.partials
+                 + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * ((size_t)KC * a.C8);
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int kl = warp * (MT * 8) + 8 * mt + grp;
+        const int c = 8 * nt + 2 * tig + j;
+        part[(size_t)kl * a.C8 + c] = acc[mt][nt][j];
+      }
+}
+
 // ----------------------------------------------------------------- d_x = T beta^T
 // One thread per row, T row in registers, beta broadcast from global (L1).
 template <int CMAX>
@@ -366,6 +674,46 @@ static int run_dbeta(const CatArgs& a, dim3 grid) {
   cat_dbeta_kernel<NT, MT><<<grid, kCatThreads, 0, ctx().stream>>>(a);
   SMC_CUDA(cudaGetLastError());
   return SMC_OK;
+}
+
+template <int NT>
+static int run_lin_tma(const CUtensorMap& tmx, const CatArgs& a, int grid, size_t smem) {
+  static size_t attr[16] = {};
+  Context& c = ctx();
+  if (attr[c.device & 15] < smem) {
+    SMC_CUDA(cudaFuncSetAttribute(cat_lin_tma_kernel<NT>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    attr[c.device & 15] = smem;
+  }
+  cat_lin_tma_kernel<NT><<<grid, kCatThreads, smem, c.stream>>>(tmx, a);
+  SMC_CUDA(cudaGetLastError());
+  return SMC_OK;
+}
+
+template <int NT, int MT>
+static int run_dbeta_tma(const CUtensorMap& tmx, const CUtensorMap& tmt,
+                         const CatArgs& a, dim3 grid, size_t smem) {
+  static size_t attr[16] = {};
+  Context& c = ctx();
+  if (attr[c.device & 15] < smem) {
+    SMC_CUDA(cudaFuncSetAttribute(cat_dbeta_tma_kernel<NT, MT>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    attr[c.device & 15] = smem;
+  }
+  cat_dbeta_tma_kernel<NT, MT><<<grid, kCatThreads, smem, c.stream>>>(tmx, tmt, a);
+  SMC_CUDA(cudaGetLastError());
+  return SMC_OK;
+}
+
+static bool cat_tma_ok(const smc_matrix* x) {
+  const char* force = getenv("SMC_CAT_NO_TMA");
+  if (force && force[0] == '1') return false;
+  if (!get_encode()) return false;
+  if ((reinterpret_cast<uintptr_t>(x->data) & 15) != 0) return false;
+  if (x->cols > 1 && (x->ld & 1)) return false;
+  return x->rows < 0x7fffff00ll && x->cols >= 1;
 }
 
 int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
@@ -409,7 +757,19 @@ int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
     kchunk = ((kchunk / 2) + 7) & ~7;
   a.kchunk = kchunk;
   a.kstride = kchunk + 4;
-  const size_t smem1 = (size_t)a.C8 * a.kstride * 8 + fixed;
+  size_t smem1 = (size_t)a.C8 * a.kstride * 8 + fixed;
+  // TMA-staged kernels when x is TMA-addressable and the whole beta fits
+  const bool tma = cat_tma_ok(x);
+  const size_t smem1_tma = (size_t)kLinStages * kLinCols * kLinRows * 8
+                           + (size_t)a.C8 * ((((size_t)a.K + 7) & ~(size_t)7) + 4) * 8
+                           + (size_t)a.C8 * 8 + (size_t)kCatWarps * (2 + a.C8) * 8
+                           + 2 * kLinStages * 8 + 64;
+  const bool lin_tma = tma && smem1_tma <= 224 * 1024;
+  if (lin_tma) {
+    a.kchunk = (a.K + 7) & ~7;
+    a.kstride = a.kchunk + 4;
+    smem1 = smem1_tma;
+  }
 
   const bool need_beta = flags & SMC_VAR_BETA;
   const bool need_dx = (flags & SMC_VAR_X) && d_x;
@@ -420,14 +780,19 @@ int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
   int nbx = cx.sm_count / (nby > 0 ? nby : 1);
   if (nbx < 1) nbx = 1;
   int64_t rpc = (a.N + nbx - 1) / nbx;
-  rpc = (rpc + 3) & ~3ll;
-  if (rpc < 4) rpc = 4;
+  rpc = (rpc + kDbRows - 1) / kDbRows * kDbRows;  // whole 16-row tiles per CTA
+  if (rpc < kDbRows) rpc = kDbRows;
   nbx = (int)((a.N + rpc - 1) / rpc);
   a.rows_per_cta = (int)rpc;
 
   const int64_t ntiles = (a.N + 31) / 32;
   int grid1 = (int)((ntiles + kCatWarps - 1) / kCatWarps);
   if (grid1 > cx.sm_count) grid1 = cx.sm_count;
+  CUtensorMap tm_lin, tm_dbx, tm_dbt;
+  if (lin_tma
+      && encode_tmap_f64(&tm_lin, x->data, x->rows, x->cols, x->ld, kLinRows, kLinCols)
+             != CUDA_SUCCESS)
+    return fail(SMC_ERR_CUDA, "cuTensorMapEncodeTiled failed (categorical pass 1)");
   const int rs = 2 + a.C8;
 
   // scratch: T (ldT x C8), out (rs), d_beta_dev (K*C), partials
@@ -449,6 +814,18 @@ int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
   a.ld_dx = need_dx ? d_x->ld : 0;
 
   int rc = SMC_OK;
+  if (lin_tma) {
+    switch (NT) {
+      case 1: rc = run_lin_tma<1>(tm_lin, a, grid1, smem1); break;
+      case 2: rc = run_lin_tma<2>(tm_lin, a, grid1, smem1); break;
+      case 3: rc = run_lin_tma<3>(tm_lin, a, grid1, smem1); break;
+      case 4: rc = run_lin_tma<4>(tm_lin, a, grid1, smem1); break;
+      case 5: rc = run_lin_tma<5>(tm_lin, a, grid1, smem1); break;
+      case 6: rc = run_lin_tma<6>(tm_lin, a, grid1, smem1); break;
+      case 7: rc = run_lin_tma<7>(tm_lin, a, grid1, smem1); break;
+      default: rc = run_lin_tma<8>(tm_lin, a, grid1, smem1); break;
+    }
+  } else
   switch (NT) {
     case 1: rc = run_lin<1>(a, grid1, smem1); break;
     case 2: rc = run_lin<2>(a, grid1, smem1); break;
@@ -468,6 +845,26 @@ int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
 
   if (need_beta && a.K > 0) {
     dim3 g2(nbx, nby);
+    const size_t smem2 = (size_t)kDbStages * (kchunk2 + a.C8) * kDbRows * 8
+                         + 2 * kDbStages * 8 + 64;
+    if (tma) {
+      const int xbox = kchunk2 > 256 ? 256 : kchunk2;
+      if (encode_tmap_f64(&tm_dbx, x->data, x->rows, x->cols, x->ld, kDbRows, xbox)
+              != CUDA_SUCCESS
+          || encode_tmap_f64(&tm_dbt, a.T, a.N, a.C8, a.ldT, kDbRows, a.C8)
+                 != CUDA_SUCCESS)
+        return fail(SMC_ERR_CUDA, "cuTensorMapEncodeTiled failed (categorical pass 2)");
+      switch (NT) {
+        case 1: rc = run_dbeta_tma<1, 8>(tm_dbx, tm_dbt, a, g2, smem2); break;
+        case 2: rc = run_dbeta_tma<2, 8>(tm_dbx, tm_dbt, a, g2, smem2); break;
+        case 3: rc = run_dbeta_tma<3, 8>(tm_dbx, tm_dbt, a, g2, smem2); break;
+        case 4: rc = run_dbeta_tma<4, 8>(tm_dbx, tm_dbt, a, g2, smem2); break;
+        case 5: rc = run_dbeta_tma<5, 4>(tm_dbx, tm_dbt, a, g2, smem2); break;
+        case 6: rc = run_dbeta_tma<6, 4>(tm_dbx, tm_dbt, a, g2, smem2); break;
+        case 7: rc = run_dbeta_tma<7, 4>(tm_dbx, tm_dbt, a, g2, smem2); break;
+        default: rc = run_dbeta_tma<8, 4>(tm_dbx, tm_dbt, a, g2, smem2); break;
+      }
+    } else
     switch (NT) {
       case 1: rc = run_dbeta<1, 8>(a, g2); break;
       case 2: rc = run_dbeta<2, 8>(a, g2); break;

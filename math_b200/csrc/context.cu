@@ -68,6 +68,15 @@ static int bind_device(int device) {
   c.stream = c.own_stream;
   SMC_CUDA(cudaMalloc(&c.counter, 64));
   SMC_CUDA(cudaMemset(c.counter, 0, 64));
+  {
+    // matrices come from the device's stream-ordered pool; keep freed blocks
+    // cached so the per-evaluation arena buffers (N-vector partials, the N x K
+    // d_x of an autodiff x) are recycled instead of going back to the driver
+    cudaMemPool_t pool;
+    SMC_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = UINT64_MAX;
+    SMC_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   c.inited = true;
   return SMC_OK;
 }
@@ -257,10 +266,10 @@ int smc_matrix_create(int64_t rows, int64_t cols, int dtype, smc_matrix** out) {
   m->ld = cols > 1 ? (rows + align - 1) / align * align : rows;
   if (m->ld < 1) m->ld = 1;
   const size_t bytes = (size_t)m->ld * (size_t)(cols > 0 ? cols : 1) * elem_size(dtype);
-  cudaError_t e = cudaMalloc(&m->data, bytes < 256 ? 256 : bytes);
+  cudaError_t e = cudaMallocAsync(&m->data, bytes < 256 ? 256 : bytes, ctx().stream);
   if (e != cudaSuccess) {
     delete m;
-    return fail(SMC_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", bytes,
+    return fail(SMC_ERR_CUDA, "cudaMallocAsync(%zu bytes) failed: %s", bytes,
                 cudaGetErrorString(e));
   }
   m->owned = true;
@@ -290,8 +299,9 @@ int smc_matrix_free(smc_matrix* m) {
   if (!m) return SMC_OK;
   if (m->owned && m->data) {
     if (int rc = ensure_ctx()) return rc;
-    SMC_CUDA(cudaStreamSynchronize(ctx().stream));
-    SMC_CUDA(cudaFree(m->data));
+    // stream-ordered: the block returns to the pool once everything queued
+    // on this thread's stream so far has run
+    SMC_CUDA(cudaFreeAsync(m->data, ctx().stream));
   }
   delete m;
   return SMC_OK;

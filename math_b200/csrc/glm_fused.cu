@@ -30,72 +30,17 @@
 #include <cstring>
 
 #include "glm_link.cuh"
+#include "tma_utils.cuh"
 
 namespace smc {
 
 constexpr int kStages = 3;
 constexpr int kCutsPerThread = 4;
 
-// ------------------------------------------------------------------ PTX glue
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(count));
-}
-__device__ __forceinline__ void fence_barrier_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-// TMA: 2-D tiled bulk tensor load global -> shared, completion on an mbarrier.
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map,
-                                            int c0, int c1, uint64_t* bar,
-                                            uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::"
-      "bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1),
-      "r"(smem_u32(bar)), "l"(policy)
-      : "memory");
-}
-__device__ __forceinline__ uint64_t policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ void group_bar(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ void st_stream(double* p, double v) {
-  asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+__host__ __device__ inline int link_tab_doubles(int fam, int ncuts, int tab_n) {
+  if (fam == kOrdered) return 4 * (ncuts + 1);
+  if (fam == kNegBinomial) return 2 * tab_n;
+  return 0;
 }
 
 // ------------------------------------------------------------------- the kernel
@@ -144,6 +89,10 @@ __global__ void __launch_bounds__(256, 1)
   p += (size_t)CW * 8;
   double* cuts_s = reinterpret_cast<double*>(p);  // ncuts (padded) doubles
   p += (size_t)((a.ncuts + 1) & ~1) * 8;
+  // link tables: ordered -> 4 doubles per class; neg-binomial -> lgamma / digamma
+  // of (y + phi) for y < tab_n
+  double* tab_s = reinterpret_cast<double*>(p);
+  p += (size_t)link_tab_doubles(FAM, a.ncuts, a.tab_n) * 8;
   double* partial_s = reinterpret_cast<double*>(p);  // [2][S][R]
   p += (size_t)2 * S * R * 8;
   double* d1_s = reinterpret_cast<double*>(p);  // [2][R] (ordered)
@@ -162,6 +111,25 @@ __global__ void __launch_bounds__(256, 1)
   const double* params = a.params_dev ? a.params_dev : a.inline_params;
   for (int j = tid; j < CW; j += blockDim.x) beta_s[j] = j < a.K ? params[j] : 0.0;
   for (int j = tid; j < a.ncuts; j += blockDim.x) cuts_s[j] = params[a.K + j];
+  LinkTab tab;
+  tab.cuts = cuts_s;
+  if constexpr (FAM == kOrdered) {
+    tab.cls = tab_s;
+    for (int c = 1 + tid; c <= a.ncuts + 1; c += blockDim.x)
+      ordered_class_entry(params + a.K, a.ncuts, c, tab_s + 4 * (c - 1));
+  }
+  if constexpr (FAM == kNegBinomial) {
+    if (a.tab_n > 0) {
+      tab.lg = tab_s;
+      tab.dg = tab_s + a.tab_n;
+      tab.tab_n = a.tab_n;
+      const bool need_dg = a.flags & SMC_VAR_AUX;
+      for (int j = tid; j < a.tab_n; j += blockDim.x) {
+        tab_s[j] = lgamma((double)j + a.aux);
+        tab_s[a.tab_n + j] = need_dg ? digamma((double)j + a.aux) : 0.0;
+      }
+    }
+  }
   if (tid == 0) {
     for (int st = 0; st < kStages; ++st) {
       mbar_init(&full_bar[st], 1);
@@ -269,7 +237,7 @@ __global__ void __launch_bounds__(256, 1)
 
       double d1 = 0, d2 = 0;
       const double d
-          = link_row<FAM>(a, xb, in, valid, lead, row, racc, cuts_s, d1, d2);
+          = link_row<FAM>(a, xb, in, valid, lead, row, racc, tab, d1, d2);
 
       if (need_beta) {
 #pragma unroll
@@ -393,27 +361,6 @@ __global__ void __launch_bounds__(256, 1)
 }
 
 // ---------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
-                                  void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault,
-                                &q)
-            == cudaSuccess
-        && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
 static void tile_shape(int64_t K, int* S, int* G) {
   int s = (int)((K + kColsPerThread - 1) / kColsPerThread);
   if (s < 1) s = 1;
@@ -438,17 +385,8 @@ static int get_tmap(const smc_matrix* xc, int R, int CW, CUtensorMap* out) {
     *out = x->tmap;
     return SMC_OK;
   }
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return fail(SMC_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
-  cuuint64_t gdim[2] = {(cuuint64_t)x->rows, (cuuint64_t)x->cols};
-  cuuint64_t gstr[1] = {(cuuint64_t)x->ld * 8};
-  if (x->cols == 1) gstr[0] = (cuuint64_t)((x->rows + 1) & ~1ll) * 8;
-  cuuint32_t box[2] = {(cuuint32_t)R, (cuuint32_t)CW};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(&x->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, x->data, gdim,
-                   gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (!get_encode()) return fail(SMC_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  CUresult r = encode_tmap_f64(&x->tmap, x->data, x->rows, x->cols, x->ld, R, CW);
   if (r != CUDA_SUCCESS)
     return fail(SMC_ERR_CUDA,
                 "cuTensorMapEncodeTiled failed (%d) for %lld x %lld ld %lld box "
@@ -536,7 +474,9 @@ int launch_glm_fused(const GlmCall& c) {
 
   const size_t stage_bytes = (size_t)R * CW * 8;
   size_t smem = kStages * stage_bytes + (size_t)CW * 8
-                + (size_t)((a.ncuts + 1) & ~1) * 8 + (size_t)2 * a.S * R * 8
+                + (size_t)((a.ncuts + 1) & ~1) * 8
+                + (size_t)link_tab_doubles(c.family, a.ncuts, a.tab_n) * 8
+                + (size_t)2 * a.S * R * 8
                 + (size_t)4 * R * 8 + (size_t)2 * R * 4 + 8 + 2 * kStages * 8;
   const size_t red_bytes = (size_t)a.G * a.pstride * 8;
   if (red_bytes > kStages * stage_bytes)

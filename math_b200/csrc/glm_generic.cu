@@ -63,6 +63,13 @@ int prepare_args(const GlmCall& c, FusedArgs* ap) {
         a.c0 -= lg;
       }
       if (c.family == kNegBinomial && !c.aux_vec) {
+        // lgamma(y + phi) / digamma(y + phi) tables cover y in [0, tab_n)
+        int lo = 0, hi = (int)c.y_scalar;
+        if (c.y) {
+          if (int rc = y_range(c.y, &lo, &hi)) return rc;
+        }
+        if (!propto || (c.flags & SMC_VAR_AUX))
+          a.tab_n = hi + 1 < kMaxLgammaTab ? (hi + 1 > 0 ? hi + 1 : 0) : kMaxLgammaTab;
         a.log_aux = std::log(c.aux);
         a.digamma_aux = digamma(c.aux);
         // N (phi log phi - lgamma phi), L177-182 (multiply_log(0,0) = 0)
@@ -100,7 +107,8 @@ __global__ void __launch_bounds__(kGenThreads)
                         double* __restrict__ block_partials) {
   __shared__ double sh[kGenThreads / 32];
   RowAcc racc;
-  const double* cuts = params + a.K;
+  LinkTab tab;
+  tab.cuts = params + a.K;
   for (int64_t row = blockIdx.x * (int64_t)kGenThreads + threadIdx.x; row < a.N;
        row += (int64_t)gridDim.x * kGenThreads) {
     double xb = 0.0;
@@ -114,7 +122,7 @@ __global__ void __launch_bounds__(kGenThreads)
     in.alpha = a.alpha_vec ? a.alpha_vec[row] : a.alpha;
     in.aux = a.aux_vec ? a.aux_vec[row] : a.aux;
     double d1 = 0, d2 = 0;
-    const double d = link_row<FAM>(a, xb, in, true, true, row, racc, cuts, d1, d2);
+    const double d = link_row<FAM>(a, xb, in, true, true, row, racc, tab, d1, d2);
     dvec[row] = d;
     if constexpr (FAM == kOrdered) {
       d1v[row] = d1;

@@ -36,8 +36,41 @@ struct FusedArgs {
   unsigned int* counter;
   double* out;
   double c0;
+  int tab_n;  // neg-binomial, scalar phi: rows with y < tab_n read lgamma / digamma
+              // of (y + phi) from a per-CTA table instead of evaluating them
   double inline_params[kMaxParamDoubles];
 };
+
+// Per-CTA lookup tables that take row-independent transcendentals out of the
+// per-row link (values are produced by the very same expressions, so results
+// are bit-identical to evaluating them per row):
+//   ordered   cls[4 c' .. 4 c' + 3], c' = class - 1:  c1, c2 (the two cut points
+//             of the class, +-inf at the ends), ed / (ed - 1), 1 / (1 - ed) with
+//             ed = exp(c2 - c1)          (ordered_logistic_glm_lpmf.hpp L108-121, L165-174)
+//   neg-binomial (scalar phi)  lg[y] = lgamma(y + phi), dg[y] = digamma(y + phi)
+//             for integer y < tab_n     (neg_binomial_2_log_glm_lpmf.hpp L189-195, L235-244)
+// Null pointers mean "evaluate per row" (the general two-pass path).
+struct LinkTab {
+  const double* cuts = nullptr;
+  const double* cls = nullptr;
+  const double* lg = nullptr;
+  const double* dg = nullptr;
+  int tab_n = 0;
+};
+
+constexpr int kMaxLgammaTab = 512;
+
+__device__ __forceinline__ void ordered_class_entry(const double* cuts, int ncuts,
+                                                    int c, double* e) {
+  const int C = ncuts + 1;
+  const double c1 = c != C ? cuts[c - 1] : __longlong_as_double(0x7ff0000000000000ll);
+  const double c2 = c != 1 ? cuts[c - 2] : __longlong_as_double(0xfff0000000000000ll);
+  const double ed = exp(c2 - c1);
+  e[0] = c1;
+  e[1] = c2;
+  e[2] = ed / (ed - 1.0);
+  e[3] = 1.0 / (1.0 - ed);
+}
 
 // Fills everything in `a` that does not depend on the kernel variant: shapes,
 // pointers, flags, host-side constants of the log density (c0, log phi, ...).
@@ -63,7 +96,7 @@ template <int FAM>
 __device__ __forceinline__ double link_row(const FusedArgs& a, double xb,
                                            const RowIn<FAM>& in, bool valid,
                                            bool lead, int64_t row, RowAcc& acc,
-                                           const double* cuts_s, double& d1o,
+                                           const LinkTab& tab, double& d1o,
                                            double& d2o) {
   double d = 0, lp = 0, s2 = 0, s3 = 0;
   int bad = 0;
@@ -73,7 +106,8 @@ __device__ __forceinline__ double link_row(const FusedArgs& a, double xb,
     const double e = exp(-t);
     // bernoulli_logit_glm_lpmf.hpp L120-126 / L137-142 (the t > 20 derivative
     // branch is -e whatever the sign: reproduced for parity)
-    lp = t > 20.0 ? -e : (t < -20.0 ? t : -log1p(e));
+    // only the lead warp of a row group owns the log-density sum
+    if (lead) lp = t > 20.0 ? -e : (t < -20.0 ? t : -log1p(e));
     d = t > 20.0 ? -e : (t < -20.0 ? sgn : sgn * e / (e + 1.0));
     bad = !isfinite(t);
     if (lead && valid && a.d_alpha_vec) a.d_alpha_vec[row] = d;
@@ -119,8 +153,10 @@ __device__ __forceinline__ double link_row(const FusedArgs& a, double xb,
     const double te = exp(th);
     d = in.y - te * ypp / (te + ph);  // L203-204
     if (lead && valid) {
+      const int yi = (int)in.y;
+      const bool in_tab = tab.lg != nullptr && yi < tab.tab_n;
       if (inc_phi) {
-        lp += lgamma(ypp);  // L189-195
+        lp += in_tab ? tab.lg[yi] : lgamma(ypp);  // L189-195
         if (a.aux_vec) lp += multiply_log(ph, ph) - lgamma(ph);  // L171-176
       }
       if (!propto && a.y == nullptr) {
@@ -128,8 +164,9 @@ __device__ __forceinline__ double link_row(const FusedArgs& a, double xb,
       }
       if (a.flags & SMC_VAR_AUX) {
         const double dg_phi = a.aux_vec ? digamma(ph) : a.digamma_aux;
-        const double dp = 1.0 - ypp / (te + ph) + log_phi - lse + digamma(ypp)
-                          - dg_phi;  // L235-244
+        const double dg_ypp = in_tab ? tab.dg[yi] : digamma(ypp);
+        const double dp
+            = 1.0 - ypp / (te + ph) + log_phi - lse + dg_ypp - dg_phi;  // L235-244
         if (a.d_aux_vec)
           a.d_aux_vec[row] = dp;
         else
@@ -140,27 +177,38 @@ __device__ __forceinline__ double link_row(const FusedArgs& a, double xb,
   } else if constexpr (FAM == kOrdered) {
     const int C = a.ncuts + 1;
     const int c = valid ? (int)in.y : 1;
-    // ordered_logistic_glm_lpmf.hpp L108-121
-    const double c1 = c != C ? cuts_s[c - 1] : __longlong_as_double(0x7ff0000000000000ll);
-    const double c2 = c != 1 ? cuts_s[c - 2] : __longlong_as_double(0xfff0000000000000ll);
-    const double cut2 = xb - c2, cut1 = xb - c1;  // L129-132
-    const double A = (cut1 > 0.0 ? -cut1 : 0.0) - log1p(exp(-fabs(cut1)));
-    const double B = (cut2 <= 0.0 ? cut2 : 0.0) - log1p(exp(-fabs(cut2)));
-    if (c == 1)
-      lp = A;
-    else if (c == C)
-      lp = B;
-    else
-      lp = B + log1m_exp(cut1 - cut2) + A;  // L141-161
-    const double em1 = exp(-cut1), em2 = exp(-cut2), ed = exp(c2 - c1);
-    const double d1 = (cut2 > 0.0 ? em2 / (1.0 + em2) : 1.0 / (1.0 + exp(cut2)))
-                      - ed / (ed - 1.0);  // L168-170
-    const double d2 = 1.0 / (1.0 - ed)
-                      - (cut1 > 0.0 ? em1 / (1.0 + em1)
-                                    : 1.0 / (1.0 + exp(cut1)));  // L171-174
+    // ordered_logistic_glm_lpmf.hpp L108-121 and the class-only factors of L165-174
+    double ce[4];
+    if (tab.cls) {
+      const double2 v0 = *reinterpret_cast<const double2*>(tab.cls + 4 * (c - 1));
+      const double2 v1 = *reinterpret_cast<const double2*>(tab.cls + 4 * (c - 1) + 2);
+      ce[0] = v0.x;
+      ce[1] = v0.y;
+      ce[2] = v1.x;
+      ce[3] = v1.y;
+    } else {
+      ordered_class_entry(tab.cuts, a.ncuts, c, ce);
+    }
+    const double cut2 = xb - ce[1], cut1 = xb - ce[0];  // L129-132
+    // exp(-|cut|) serves both the stable log1p_exp forms (L135-138) and the
+    // stable inv_logit selects (L168-174): for cut > 0 it IS exp(-cut), for
+    // cut <= 0 it IS exp(cut) -- same argument, same bits
+    const double e1 = exp(-fabs(cut1)), e2 = exp(-fabs(cut2));
+    const double d1 = (cut2 > 0.0 ? e2 / (1.0 + e2) : 1.0 / (1.0 + e2)) - ce[2];
+    const double d2 = ce[3] - (cut1 > 0.0 ? e1 / (1.0 + e1) : 1.0 / (1.0 + e1));
     d = d1 - d2;
     d1o = d1;
     d2o = d2;
+    if (lead) {
+      const double A = (cut1 > 0.0 ? -cut1 : 0.0) - log1p(e1);
+      const double B = (cut2 <= 0.0 ? cut2 : 0.0) - log1p(e2);
+      if (c == 1)
+        lp = A;
+      else if (c == C)
+        lp = B;
+      else
+        lp = B + log1m_exp(cut1 - cut2) + A;  // L141-161
+    }
     s3 = xb;  // sum(location) for the lazy finiteness check, L124
   }
   if (!valid) return 0.0;
