@@ -36,6 +36,7 @@ namespace smc {
 
 constexpr int kStages = 3;
 constexpr int kCutsPerThread = 4;
+constexpr int kFastCuts = 16;  // up to this many cut points: lane-private d_cuts slots
 
 __host__ __device__ inline int link_tab_doubles(int fam, int ncuts, int tab_n) {
   if (fam == kOrdered) return 4 * (ncuts + 1);
@@ -93,6 +94,11 @@ __global__ void __launch_bounds__(256, 1)
   // of (y + phi) for y < tab_n
   double* tab_s = reinterpret_cast<double*>(p);
   p += (size_t)link_tab_doubles(FAM, a.ncuts, a.tab_n) * 8;
+  // ordered, few cut points: d_cuts accumulators [G][ncuts][32 lanes], one
+  // private slot per (cut, lane) of each row group's lead warp
+  const bool fast_cuts = FAM == kOrdered && a.ncuts <= kFastCuts;
+  double* cacc_s = reinterpret_cast<double*>(p);
+  if (fast_cuts) p += (size_t)G * a.ncuts * 32 * 8;
   double* partial_s = reinterpret_cast<double*>(p);  // [2][S][R]
   p += (size_t)2 * S * R * 8;
   double* d1_s = reinterpret_cast<double*>(p);  // [2][R] (ordered)
@@ -111,6 +117,8 @@ __global__ void __launch_bounds__(256, 1)
   const double* params = a.params_dev ? a.params_dev : a.inline_params;
   for (int j = tid; j < CW; j += blockDim.x) beta_s[j] = j < a.K ? params[j] : 0.0;
   for (int j = tid; j < a.ncuts; j += blockDim.x) cuts_s[j] = params[a.K + j];
+  if (fast_cuts)
+    for (int j = tid; j < G * a.ncuts * 32; j += blockDim.x) cacc_s[j] = 0.0;
   LinkTab tab;
   tab.cuts = cuts_s;
   if constexpr (FAM == kOrdered) {
@@ -250,10 +258,18 @@ __global__ void __launch_bounds__(256, 1)
           if (32 * s + kk < a.K) st_stream(dx + (size_t)kk * a.ld_dx, bs[kk] * d);
       }
       if constexpr (FAM == kOrdered) {
-        if (need_cuts) {
-          // ordered_logistic_glm_lpmf.hpp L197-207: scatter d2 / -d1 into the
-          // cut of each row's class -- done as an owner-computes loop so the
-          // order of additions is fixed.
+        if (need_cuts && fast_cuts) {
+          // ordered_logistic_glm_lpmf.hpp L197-207: cuts'[y-1] += d2, cuts'[y-2] -= d1.
+          // Each lane of the lead warp owns a private slot per cut point, so the
+          // scatter is conflict-free and its order of additions is fixed.
+          if (lead && valid) {
+            const int yy = (int)in.y;
+            double* cs = cacc_s + (size_t)g * a.ncuts * 32 + lane;
+            if (yy - 1 < a.ncuts) cs[(yy - 1) * 32] += d2;
+            if (yy >= 2) cs[(yy - 2) * 32] -= d1;
+          }
+        } else if (need_cuts) {
+          // many cut points: owner-computes loop over the rows of the tile
           if (lead) {
             d1_s[par * R + rloc] = d1;
             d2_s[par * R + rloc] = d2;
@@ -306,7 +322,13 @@ __global__ void __launch_bounds__(256, 1)
         red[g * ps + SMC_OUT_AUX2] = v3;
       }
     }
-    if (need_cuts) {
+    if (need_cuts && fast_cuts) {
+      if (lead)
+        for (int c = 0; c < a.ncuts; ++c) {
+          const double v = warp_sum(cacc_s[((size_t)g * a.ncuts + c) * 32 + lane]);
+          if (lane == 0) red[g * ps + kHdr + CW + c] = v;
+        }
+    } else if (need_cuts) {
       const int tg = s * 32 + lane;
 #pragma unroll
       for (int j = 0; j < kCutsPerThread; ++j) {
@@ -476,6 +498,9 @@ int launch_glm_fused(const GlmCall& c) {
   size_t smem = kStages * stage_bytes + (size_t)CW * 8
                 + (size_t)((a.ncuts + 1) & ~1) * 8
                 + (size_t)link_tab_doubles(c.family, a.ncuts, a.tab_n) * 8
+                + (c.family == kOrdered && a.ncuts <= kFastCuts
+                       ? (size_t)a.G * a.ncuts * 32 * 8
+                       : 0)
                 + (size_t)2 * a.S * R * 8
                 + (size_t)4 * R * 8 + (size_t)2 * R * 4 + 8 + 2 * kStages * 8;
   const size_t red_bytes = (size_t)a.G * a.pstride * 8;

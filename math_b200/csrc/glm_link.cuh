@@ -139,28 +139,27 @@ __device__ __forceinline__ double link_row(const FusedArgs& a, double xb,
     const double ph = in.aux;
     // check_finite(theta) L152; check_positive_finite(phi) L130 for vector phi
     bad = !isfinite(th) || (a.aux_vec && (!(ph > 0.0) || !isfinite(ph)));
-    const double log_phi = a.aux_vec ? log(ph) : a.log_aux;
-    // neg_binomial_2_log_glm_lpmf.hpp L154-157
-    const double lse = th > log_phi ? th + log1p_exp(log_phi - th)
-                                    : log_phi + log1p_exp(th - log_phi);
     const double ypp = in.y + ph;
-    const bool propto = a.flags & SMC_PROPTO;
-    const bool inc_phi = !propto || (a.flags & SMC_VAR_AUX);
-    const bool inc_lin
-        = !propto || (a.flags & (SMC_VAR_X | SMC_VAR_ALPHA | SMC_VAR_BETA));
-    lp = -ypp * lse;              // L184
-    if (inc_lin) lp += in.y * th;  // L186-188
     const double te = exp(th);
     d = in.y - te * ypp / (te + ph);  // L203-204
+    // everything else feeds the log density and d_phi, which only the lead warp
+    // of a row group accumulates
     if (lead && valid) {
+      const bool propto = a.flags & SMC_PROPTO;
+      const bool inc_phi = !propto || (a.flags & SMC_VAR_AUX);
+      const bool inc_lin
+          = !propto || (a.flags & (SMC_VAR_X | SMC_VAR_ALPHA | SMC_VAR_BETA));
+      const double log_phi = a.aux_vec ? log(ph) : a.log_aux;
+      // neg_binomial_2_log_glm_lpmf.hpp L154-157
+      const double lse = th > log_phi ? th + log1p_exp(log_phi - th)
+                                      : log_phi + log1p_exp(th - log_phi);
+      lp = -ypp * lse;               // L184
+      if (inc_lin) lp += in.y * th;  // L186-188
       const int yi = (int)in.y;
       const bool in_tab = tab.lg != nullptr && yi < tab.tab_n;
       if (inc_phi) {
         lp += in_tab ? tab.lg[yi] : lgamma(ypp);  // L189-195
         if (a.aux_vec) lp += multiply_log(ph, ph) - lgamma(ph);  // L171-176
-      }
-      if (!propto && a.y == nullptr) {
-        // scalar y broadcast: host adds N * lgamma(y+1); nothing here
       }
       if (a.flags & SMC_VAR_AUX) {
         const double dg_phi = a.aux_vec ? digamma(ph) : a.digamma_aux;
