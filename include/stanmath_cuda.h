@@ -78,6 +78,10 @@ int smc_get_device(int* device);
  * NULL restores the library's own non-blocking stream. */
 int smc_set_stream(void* cuda_stream);
 int smc_synchronize(void);
+/* Device blocks of freed matrices are kept by the calling thread for reuse (an
+ * HMC run re-creates the same arena buffers every evaluation); this returns
+ * them to the driver.  Done automatically when an allocation fails. */
+int smc_trim_cache(void);
 int smc_device_info(int* sm_count, int* cc_major, int* cc_minor,
                     size_t* free_bytes, size_t* total_bytes);
 const char* smc_last_error(void);

@@ -38,6 +38,7 @@ SIGNATURES = {
     "smc_get_device": (_I, [C.POINTER(_I)]),
     "smc_set_stream": (_I, [_P]),
     "smc_synchronize": (_I, []),
+    "smc_trim_cache": (_I, []),
     "smc_device_info": (_I, [C.POINTER(_I), C.POINTER(_I), C.POINTER(_I),
                              C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "smc_last_error": (C.c_char_p, []),

@@ -53,6 +53,8 @@ struct CatArgs {
   int kchunk;   // k columns of beta resident in shared memory at a time (mult of 4)
   int kstride;  // kchunk + 4
   int rows_per_cta;  // pass 2 row slice (multiple of 4)
+  int lin_stages;    // pass 1 (TMA): depth of the x / beta^T ring
+  const double* beta_t;  // pass 1 (TMA): beta^T, [K][C8 + 4], zero padded
 };
 
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
@@ -344,61 +346,81 @@ __global__ void cat_dbeta_finalize_kernel(const double* __restrict__ partials,
 //         T tiles; rows of an 8-row block are paired (2 tig, 2 tig + 1) so each
 //         lane feeds two DMMAs from one 16-byte LDS.
 constexpr int kLinRows = 256;   // rows per CTA row block in pass 1
-constexpr int kLinCols = 8;     // columns per stage in pass 1
-constexpr int kLinStages = 4;
 constexpr int kDbRows = 16;     // rows per stage in pass 2
 constexpr int kDbStages = 3;
 
-template <int NT>
-__global__ void __launch_bounds__(kCatThreads, 1)
+// beta^T with the class index contiguous and a pitch of C8 + 4 doubles, so that
+// the DMMA B fragments of pass 1 read shared memory without bank conflicts
+__global__ void cat_beta_transpose_kernel(const double* __restrict__ beta, int K,
+                                          int C, int C8p, double* __restrict__ bt) {
+  const int64_t total = (int64_t)K * C8p;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i / C8p), c = (int)(i - (int64_t)k * C8p);
+    bt[i] = c < C ? beta[(size_t)c * K + k] : 0.0;
+  }
+}
+
+constexpr int kLinWarps = 16;           // pass 1 (TMA): 16 warps x 16 rows
+constexpr int kLinThreads = 32 * kLinWarps;
+constexpr int kLinBox = 136;            // rows per TMA box: 128 used + 8 of padding, so
+                                        // the column pitch is 8 (mod 16) doubles and the
+                                        // DMMA A fragments read conflict-free
+
+template <int NT, int KS>
+__global__ void __launch_bounds__(kLinThreads, 1)
     cat_lin_tma_kernel(const __grid_constant__ CUtensorMap tmx,
+                       const __grid_constant__ CUtensorMap tmb,
                        const __grid_constant__ CatArgs a) {
   extern __shared__ __align__(1024) unsigned char cat_smem[];
-  double* xs = reinterpret_cast<double*>(cat_smem);  // [stages][8 cols][256 rows]
-  double* beta_s = xs + (size_t)kLinStages * kLinCols * kLinRows;  // [C8][kstride]
-  double* alpha_s = beta_s + (size_t)a.C8 * a.kstride;            // [C8]
+  // stage = two x boxes [KS cols][136 rows] (rows 0-127 and 128-255 of the row
+  // block, each with 8 rows of padding) followed by the matching slice of beta^T
+  // [KS attributes][C8 + 4]; beta streams from L2 with x, so no K x C block has to
+  // stay resident and the whole shared memory is ring
+  const int kLinStages = a.lin_stages;
+  const int C8p = a.C8 + 4;
+  constexpr int xbox = kLinBox * KS;  // doubles per x box
+  const uint32_t stage_bytes = (uint32_t)(2 * xbox + C8p * KS) * 8u;
+  double* ring = reinterpret_cast<double*>(cat_smem);
+  double* alpha_s = ring + (size_t)kLinStages * (stage_bytes / 8);  // [C8]
   double* red_s = alpha_s + a.C8;                                 // [warps][2 + C8]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(red_s + kCatWarps * (2 + a.C8));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(red_s + kLinWarps * (2 + a.C8));
   uint64_t* empty_bar = full_bar + kLinStages;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = lane >> 2, tig = lane & 3;
-  constexpr uint32_t stage_bytes = kLinCols * kLinRows * 8;
 
   const int64_t nblocks = (a.N + kLinRows - 1) / kLinRows;
-  const int ksteps = (a.K + kLinCols - 1) / kLinCols;  // stages per row block
+  const int ksteps = (a.K + KS - 1) / KS;  // stages per row block
   // this CTA's row blocks: blockIdx.x, blockIdx.x + gridDim.x, ...
   const int64_t my_blocks
       = nblocks > blockIdx.x ? (nblocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const int64_t total = my_blocks * ksteps;  // stage loads of this CTA
 
-  // beta -> shared memory, zero padded: beta_s[c][k]
-  const int kpad = (a.K + 7) & ~7;
-  for (int idx = tid; idx < a.C8 * kpad; idx += kCatThreads) {
-    const int c = idx / kpad, k = idx - c * kpad;
-    beta_s[(size_t)c * a.kstride + k]
-        = (c < a.C && k < a.K) ? a.beta[(size_t)c * a.K + k] : 0.0;
-  }
-  for (int c = tid; c < a.C8; c += kCatThreads) alpha_s[c] = c < a.C ? a.alpha[c] : 0.0;
+  for (int c = tid; c < a.C8; c += kLinThreads) alpha_s[c] = c < a.C ? a.alpha[c] : 0.0;
   if (tid == 0) {
     for (int st = 0; st < kLinStages; ++st) {
       mbar_init(&full_bar[st], 1);
-      mbar_init(&empty_bar[st], kCatWarps);
+      mbar_init(&empty_bar[st], kLinWarps);
     }
     fence_barrier_init();
   }
   __syncthreads();
 
-  uint64_t pol = 0;
+  uint64_t pol = 0, pol_keep = 0;
   auto issue = [&](int64_t q) {  // q-th stage load of this CTA
     const int st = (int)(q % kLinStages);
     const int64_t blk = blockIdx.x + (q / ksteps) * gridDim.x;
     const int ks = (int)(q % ksteps);
+    double* dst = ring + (size_t)st * (stage_bytes / 8);
     mbar_expect_tx(&full_bar[st], stage_bytes);
-    tma_load_2d(xs + (size_t)st * (stage_bytes / 8), &tmx, (int)(blk * kLinRows),
-                ks * kLinCols, &full_bar[st], pol);
+    tma_load_2d(dst, &tmx, (int)(blk * kLinRows), ks * KS, &full_bar[st], pol);
+    tma_load_2d(dst + xbox, &tmx, (int)(blk * kLinRows + 128), ks * KS, &full_bar[st],
+                pol);
+    tma_load_2d(dst + 2 * xbox, &tmb, 0, ks * KS, &full_bar[st], pol_keep);
   };
   if (tid == 0) {
     pol = policy_evict_first();
+    pol_keep = policy_evict_last();  // beta is re-read by every row block
     for (int64_t q = 0; q < kLinStages && q < total; ++q) issue(q);
   }
 
@@ -407,12 +429,14 @@ __global__ void __launch_bounds__(kCatThreads, 1)
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) dal[nt][0] = dal[nt][1] = 0.0;
 
+  // this warp's 16 rows inside the stage: box (warp / 8), local row 16 (warp % 8)
+  const int xoff = (warp >> 3) * xbox + 16 * (warp & 7) + grp;
   int64_t q = 0;
   for (int64_t b = 0; b < my_blocks; ++b) {
-    const int64_t r0 = (blockIdx.x + b * gridDim.x) * kLinRows + 32 * warp;
-    double acc[4][NT][2];
+    const int64_t r0 = (blockIdx.x + b * gridDim.x) * kLinRows + 16 * warp;
+    double acc[2][NT][2];
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
@@ -426,31 +450,31 @@ __global__ void __launch_bounds__(kCatThreads, 1)
         issue(q - 1 + kLinStages);
       }
       mbar_wait(&full_bar[st], ph);
-      // A fragments: x[r0 + 8 mt + grp][8 ks + 4 h + tig], h = 0, 1
-      const double* xa = xs + (size_t)st * (stage_bytes / 8) + (size_t)tig * kLinRows
-                         + 32 * warp + grp;
-      double af[2][4];
+      // A fragments: x[r0 + 8 mt + grp][KS ks + 4 h + tig]
+      // B fragments: beta[KS ks + 4 h + tig][8 nt + grp]
+      const double* stg = ring + (size_t)st * (stage_bytes / 8);
+      const double* xa = stg + xoff + tig * kLinBox;
+      const double* bfrag = stg + 2 * xbox + tig * C8p + grp;
 #pragma unroll
-      for (int h = 0; h < 2; ++h)
+      for (int h = 0; h < KS / 4; ++h) {
+        double af[2], bf[NT];
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt) af[h][mt] = xa[(size_t)(4 * h) * kLinRows + 8 * mt];
+        for (int mt = 0; mt < 2; ++mt) af[mt] = xa[4 * h * kLinBox + 8 * mt];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) bf[nt] = bfrag[4 * h * C8p + 8 * nt];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) dmma(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[st]);
-      const double* bfrag = beta_s + (size_t)grp * a.kstride + ks * kLinCols + tig;
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          const double bf = bfrag[(size_t)(8 * nt) * a.kstride + 4 * h];
-#pragma unroll
-          for (int mt = 0; mt < 4; ++mt) dmma(acc[mt][nt][0], acc[mt][nt][1], af[h][mt], bf);
-        }
     }
     if (r0 >= a.N) continue;
 
     // ---- epilogue: softmax over the C classes of each row (held by a quad)
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt) {
+    for (int mt = 0; mt < 2; ++mt) {
       const int64_t row = r0 + 8 * mt + grp;
       const bool valid = row < a.N;
       const int yc = valid ? (a.y ? a.y[row] : a.y_scalar) - 1 : 0;
@@ -532,9 +556,9 @@ __global__ void __launch_bounds__(kCatThreads, 1)
       for (int j = 0; j < 2; ++j) red_s[warp * rs + 2 + 8 * nt + 2 * tig + j] = dal[nt][j];
   }
   __syncthreads();
-  for (int j = tid; j < rs; j += kCatThreads) {
+  for (int j = tid; j < rs; j += kLinThreads) {
     double v = 0.0;
-    for (int w = 0; w < kCatWarps; ++w) v += red_s[w * rs + j];
+    for (int w = 0; w < kLinWarps; ++w) v += red_s[w * rs + j];
     a.partials[(size_t)blockIdx.x * rs + j] = v;
   }
 }
@@ -676,17 +700,18 @@ static int run_dbeta(const CatArgs& a, dim3 grid) {
   return SMC_OK;
 }
 
-template <int NT>
-static int run_lin_tma(const CUtensorMap& tmx, const CatArgs& a, int grid, size_t smem) {
+template <int NT, int KS>
+static int run_lin_tma(const CUtensorMap& tmx, const CUtensorMap& tmb, const CatArgs& a,
+                       int grid, size_t smem) {
   static size_t attr[16] = {};
   Context& c = ctx();
   if (attr[c.device & 15] < smem) {
-    SMC_CUDA(cudaFuncSetAttribute(cat_lin_tma_kernel<NT>,
+    SMC_CUDA(cudaFuncSetAttribute(cat_lin_tma_kernel<NT, KS>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     attr[c.device & 15] = smem;
   }
-  cat_lin_tma_kernel<NT><<<grid, kCatThreads, smem, c.stream>>>(tmx, a);
+  cat_lin_tma_kernel<NT, KS><<<grid, kLinThreads, smem, c.stream>>>(tmx, tmb, a);
   SMC_CUDA(cudaGetLastError());
   return SMC_OK;
 }
@@ -736,9 +761,11 @@ int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
   a.y_scalar = y_scalar;
   const int NT = a.C8 / 8;
 
-  // device staging: beta (K*C), alpha (C), out (2 + C8)
+  // device staging: beta (K x C), alpha (C), beta^T (K x (C8 + 4)) for pass 1
+  const int C8p = a.C8 + 4;
   const size_t nparam = (size_t)a.K * a.C + a.C;
-  if (int rc = ensure_params(sizeof(double) * (nparam + 8))) return rc;
+  const size_t off_bt = (nparam + 15) & ~(size_t)15;  // 128-byte aligned
+  if (int rc = ensure_params(sizeof(double) * (off_bt + (size_t)a.K * C8p + 16))) return rc;
   if (a.K)
     SMC_CUDA(cudaMemcpyAsync(cx.params_dev, beta_host, sizeof(double) * a.K * a.C,
                              cudaMemcpyHostToDevice, cx.stream));
@@ -746,6 +773,7 @@ int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
                            sizeof(double) * a.C, cudaMemcpyHostToDevice, cx.stream));
   a.beta = cx.params_dev;
   a.alpha = cx.params_dev + (size_t)a.K * a.C;
+  a.beta_t = cx.params_dev + off_bt;
 
   // shared-memory plan for beta: whole K if it fits, else chunks
   const size_t fixed = (size_t)a.C8 * 8 + (size_t)kCatWarps * (2 + a.C8) * 8 + 64;
@@ -760,16 +788,18 @@ int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
   size_t smem1 = (size_t)a.C8 * a.kstride * 8 + fixed;
   // TMA-staged kernels when x is TMA-addressable and the whole beta fits
   const bool tma = cat_tma_ok(x);
-  const size_t smem1_tma = (size_t)kLinStages * kLinCols * kLinRows * 8
-                           + (size_t)a.C8 * ((((size_t)a.K + 7) & ~(size_t)7) + 4) * 8
-                           + (size_t)a.C8 * 8 + (size_t)kCatWarps * (2 + a.C8) * 8
-                           + 2 * kLinStages * 8 + 64;
-  const bool lin_tma = tma && smem1_tma <= 224 * 1024;
-  if (lin_tma) {
-    a.kchunk = (a.K + 7) & ~7;
-    a.kstride = a.kchunk + 4;
-    smem1 = smem1_tma;
-  }
+  // pass-1 ring: the widest stage (attributes per stage) that still leaves four
+  // stages in ~216 KB
+  const size_t lin_fixed = (size_t)a.C8 * 8 + (size_t)kLinWarps * (2 + a.C8) * 8 + 64;
+  int ks_lin = 32;
+  while (ks_lin > 8
+         && 4 * ((size_t)ks_lin * (2 * kLinBox + C8p) * 8 + 16) + lin_fixed > 216 * 1024)
+    ks_lin /= 2;
+  const size_t lin_stage = (size_t)ks_lin * (2 * kLinBox + C8p) * 8;
+  a.lin_stages = (int)((216 * 1024 - lin_fixed) / (lin_stage + 16));
+  if (a.lin_stages > 12) a.lin_stages = 12;
+  const bool lin_tma = tma && a.K >= 1;
+  if (lin_tma) smem1 = (size_t)a.lin_stages * (lin_stage + 16) + lin_fixed;
 
   const bool need_beta = flags & SMC_VAR_BETA;
   const bool need_dx = (flags & SMC_VAR_X) && d_x;
@@ -788,11 +818,19 @@ int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
   const int64_t ntiles = (a.N + 31) / 32;
   int grid1 = (int)((ntiles + kCatWarps - 1) / kCatWarps);
   if (grid1 > cx.sm_count) grid1 = cx.sm_count;
-  CUtensorMap tm_lin, tm_dbx, tm_dbt;
-  if (lin_tma
-      && encode_tmap_f64(&tm_lin, x->data, x->rows, x->cols, x->ld, kLinRows, kLinCols)
-             != CUDA_SUCCESS)
-    return fail(SMC_ERR_CUDA, "cuTensorMapEncodeTiled failed (categorical pass 1)");
+  CUtensorMap tm_lin, tm_beta, tm_dbx, tm_dbt;
+  if (lin_tma) {
+    if (encode_tmap_f64(&tm_lin, x->data, x->rows, x->cols, x->ld, kLinBox, ks_lin)
+            != CUDA_SUCCESS
+        || encode_tmap_f64(&tm_beta, a.beta_t, C8p, a.K, C8p, C8p, ks_lin)
+               != CUDA_SUCCESS)
+      return fail(SMC_ERR_CUDA, "cuTensorMapEncodeTiled failed (categorical pass 1)");
+    const int64_t nbt = (int64_t)a.K * C8p;
+    cat_beta_transpose_kernel<<<(int)((nbt + 255) / 256), 256, 0, cx.stream>>>(
+        a.beta, a.K, a.C, C8p, const_cast<double*>(a.beta_t));
+    SMC_CUDA(cudaGetLastError());
+    cx.launches += 1;
+  }
   const int rs = 2 + a.C8;
 
   // scratch: T (ldT x C8), out (rs), d_beta_dev (K*C), partials
@@ -815,16 +853,27 @@ int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
 
   int rc = SMC_OK;
   if (lin_tma) {
+#define SMC_LIN_CASE(NTV)                                                         \
+  case NTV:                                                                       \
+    rc = ks_lin == 32   ? run_lin_tma<NTV, 32>(tm_lin, tm_beta, a, grid1, smem1)  \
+         : ks_lin == 16 ? run_lin_tma<NTV, 16>(tm_lin, tm_beta, a, grid1, smem1)  \
+                        : run_lin_tma<NTV, 8>(tm_lin, tm_beta, a, grid1, smem1);  \
+    break;
     switch (NT) {
-      case 1: rc = run_lin_tma<1>(tm_lin, a, grid1, smem1); break;
-      case 2: rc = run_lin_tma<2>(tm_lin, a, grid1, smem1); break;
-      case 3: rc = run_lin_tma<3>(tm_lin, a, grid1, smem1); break;
-      case 4: rc = run_lin_tma<4>(tm_lin, a, grid1, smem1); break;
-      case 5: rc = run_lin_tma<5>(tm_lin, a, grid1, smem1); break;
-      case 6: rc = run_lin_tma<6>(tm_lin, a, grid1, smem1); break;
-      case 7: rc = run_lin_tma<7>(tm_lin, a, grid1, smem1); break;
-      default: rc = run_lin_tma<8>(tm_lin, a, grid1, smem1); break;
+      SMC_LIN_CASE(1)
+      SMC_LIN_CASE(2)
+      SMC_LIN_CASE(3)
+      SMC_LIN_CASE(4)
+      SMC_LIN_CASE(5)
+      SMC_LIN_CASE(6)
+      SMC_LIN_CASE(7)
+      default:
+        rc = ks_lin == 32   ? run_lin_tma<8, 32>(tm_lin, tm_beta, a, grid1, smem1)
+             : ks_lin == 16 ? run_lin_tma<8, 16>(tm_lin, tm_beta, a, grid1, smem1)
+                            : run_lin_tma<8, 8>(tm_lin, tm_beta, a, grid1, smem1);
+        break;
     }
+#undef SMC_LIN_CASE
   } else
   switch (NT) {
     case 1: rc = run_lin<1>(a, grid1, smem1); break;

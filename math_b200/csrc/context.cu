@@ -16,6 +16,9 @@ Context::~Context() {
   // so errors are ignored.
   if (!inited) return;
   if (cudaSetDevice(device) != cudaSuccess) return;
+  for (auto& kv : block_cache)
+    for (void* b : kv.second) cudaFree(b);
+  block_cache.clear();
   if (partials) cudaFree(partials);
   if (counter) cudaFree(counter);
   if (params_dev) cudaFree(params_dev);
@@ -68,15 +71,6 @@ static int bind_device(int device) {
   c.stream = c.own_stream;
   SMC_CUDA(cudaMalloc(&c.counter, 64));
   SMC_CUDA(cudaMemset(c.counter, 0, 64));
-  {
-    // matrices come from the device's stream-ordered pool; keep freed blocks
-    // cached so the per-evaluation arena buffers (N-vector partials, the N x K
-    // d_x of an autodiff x) are recycled instead of going back to the driver
-    cudaMemPool_t pool;
-    SMC_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t keep = UINT64_MAX;
-    SMC_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-  }
   c.inited = true;
   return SMC_OK;
 }
@@ -108,6 +102,47 @@ static int grow(void** p, size_t* have, size_t want, bool pinned) {
     SMC_CUDA(cudaMalloc(p, n));
   *have = n;
   return SMC_OK;
+}
+
+int cache_alloc(void** p, size_t bytes) {
+  Context& c = t_ctx;
+  auto it = c.block_cache.find(bytes);
+  if (it != c.block_cache.end() && !it->second.empty()) {
+    *p = it->second.back();
+    it->second.pop_back();
+    c.cached_bytes -= bytes;
+    return SMC_OK;
+  }
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e == cudaErrorMemoryAllocation && c.cached_bytes > 0) {
+    (void)cudaGetLastError();
+    cache_trim();  // give the cached blocks back and retry once
+    e = cudaMalloc(p, bytes);
+  }
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return fail(SMC_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", bytes,
+                cudaGetErrorString(e));
+  }
+  return SMC_OK;
+}
+
+void cache_free(void* p, size_t bytes) {
+  // work queued on this thread's stream may still touch the block; the next
+  // owner is this thread again, on the same stream, so no synchronisation
+  Context& c = t_ctx;
+  c.block_cache[bytes].push_back(p);
+  c.cached_bytes += bytes;
+}
+
+void cache_trim() {
+  Context& c = t_ctx;
+  if (c.cached_bytes == 0) return;
+  cudaStreamSynchronize(c.stream);
+  for (auto& kv : c.block_cache)
+    for (void* b : kv.second) cudaFree(b);
+  c.block_cache.clear();
+  c.cached_bytes = 0;
 }
 
 int ensure_partials(size_t bytes) {
@@ -219,8 +254,16 @@ int smc_get_device(int* device) {
   return SMC_OK;
 }
 
+int smc_trim_cache(void) {
+  if (int rc = ensure_ctx()) return rc;
+  cache_trim();
+  return SMC_OK;
+}
+
 int smc_set_stream(void* s) {
   if (int rc = ensure_ctx()) return rc;
+  // recycled blocks are ordered on the stream they were last used on
+  SMC_CUDA(cudaStreamSynchronize(ctx().stream));
   ctx().stream = s ? static_cast<cudaStream_t>(s) : ctx().own_stream;
   return SMC_OK;
 }
@@ -266,11 +309,10 @@ int smc_matrix_create(int64_t rows, int64_t cols, int dtype, smc_matrix** out) {
   m->ld = cols > 1 ? (rows + align - 1) / align * align : rows;
   if (m->ld < 1) m->ld = 1;
   const size_t bytes = (size_t)m->ld * (size_t)(cols > 0 ? cols : 1) * elem_size(dtype);
-  cudaError_t e = cudaMallocAsync(&m->data, bytes < 256 ? 256 : bytes, ctx().stream);
-  if (e != cudaSuccess) {
+  m->alloc_bytes = bytes < 256 ? 256 : (bytes + 255) & ~(size_t)255;
+  if (int rc = cache_alloc(&m->data, m->alloc_bytes)) {
     delete m;
-    return fail(SMC_ERR_CUDA, "cudaMallocAsync(%zu bytes) failed: %s", bytes,
-                cudaGetErrorString(e));
+    return rc;
   }
   m->owned = true;
   *out = m;
@@ -299,9 +341,13 @@ int smc_matrix_free(smc_matrix* m) {
   if (!m) return SMC_OK;
   if (m->owned && m->data) {
     if (int rc = ensure_ctx()) return rc;
-    // stream-ordered: the block returns to the pool once everything queued
-    // on this thread's stream so far has run
-    SMC_CUDA(cudaFreeAsync(m->data, ctx().stream));
+    if (m->device == ctx().device) {
+      cache_free(m->data, m->alloc_bytes);
+    } else {  // owned by another GPU than this thread's: hand it straight back
+      cudaSetDevice(m->device);
+      cudaFree(m->data);
+      cudaSetDevice(ctx().device);
+    }
   }
   delete m;
   return SMC_OK;

@@ -108,6 +108,8 @@ __global__ void __launch_bounds__(256, 1)
   p = reinterpret_cast<unsigned char*>(((uintptr_t)p + 7) & ~(uintptr_t)7);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(p);
   uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* part_bar = empty_bar + kStages;  // [G][2]: partial dot products published
+  double* hdr_s = reinterpret_cast<double*>(part_bar + 2 * G);  // [warps][8] row sums
   __shared__ int s_last;
 
   const int tid = threadIdx.x;
@@ -143,14 +145,14 @@ __global__ void __launch_bounds__(256, 1)
       mbar_init(&full_bar[st], 1);
       mbar_init(&empty_bar[st], n_cons_warps);
     }
+    for (int j = 0; j < 2 * G; ++j) mbar_init(&part_bar[j], S);
     fence_barrier_init();
   }
   __syncthreads();
 
-  // consumer identity: slab-major so the lead warps (s == 0) of different row
-  // groups sit on different SM sub-partitions
+  // consumer identity: slab-major, so the S warps of a row group share one SM
+  // sub-partition when G = 4 and the row groups spread over all four
   const int s = warp / G, g = warp - s * G;
-  const bool lead = s == 0;
   double acc[kColsPerThread];
 #pragma unroll
   for (int kk = 0; kk < kColsPerThread; ++kk) acc[kk] = 0.0;
@@ -176,15 +178,30 @@ __global__ void __launch_bounds__(256, 1)
     }
   }
   {
-    int it = 0;
+    // Software pipeline over this CTA's tiles t = blockIdx.x + it * gridDim.x:
+    //   stage A(it)  wait for the tile, pull the warp's 32 x 32 slab into
+    //                registers, release the ring slot, partial dot product ->
+    //                shared memory, ARRIVE on the row group's mbarrier
+    //   stage C(it)  WAIT for the S partials, theta, derivative part of the link,
+    //                d_beta / d_x / d_cuts accumulation
+    //   stage L(it)  log-density part of the link, by the tile's lead warp only
+    // executed in the order A(0) | C(0) A(1) L(0) | C(1) A(2) L(1) | ...  The lead
+    // role rotates over the S warps of a row group (lead(it) = it mod S) and L(it)
+    // comes after the warp has already published its partial for tile it+1, so the
+    // transcendental-heavy L never holds up the other warps of the group.
     const int rloc = 32 * g + lane;
-    RowRaw nxt = load_row<FAM>(a, (int64_t)blockIdx.x * R + rloc);
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+    const double* bs = beta_s + 32 * s;
+    double xv[kColsPerThread];
+    RowRaw nxt;
+    const int my_tiles
+        = a.ntiles > (int)blockIdx.x ? (a.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    auto stage_a = [&](int it) {
       const int st = it % kStages;
-      const uint32_t ph = (uint32_t)(it / kStages) & 1u;
       const int par = it & 1;
+      const int tile = blockIdx.x + it * gridDim.x;
       if (tid == 0 && it >= 1) {
-        // refill the stage tile it-1 occupied, once every warp has released it
+        // refill the slot tile it-1 occupied, once every warp has released it
         const int64_t nt = (int64_t)tile + (int64_t)(kStages - 1) * gridDim.x;
         if (nt < a.ntiles) {
           const int rs = (it - 1) % kStages;
@@ -194,32 +211,16 @@ __global__ void __launch_bounds__(256, 1)
                       &full_bar[rs], pol);
         }
       }
-      const int64_t row = (int64_t)tile * R + rloc;
-      const bool valid = row < a.N;
-
-      // per-row inputs of THIS tile were loaded during the previous iteration;
-      // issue the loads for the next tile now
-      const RowRaw cur = nxt;
-      nxt = load_row<FAM>(a, row + (int64_t)gridDim.x * R);
-      RowIn<FAM> in;
-      if constexpr (FAM == kNormal)
-        in.y = cur.y;
-      else
-        in.y = a.y ? (double)cur.yi : cur.y;
-      in.alpha = cur.alpha;
-      in.aux = cur.aux;
-
-      mbar_wait(&full_bar[st], ph);
+      // per-row inputs of this tile: in flight while the partials are formed
+      nxt = load_row<FAM>(a, (int64_t)tile * R + rloc);
+      mbar_wait(&full_bar[st], (uint32_t)(it / kStages) & 1u);
       const double* xs
           = tiles + (size_t)st * (stage_bytes / 8) + (size_t)(32 * s) * R + rloc;
-      double xv[kColsPerThread];
 #pragma unroll
       for (int kk = 0; kk < kColsPerThread; ++kk) xv[kk] = xs[kk * R];
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[st]);  // stage is free again
-
+      if (lane == 0) mbar_arrive(&empty_bar[st]);  // slot is free again
       // partial dot product: four independent FMA chains (fixed association)
-      const double* bs = beta_s + 32 * s;
       double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
 #pragma unroll
       for (int kk = 0; kk < kColsPerThread; kk += 4) {
@@ -229,23 +230,47 @@ __global__ void __launch_bounds__(256, 1)
         p3 = fma(xv[kk + 3], bs[kk + 3], p3);
       }
       const double part = (p0 + p1) + (p2 + p3);
-
-      double xb = part;
+      partial_s[(par * S + s) * R + rloc] = part;
       if (S > 1) {
-        partial_s[(par * S + s) * R + rloc] = part;
-        group_bar(1 + g, 32 * S);
-        // every warp of the row group adds the S partials in the same fixed
-        // tree, so all of them hold the identical theta
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&part_bar[g * 2 + par]);
+      }
+    };
+
+    if (my_tiles > 0) stage_a(0);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int par = it & 1;
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int64_t row = (int64_t)tile * R + rloc;
+      const bool valid = row < a.N;
+      const bool lead = (it % S) == s;
+      const RowRaw cur = nxt;
+      RowIn<FAM> in;
+      if constexpr (FAM == kNormal)
+        in.y = cur.y;
+      else
+        in.y = a.y ? (double)cur.yi : cur.y;
+      in.alpha = cur.alpha;
+      in.aux = cur.aux;
+
+      // ---- stage C: every warp of the row group adds the S partials in the same
+      // fixed tree, so all of them hold the identical theta
+      double xb;
+      if (S > 1) {
+        mbar_wait(&part_bar[g * 2 + par], (uint32_t)(it >> 1) & 1u);
         double q[8];
 #pragma unroll
         for (int ss = 0; ss < 8; ++ss)
           q[ss] = ss < S ? partial_s[(par * S + ss) * R + rloc] : 0.0;
         xb = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
+      } else {
+        xb = partial_s[par * R + rloc];
       }
 
       double d1 = 0, d2 = 0;
+      LinkStash<FAM> stash;
       const double d
-          = link_row<FAM>(a, xb, in, valid, lead, row, racc, tab, d1, d2);
+          = link_d<FAM>(a, xb, in, valid, lead, row, racc, tab, d1, d2, stash);
 
       if (need_beta) {
 #pragma unroll
@@ -260,8 +285,9 @@ __global__ void __launch_bounds__(256, 1)
       if constexpr (FAM == kOrdered) {
         if (need_cuts && fast_cuts) {
           // ordered_logistic_glm_lpmf.hpp L197-207: cuts'[y-1] += d2, cuts'[y-2] -= d1.
-          // Each lane of the lead warp owns a private slot per cut point, so the
-          // scatter is conflict-free and its order of additions is fixed.
+          // Each lane of the tile's lead warp owns a private slot per cut point,
+          // so the scatter is conflict-free and its order of additions is fixed
+          // (tile order; consecutive leads are ordered by the partial mbarrier).
           if (lead && valid) {
             const int yy = (int)in.y;
             double* cs = cacc_s + (size_t)g * a.ncuts * 32 + lane;
@@ -295,6 +321,9 @@ __global__ void __launch_bounds__(256, 1)
           }
         }
       }
+      // ---- stage A of the next tile, then the deferred stage L of this one
+      if (it + 1 < my_tiles) stage_a(it + 1);
+      if (lead) link_lp<FAM>(a, stash, racc, tab);
     }
   }
 
@@ -310,20 +339,23 @@ __global__ void __launch_bounds__(256, 1)
       const double v = warp_sum(acc[kk]);
       if (lane == kk) red[g * ps + kHdr + 32 * s + kk] = v;
     }
-    if (lead) {
+    {
+      // every warp led some of its row group's tiles: row sums per warp
       const double v0 = warp_sum(racc.lp), v1 = warp_sum(racc.sd),
                    v2 = warp_sum(racc.s2), v3 = warp_sum(racc.s3),
                    vb = warp_sum((double)racc.bad);
       if (lane == 0) {
-        red[g * ps + SMC_OUT_LOGP] = v0;
-        red[g * ps + SMC_OUT_SUM_D] = v1;
-        red[g * ps + SMC_OUT_AUX] = v2;
-        red[g * ps + SMC_OUT_NONFINITE] = vb;
-        red[g * ps + SMC_OUT_AUX2] = v3;
+        double* h = hdr_s + warp * kHdr;
+        h[SMC_OUT_LOGP] = v0;
+        h[SMC_OUT_SUM_D] = v1;
+        h[SMC_OUT_AUX] = v2;
+        h[SMC_OUT_NONFINITE] = vb;
+        h[SMC_OUT_AUX2] = v3;
+        h[5] = h[6] = h[7] = 0.0;
       }
     }
     if (need_cuts && fast_cuts) {
-      if (lead)
+      if (s == 0)
         for (int c = 0; c < a.ncuts; ++c) {
           const double v = warp_sum(cacc_s[((size_t)g * a.ncuts + c) * 32 + lane]);
           if (lane == 0) red[g * ps + kHdr + CW + c] = v;
@@ -341,7 +373,11 @@ __global__ void __launch_bounds__(256, 1)
   double* my_partial = a.partials + (size_t)blockIdx.x * ps;
   for (int j = tid; j < ps; j += blockDim.x) {
     double v = 0.0;
-    for (int gg = 0; gg < G; ++gg) v += red[gg * ps + j];
+    if (j < kHdr) {
+      for (int w = 0; w < n_cons_warps; ++w) v += hdr_s[w * kHdr + j];  // fixed order
+    } else {
+      for (int gg = 0; gg < G; ++gg) v += red[gg * ps + j];
+    }
     my_partial[j] = v;
   }
 
@@ -502,7 +538,8 @@ int launch_glm_fused(const GlmCall& c) {
                        ? (size_t)a.G * a.ncuts * 32 * 8
                        : 0)
                 + (size_t)2 * a.S * R * 8
-                + (size_t)4 * R * 8 + (size_t)2 * R * 4 + 8 + 2 * kStages * 8;
+                + (size_t)4 * R * 8 + (size_t)2 * R * 4 + 8 + 2 * kStages * 8
+                + (size_t)2 * a.G * 8 + (size_t)a.S * a.G * kHdr * 8;
   const size_t red_bytes = (size_t)a.G * a.pstride * 8;
   if (red_bytes > kStages * stage_bytes)
     return fail(SMC_ERR_UNSUPPORTED, "reduction scratch exceeds the tile ring");

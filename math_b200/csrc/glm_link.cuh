@@ -92,30 +92,46 @@ struct RowIn {
   double aux;    // sigma / phi for this row
 };
 
+// What the deferred log-density part of a row needs from the derivative part.
 template <int FAM>
-__device__ __forceinline__ double link_row(const FusedArgs& a, double xb,
-                                           const RowIn<FAM>& in, bool valid,
-                                           bool lead, int64_t row, RowAcc& acc,
-                                           const LinkTab& tab, double& d1o,
-                                           double& d2o) {
-  double d = 0, lp = 0, s2 = 0, s3 = 0;
+struct LinkStash {
+  double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+  int64_t row = 0;
+  int c = 0;
+  bool valid = false;
+};
+
+// Derivative part of the link of one row: returns d = d logp_i / d theta_i, writes
+// the per-row (N-vector) partials, accumulates the sums that depend on d only, and
+// leaves in `st` what link_lp() needs.  Every warp of a row group runs this (all
+// of them need d for their columns of d_beta); only the row's `lead` warp writes
+// and accumulates.
+template <int FAM>
+__device__ __forceinline__ double link_d(const FusedArgs& a, double xb,
+                                         const RowIn<FAM>& in, bool valid, bool lead,
+                                         int64_t row, RowAcc& acc, const LinkTab& tab,
+                                         double& d1o, double& d2o,
+                                         LinkStash<FAM>& st) {
+  double d = 0, lp = 0, s3 = 0;
   int bad = 0;
+  st.valid = valid;
+  st.row = row;
   if constexpr (FAM == kBernoulli) {
     const double sgn = 2.0 * in.y - 1.0;
     const double t = sgn * (xb + in.alpha);
     const double e = exp(-t);
-    // bernoulli_logit_glm_lpmf.hpp L120-126 / L137-142 (the t > 20 derivative
-    // branch is -e whatever the sign: reproduced for parity)
-    // only the lead warp of a row group owns the log-density sum
-    if (lead) lp = t > 20.0 ? -e : (t < -20.0 ? t : -log1p(e));
+    // bernoulli_logit_glm_lpmf.hpp L137-142 (the t > 20 derivative branch is -e
+    // whatever the sign: reproduced for parity)
     d = t > 20.0 ? -e : (t < -20.0 ? sgn : sgn * e / (e + 1.0));
     bad = !isfinite(t);
+    st.v0 = t;
+    st.v1 = e;
     if (lead && valid && a.d_alpha_vec) a.d_alpha_vec[row] = d;
   } else if constexpr (FAM == kPoisson) {
     const double th = xb + in.alpha;
     const double e = exp(th);
-    d = in.y - e;          // poisson_log_glm_lpmf.hpp L117-118
-    lp = in.y * th - e;    // L130-131
+    d = in.y - e;        // poisson_log_glm_lpmf.hpp L117-118
+    lp = in.y * th - e;  // L130-131
     bad = !isfinite(th);
     if (lead && valid && a.d_alpha_vec) a.d_alpha_vec[row] = d;
   } else if constexpr (FAM == kNormal) {
@@ -142,49 +158,22 @@ __device__ __forceinline__ double link_row(const FusedArgs& a, double xb,
     const double ypp = in.y + ph;
     const double te = exp(th);
     d = in.y - te * ypp / (te + ph);  // L203-204
-    // everything else feeds the log density and d_phi, which only the lead warp
-    // of a row group accumulates
-    if (lead && valid) {
-      const bool propto = a.flags & SMC_PROPTO;
-      const bool inc_phi = !propto || (a.flags & SMC_VAR_AUX);
-      const bool inc_lin
-          = !propto || (a.flags & (SMC_VAR_X | SMC_VAR_ALPHA | SMC_VAR_BETA));
-      const double log_phi = a.aux_vec ? log(ph) : a.log_aux;
-      // neg_binomial_2_log_glm_lpmf.hpp L154-157
-      const double lse = th > log_phi ? th + log1p_exp(log_phi - th)
-                                      : log_phi + log1p_exp(th - log_phi);
-      lp = -ypp * lse;               // L184
-      if (inc_lin) lp += in.y * th;  // L186-188
-      const int yi = (int)in.y;
-      const bool in_tab = tab.lg != nullptr && yi < tab.tab_n;
-      if (inc_phi) {
-        lp += in_tab ? tab.lg[yi] : lgamma(ypp);  // L189-195
-        if (a.aux_vec) lp += multiply_log(ph, ph) - lgamma(ph);  // L171-176
-      }
-      if (a.flags & SMC_VAR_AUX) {
-        const double dg_phi = a.aux_vec ? digamma(ph) : a.digamma_aux;
-        const double dg_ypp = in_tab ? tab.dg[yi] : digamma(ypp);
-        const double dp
-            = 1.0 - ypp / (te + ph) + log_phi - lse + dg_ypp - dg_phi;  // L235-244
-        if (a.d_aux_vec)
-          a.d_aux_vec[row] = dp;
-        else
-          s2 = dp;
-      }
-      if (a.d_alpha_vec) a.d_alpha_vec[row] = d;
-    }
+    st.v0 = th;
+    st.v1 = te;
+    st.v2 = in.y;
+    st.v3 = ph;
+    if (lead && valid && a.d_alpha_vec) a.d_alpha_vec[row] = d;
   } else if constexpr (FAM == kOrdered) {
-    const int C = a.ncuts + 1;
     const int c = valid ? (int)in.y : 1;
     // ordered_logistic_glm_lpmf.hpp L108-121 and the class-only factors of L165-174
     double ce[4];
     if (tab.cls) {
-      const double2 v0 = *reinterpret_cast<const double2*>(tab.cls + 4 * (c - 1));
-      const double2 v1 = *reinterpret_cast<const double2*>(tab.cls + 4 * (c - 1) + 2);
-      ce[0] = v0.x;
-      ce[1] = v0.y;
-      ce[2] = v1.x;
-      ce[3] = v1.y;
+      const double2 w0 = *reinterpret_cast<const double2*>(tab.cls + 4 * (c - 1));
+      const double2 w1 = *reinterpret_cast<const double2*>(tab.cls + 4 * (c - 1) + 2);
+      ce[0] = w0.x;
+      ce[1] = w0.y;
+      ce[2] = w1.x;
+      ce[3] = w1.y;
     } else {
       ordered_class_entry(tab.cuts, a.ncuts, c, ce);
     }
@@ -198,26 +187,88 @@ __device__ __forceinline__ double link_row(const FusedArgs& a, double xb,
     d = d1 - d2;
     d1o = d1;
     d2o = d2;
-    if (lead) {
-      const double A = (cut1 > 0.0 ? -cut1 : 0.0) - log1p(e1);
-      const double B = (cut2 <= 0.0 ? cut2 : 0.0) - log1p(e2);
-      if (c == 1)
-        lp = A;
-      else if (c == C)
-        lp = B;
-      else
-        lp = B + log1m_exp(cut1 - cut2) + A;  // L141-161
-    }
+    st.v0 = cut1;
+    st.v1 = cut2;
+    st.v2 = e1;
+    st.v3 = e2;
+    st.c = c;
     s3 = xb;  // sum(location) for the lazy finiteness check, L124
   }
   if (!valid) return 0.0;
   if (lead) {
     acc.lp += lp;
     acc.sd += d;
-    acc.s2 += s2;
     acc.s3 += s3;
     acc.bad += bad;
   }
+  return d;
+}
+
+// Log-density part of the link of one row (plus d_phi of the neg-binomial): the
+// transcendental-heavy terms that only feed sums owned by the row's lead warp.
+// It runs after the derivative part, possibly later (the fused kernel defers it
+// past the next tile's partial dot product so that no other warp waits for it).
+template <int FAM>
+__device__ __forceinline__ void link_lp(const FusedArgs& a, const LinkStash<FAM>& st,
+                                        RowAcc& acc, const LinkTab& tab) {
+  if (!st.valid) return;
+  if constexpr (FAM == kBernoulli) {
+    const double t = st.v0, e = st.v1;
+    acc.lp += t > 20.0 ? -e : (t < -20.0 ? t : -log1p(e));  // L120-126
+  } else if constexpr (FAM == kNegBinomial) {
+    const double th = st.v0, te = st.v1, y = st.v2, ph = st.v3;
+    const double ypp = y + ph;
+    const bool propto = a.flags & SMC_PROPTO;
+    const bool inc_phi = !propto || (a.flags & SMC_VAR_AUX);
+    const bool inc_lin
+        = !propto || (a.flags & (SMC_VAR_X | SMC_VAR_ALPHA | SMC_VAR_BETA));
+    const double log_phi = a.aux_vec ? log(ph) : a.log_aux;
+    // neg_binomial_2_log_glm_lpmf.hpp L154-157
+    const double lse = th > log_phi ? th + log1p_exp(log_phi - th)
+                                    : log_phi + log1p_exp(th - log_phi);
+    double lp = -ypp * lse;     // L184
+    if (inc_lin) lp += y * th;  // L186-188
+    const int yi = (int)y;
+    const bool in_tab = tab.lg != nullptr && yi < tab.tab_n;
+    if (inc_phi) {
+      lp += in_tab ? tab.lg[yi] : lgamma(ypp);  // L189-195
+      if (a.aux_vec) lp += multiply_log(ph, ph) - lgamma(ph);  // L171-176
+    }
+    acc.lp += lp;
+    if (a.flags & SMC_VAR_AUX) {
+      const double dg_phi = a.aux_vec ? digamma(ph) : a.digamma_aux;
+      const double dg_ypp = in_tab ? tab.dg[yi] : digamma(ypp);
+      const double dp
+          = 1.0 - ypp / (te + ph) + log_phi - lse + dg_ypp - dg_phi;  // L235-244
+      if (a.d_aux_vec)
+        a.d_aux_vec[st.row] = dp;
+      else
+        acc.s2 += dp;
+    }
+  } else if constexpr (FAM == kOrdered) {
+    const double cut1 = st.v0, cut2 = st.v1, e1 = st.v2, e2 = st.v3;
+    const int C = a.ncuts + 1;
+    const double A = (cut1 > 0.0 ? -cut1 : 0.0) - log1p(e1);
+    const double B = (cut2 <= 0.0 ? cut2 : 0.0) - log1p(e2);
+    if (st.c == 1)
+      acc.lp += A;
+    else if (st.c == C)
+      acc.lp += B;
+    else
+      acc.lp += B + log1m_exp(cut1 - cut2) + A;  // L141-161
+  }
+}
+
+// Both parts back to back (the general two-pass path).
+template <int FAM>
+__device__ __forceinline__ double link_row(const FusedArgs& a, double xb,
+                                           const RowIn<FAM>& in, bool valid,
+                                           bool lead, int64_t row, RowAcc& acc,
+                                           const LinkTab& tab, double& d1o,
+                                           double& d2o) {
+  LinkStash<FAM> st;
+  const double d = link_d<FAM>(a, xb, in, valid, lead, row, acc, tab, d1o, d2o, st);
+  if (lead) link_lp<FAM>(a, st, acc, tab);
   return d;
 }
 

@@ -7,6 +7,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <unordered_map>
+#include <vector>
 
 #include "../../include/stanmath_cuda.h"
 
@@ -43,6 +45,13 @@ struct Context {
   double* scratch = nullptr;   // generic device scratch (N-vectors for fallbacks)
   size_t scratch_bytes = 0;
   int64_t launches = 0;
+  // Recycled device blocks, keyed by exact size.  An HMC run allocates the same
+  // arena buffers (N-vector partials, the N x K d_x of an autodiff x) on every
+  // evaluation: a freed block goes here and the next create of that size takes
+  // it back without touching the driver.  Blocks are reused only by this
+  // thread, on this thread's stream, so reuse is stream-ordered.
+  std::unordered_map<size_t, std::vector<void*>> block_cache;
+  size_t cached_bytes = 0;
   std::string last_error;
   ~Context();
 };
@@ -54,6 +63,9 @@ int ensure_partials(size_t bytes);
 int ensure_params(size_t bytes);
 int ensure_out(size_t bytes);
 int ensure_scratch(size_t bytes);
+int cache_alloc(void** p, size_t bytes);  // recycled block or cudaMalloc
+void cache_free(void* p, size_t bytes);
+void cache_trim();  // return every cached block to the driver
 
 #define SMC_CUDA(expr)                                                        \
   do {                                                                        \
@@ -109,6 +121,7 @@ struct smc_matrix {
   int64_t rows = 0, cols = 0, ld = 0;
   int dtype = SMC_F64;
   bool owned = false;
+  size_t alloc_bytes = 0;  // size of the owned block (key of the block cache)
   int device = 0;
   // cached TMA descriptor for the fused kernel (depends on the tile shape)
   CUtensorMap tmap;
