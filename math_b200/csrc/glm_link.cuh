@@ -182,8 +182,9 @@ __device__ __forceinline__ double link_d(const FusedArgs& a, double xb,
     // stable inv_logit selects (L168-174): for cut > 0 it IS exp(-cut), for
     // cut <= 0 it IS exp(cut) -- same argument, same bits
     const double e1 = exp(-fabs(cut1)), e2 = exp(-fabs(cut2));
-    const double d1 = (cut2 > 0.0 ? e2 / (1.0 + e2) : 1.0 / (1.0 + e2)) - ce[2];
-    const double d2 = ce[3] - (cut1 > 0.0 ? e1 / (1.0 + e1) : 1.0 / (1.0 + e1));
+    // (one division per select: the numerator is chosen, the quotient is the same)
+    const double d1 = (cut2 > 0.0 ? e2 : 1.0) / (1.0 + e2) - ce[2];
+    const double d2 = ce[3] - (cut1 > 0.0 ? e1 : 1.0) / (1.0 + e1);
     d = d1 - d2;
     d1o = d1;
     d2o = d2;
