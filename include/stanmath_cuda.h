@@ -152,6 +152,18 @@ int smc_bernoulli_logit_glm(const smc_matrix* y, int y_scalar,
                             smc_matrix* d_alpha_vec, double* d_beta,
                             smc_matrix* d_x);
 
+/* prim/prob/binomial_logit_glm_lpmf.hpp L54-160 (device twin:
+ * opencl/prim/binomial_logit_glm_lpmf.hpp L28-139)
+ *   n       N x 1 i32 device vector of successes, or NULL -> n_scalar
+ *   trials  N x 1 i32 device vector of population sizes, or NULL -> trials_scalar */
+int smc_binomial_logit_glm(const smc_matrix* n, int n_scalar,
+                           const smc_matrix* trials, int trials_scalar,
+                           const smc_matrix* x, const smc_matrix* alpha_vec,
+                           double alpha, const double* beta, unsigned flags,
+                           double* logp, double* d_alpha,
+                           smc_matrix* d_alpha_vec, double* d_beta,
+                           smc_matrix* d_x);
+
 /* prim/prob/poisson_log_glm_lpmf.hpp L51-163 */
 int smc_poisson_log_glm(const smc_matrix* y, int y_scalar, const smc_matrix* x,
                         const smc_matrix* alpha_vec, double alpha,
@@ -203,8 +215,9 @@ int smc_categorical_logit_glm(const smc_matrix* y, int y_scalar,
  * left in `out_dev` for an NCCL all-reduce; no host synchronisation and no
  * value checks (the caller inspects out[SMC_OUT_NONFINITE]).  `family`:
  * 0 normal_id, 1 bernoulli_logit, 2 poisson_log, 3 neg_binomial_2_log,
- * 4 ordered_logistic.  Scalars alpha/aux are passed by value; out[0] already
- * contains every term of the reference's logp for this rank's rows. */
+ * 4 ordered_logistic, 5 binomial_logit (aux_vec = the i32 trials vector, aux =
+ * the scalar number of trials).  Scalars alpha/aux are passed by value; out[0]
+ * already contains every term of the reference's logp for this rank's rows. */
 int smc_glm_eval_device(int family, const smc_matrix* y, double y_scalar,
                         const smc_matrix* x, const smc_matrix* alpha_vec,
                         double alpha, const smc_matrix* aux_vec, double aux,

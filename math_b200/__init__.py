@@ -6,5 +6,6 @@ from .matrix_cuda import (MatrixCuda, to_matrix_cuda, from_matrix_cuda,
                           synthetic_host)
 from .glm import (GlmResult, bernoulli_logit_glm_lpmf, poisson_log_glm_lpmf,
                   normal_id_glm_lpdf, neg_binomial_2_log_glm_lpmf,
-                  ordered_logistic_glm_lpmf, categorical_logit_glm_lpmf)
+                  ordered_logistic_glm_lpmf, categorical_logit_glm_lpmf,
+                  binomial_logit_glm_lpmf)
 from . import runtime

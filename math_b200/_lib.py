@@ -64,6 +64,8 @@ SIGNATURES = {
     "smc_matrix_fill_synthetic": (_I, [_P, C.c_uint64, _I64, _I, _D, _I, _I]),
     "smc_bernoulli_logit_glm": (_I, [_P, _I, _P, _P, _D, _DP, _U, _DP, _DP, _P,
                                      _DP, _P]),
+    "smc_binomial_logit_glm": (_I, [_P, _I, _P, _I, _P, _P, _D, _DP, _U, _DP, _DP,
+                                    _P, _DP, _P]),
     "smc_poisson_log_glm": (_I, [_P, _I, _P, _P, _D, _DP, _U, _DP, _DP, _P, _DP,
                                  _P]),
     "smc_normal_id_glm": (_I, [_P, _D, _P, _P, _D, _DP, _P, _D, _U, _DP, _DP, _P,

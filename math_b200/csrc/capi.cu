@@ -139,6 +139,95 @@ int smc_bernoulli_logit_glm(const smc_matrix* y, int y_scalar,
   return SMC_OK;
 }
 
+int smc_binomial_logit_glm(const smc_matrix* n, int n_scalar,
+                           const smc_matrix* trials, int trials_scalar,
+                           const smc_matrix* x, const smc_matrix* alpha_vec,
+                           double alpha, const double* beta, unsigned flags,
+                           double* logp, double* d_alpha,
+                           smc_matrix* d_alpha_vec, double* d_beta,
+                           smc_matrix* d_x) {
+  static const char* fn = "binomial_logit_glm_lpmf";
+  if (int rc = ensure_ctx()) return rc;
+  if (!x || x->dtype != SMC_F64)
+    return fail(SMC_ERR_INVALID_ARGUMENT, "%s: x must be an f64 device matrix", fn);
+  if (!logp) return fail(SMC_ERR_INVALID_ARGUMENT, "%s: NULL logp", fn);
+  const int64_t N = x->rows, K = x->cols;
+  *logp = 0.0;
+  // size_zero(n, N, alpha, beta, x) comes BEFORE the size checks, L76-78
+  if (N == 0 || K == 0 || (n && n->rows * n->cols == 0)
+      || (trials && trials->rows * trials->cols == 0)
+      || (alpha_vec && alpha_vec->rows * alpha_vec->cols == 0))
+    return SMC_OK;
+  if ((flags & SMC_PROPTO)
+      && !(flags & (SMC_VAR_X | SMC_VAR_ALPHA | SMC_VAR_BETA)))
+    return SMC_OK;  // include_summand, L80-82
+  if (int rc = check_shapes(fn, x, n, SMC_I32, alpha_vec, nullptr)) return rc;  // L88-93
+  if (trials
+      && (trials->dtype != SMC_I32 || trials->rows * trials->cols != N
+          || (trials->cols != 1 && trials->rows != 1)))
+    return fail(SMC_ERR_INVALID_ARGUMENT,
+                "%s: size of the population size parameter (%lld) does not match "
+                "rows of x (%lld)",
+                fn, (long long)(trials->rows * trials->cols), (long long)N);
+  if (!beta) return fail(SMC_ERR_INVALID_ARGUMENT, "%s: NULL beta", fn);
+  if (int rc = check_out_vec(fn, d_alpha_vec, N)) return rc;
+  if (int rc = check_dx(fn, flags, x, d_x)) return rc;
+  {
+    // check_bounded(n, 0, N), check_nonnegative(N), L98-99 (n, N are data: cached)
+    bool ok = true;
+    double bc = 0.0;
+    if (int rc = binom_stats(n, n_scalar, trials, trials_scalar,
+                             (n || trials) ? N : 1, &ok, &bc))
+      return rc;
+    if (!ok)
+      return fail(SMC_ERR_DOMAIN,
+                  "%s: Successes variable must be in the interval [0, N] and the "
+                  "population size nonnegative",
+                  fn);
+  }
+  GlmCall c;
+  c.family = kBinomial;
+  c.x = x;
+  c.y = n;
+  c.y_scalar = n_scalar;
+  c.aux_vec = trials;
+  c.aux = trials_scalar;
+  c.alpha_vec = alpha_vec;
+  c.alpha = alpha;
+  c.beta_host = beta;
+  c.flags = flags;
+  c.d_alpha_vec = (flags & SMC_VAR_ALPHA) ? d_alpha_vec : nullptr;
+  c.d_x = d_x;
+  const double* o;
+  if (int rc = run_sync(c, SMC_OUT_HEADER + (int)K, &o)) return rc;
+  if (!std::isfinite(o[SMC_OUT_LOGP])) {  // lazy checks, L118-122
+    if (!host_all_finite(beta, K))
+      return fail(SMC_ERR_DOMAIN, "%s: Weight vector is not finite", fn);
+    if (!alpha_vec && !std::isfinite(alpha))
+      return fail(SMC_ERR_DOMAIN, "%s: Intercept is not finite", fn);
+    std::vector<double> keep(o, o + SMC_OUT_HEADER + K);
+    int ok = 1;
+    if (alpha_vec) {
+      if (int rc = smc_matrix_all_finite(alpha_vec, &ok)) return rc;
+      if (!ok) return fail(SMC_ERR_DOMAIN, "%s: Intercept is not finite", fn);
+    }
+    if (int rc = smc_matrix_all_finite(x, &ok)) return rc;
+    if (!ok)
+      return fail(SMC_ERR_DOMAIN,
+                  "%s: Matrix of independent variables is not finite", fn);
+    *logp = keep[SMC_OUT_LOGP];
+    if (d_alpha && (flags & SMC_VAR_ALPHA)) *d_alpha = keep[SMC_OUT_SUM_D];
+    if (d_beta && (flags & SMC_VAR_BETA))
+      memcpy(d_beta, keep.data() + SMC_OUT_HEADER, sizeof(double) * K);
+    return SMC_OK;
+  }
+  *logp = o[SMC_OUT_LOGP];
+  if (d_alpha && (flags & SMC_VAR_ALPHA)) *d_alpha = o[SMC_OUT_SUM_D];
+  if (d_beta && (flags & SMC_VAR_BETA))
+    memcpy(d_beta, o + SMC_OUT_HEADER, sizeof(double) * K);
+  return SMC_OK;
+}
+
 int smc_poisson_log_glm(const smc_matrix* y, int y_scalar, const smc_matrix* x,
                         const smc_matrix* alpha_vec, double alpha,
                         const double* beta, unsigned flags, double* logp,
@@ -383,11 +472,15 @@ int smc_glm_eval_device(int family, const smc_matrix* y, double y_scalar,
                         smc_matrix* d_x) {
   static const char* fn = "smc_glm_eval_device";
   if (int rc = ensure_ctx()) return rc;
-  if (family < kNormal || family > kOrdered)
+  if (family < kNormal || family > kBinomial)
     return fail(SMC_ERR_INVALID_ARGUMENT, "%s: unknown family %d", fn, family);
   if (int rc = check_shapes(fn, x, y, family == kNormal ? SMC_F64 : SMC_I32,
-                            alpha_vec, aux_vec))
+                            alpha_vec, family == kBinomial ? nullptr : aux_vec))
     return rc;
+  if (family == kBinomial && aux_vec
+      && (aux_vec->dtype != SMC_I32 || aux_vec->rows * aux_vec->cols != x->rows))
+    return fail(SMC_ERR_INVALID_ARGUMENT,
+                "%s: binomial trials must be an i32 vector with one entry per row", fn);
   if (!params_dev || !out_dev)
     return fail(SMC_ERR_INVALID_ARGUMENT, "%s: NULL params_dev or out_dev", fn);
   if (int rc = check_dx(fn, flags, x, d_x)) return rc;

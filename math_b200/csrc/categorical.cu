@@ -363,9 +363,26 @@ __global__ void cat_beta_transpose_kernel(const double* __restrict__ beta, int K
 
 constexpr int kLinWarps = 16;           // pass 1 (TMA): 16 warps x 16 rows
 constexpr int kLinThreads = 32 * kLinWarps;
-constexpr int kLinBox = 136;            // rows per TMA box: 128 used + 8 of padding, so
-                                        // the column pitch is 8 (mod 16) doubles and the
-                                        // DMMA A fragments read conflict-free
+#ifndef SMC_LIN_BOX
+#define SMC_LIN_BOX 132
+#endif
+constexpr int kLinBox = SMC_LIN_BOX;    // rows per TMA box: 128 used + 4 of padding, so
+                                        // the column pitch is 4 (mod 16) doubles and the
+                                        // 16-byte DMMA A-fragment reads are conflict-free
+
+// Fragment layout of pass 1.  mma.m8n8k4 wants A[m = grp][k = tig] and
+// B[k = tig][n = grp] per lane.  Rows and classes are PERMUTED so that the two
+// row tiles of a warp, and two class tiles of a pair, sit next to each other in
+// shared memory and one 16-byte LDS feeds two DMMAs:
+//   row of   (mt, grp)      = r0 + 2 grp + mt
+//   class of (nt, n index g) = 16 (nt / 2) + 2 g + (nt & 1)     (paired tiles)
+//                            = 16 (NT / 2) + g                  (last tile of an odd NT)
+// The accumulator element (mt, nt, j) of a lane therefore belongs to row
+// r0 + 2 grp + mt and class lin_class<NT>(nt, 2 tig + j).
+template <int NT>
+__device__ __forceinline__ int lin_class(int nt, int g) {
+  return nt < (NT & ~1) ? 16 * (nt >> 1) + 2 * g + (nt & 1) : 16 * (NT >> 1) + g;
+}
 
 template <int NT, int KS>
 __global__ void __launch_bounds__(kLinThreads, 1)
@@ -373,19 +390,20 @@ __global__ void __launch_bounds__(kLinThreads, 1)
                        const __grid_constant__ CUtensorMap tmb,
                        const __grid_constant__ CatArgs a) {
   extern __shared__ __align__(1024) unsigned char cat_smem[];
-  // stage = two x boxes [KS cols][136 rows] (rows 0-127 and 128-255 of the row
-  // block, each with 8 rows of padding) followed by the matching slice of beta^T
-  // [KS attributes][C8 + 4]; beta streams from L2 with x, so no K x C block has to
-  // stay resident and the whole shared memory is ring
+  // stage = two x boxes [KS cols][kLinBox rows] (rows 0-127 and 128-255 of the row
+  // block, each with a few rows of padding) followed by the matching slice of
+  // beta^T [KS attributes][C8 + 4]; beta streams from L2 with x, so no K x C block
+  // has to stay resident and the whole shared memory is ring
   const int kLinStages = a.lin_stages;
   const int C8p = a.C8 + 4;
   constexpr int xbox = kLinBox * KS;  // doubles per x box
+  constexpr int NP = NT / 2;          // class-tile pairs
   const uint32_t stage_bytes = (uint32_t)(2 * xbox + C8p * KS) * 8u;
   double* ring = reinterpret_cast<double*>(cat_smem);
   double* alpha_s = ring + (size_t)kLinStages * (stage_bytes / 8);  // [C8]
   double* red_s = alpha_s + a.C8;                                 // [warps][2 + C8]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(red_s + kLinWarps * (2 + a.C8));
-  uint64_t* empty_bar = full_bar + kLinStages;
+  int* rel_cnt = reinterpret_cast<int*>(full_bar + kLinStages);  // warps done per slot
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = lane >> 2, tig = lane & 3;
 
@@ -400,13 +418,17 @@ __global__ void __launch_bounds__(kLinThreads, 1)
   if (tid == 0) {
     for (int st = 0; st < kLinStages; ++st) {
       mbar_init(&full_bar[st], 1);
-      mbar_init(&empty_bar[st], kLinWarps);
+      rel_cnt[st] = 0;
     }
     fence_barrier_init();
   }
   __syncthreads();
 
-  uint64_t pol = 0, pol_keep = 0;
+  // The ring is refilled by whichever warp releases a slot LAST (shared-memory
+  // counter): no warp ever blocks on an "empty" barrier and the refill is issued
+  // the moment the slot becomes free.
+  const uint64_t pol = policy_evict_first();
+  const uint64_t pol_keep = policy_evict_last();  // beta is re-read by every row block
   auto issue = [&](int64_t q) {  // q-th stage load of this CTA
     const int st = (int)(q % kLinStages);
     const int64_t blk = blockIdx.x + (q / ksteps) * gridDim.x;
@@ -418,11 +440,8 @@ __global__ void __launch_bounds__(kLinThreads, 1)
                 pol);
     tma_load_2d(dst + 2 * xbox, &tmb, 0, ks * KS, &full_bar[st], pol_keep);
   };
-  if (tid == 0) {
-    pol = policy_evict_first();
-    pol_keep = policy_evict_last();  // beta is re-read by every row block
+  if (tid == 0)
     for (int64_t q = 0; q < kLinStages && q < total; ++q) issue(q);
-  }
 
   double lp_acc = 0.0, bad_acc = 0.0;
   double dal[NT][2];
@@ -430,7 +449,7 @@ __global__ void __launch_bounds__(kLinThreads, 1)
   for (int nt = 0; nt < NT; ++nt) dal[nt][0] = dal[nt][1] = 0.0;
 
   // this warp's 16 rows inside the stage: box (warp / 8), local row 16 (warp % 8)
-  const int xoff = (warp >> 3) * xbox + 16 * (warp & 7) + grp;
+  const int xoff = (warp >> 3) * xbox + 16 * (warp & 7) + 2 * grp;
   int64_t q = 0;
   for (int64_t b = 0; b < my_blocks; ++b) {
     const int64_t r0 = (blockIdx.x + b * gridDim.x) * kLinRows + 16 * warp;
@@ -443,39 +462,49 @@ __global__ void __launch_bounds__(kLinThreads, 1)
     for (int ks = 0; ks < ksteps; ++ks, ++q) {
       const int st = (int)(q % kLinStages);
       const uint32_t ph = (uint32_t)(q / kLinStages) & 1u;
-      if (tid == 0 && q >= 1 && q - 1 + kLinStages < total) {
-        // refill the stage load q-1 used, once every warp has released it
-        mbar_wait(&empty_bar[(q - 1) % kLinStages],
-                  (uint32_t)((q - 1) / kLinStages) & 1u);
-        issue(q - 1 + kLinStages);
-      }
       mbar_wait(&full_bar[st], ph);
-      // A fragments: x[r0 + 8 mt + grp][KS ks + 4 h + tig]
-      // B fragments: beta[KS ks + 4 h + tig][8 nt + grp]
+      // A: x[r0 + 2 grp + {0, 1}][KS ks + 4 h + tig]      one double2
+      // B: beta[KS ks + 4 h + tig][16 p + 2 grp + {0, 1}]  one double2 per pair
       const double* stg = ring + (size_t)st * (stage_bytes / 8);
       const double* xa = stg + xoff + tig * kLinBox;
-      const double* bfrag = stg + 2 * xbox + tig * C8p + grp;
+      const double* bfrag = stg + 2 * xbox + tig * C8p + 2 * grp;
 #pragma unroll
       for (int h = 0; h < KS / 4; ++h) {
-        double af[2], bf[NT];
+        const double2 af = *reinterpret_cast<const double2*>(xa + 4 * h * kLinBox);
+        double2 bf[NP > 0 ? NP : 1];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) af[mt] = xa[4 * h * kLinBox + 8 * mt];
+        for (int pr = 0; pr < NP; ++pr)
+          bf[pr] = *reinterpret_cast<const double2*>(bfrag + 4 * h * C8p + 16 * pr);
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) bf[nt] = bfrag[4 * h * C8p + 8 * nt];
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-          for (int mt = 0; mt < 2; ++mt) dmma(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+        for (int pr = 0; pr < NP; ++pr) {
+          dmma(acc[0][2 * pr][0], acc[0][2 * pr][1], af.x, bf[pr].x);
+          dmma(acc[1][2 * pr][0], acc[1][2 * pr][1], af.y, bf[pr].x);
+          dmma(acc[0][2 * pr + 1][0], acc[0][2 * pr + 1][1], af.x, bf[pr].y);
+          dmma(acc[1][2 * pr + 1][0], acc[1][2 * pr + 1][1], af.y, bf[pr].y);
+        }
+        if constexpr (NT & 1) {
+          const double bl = bfrag[4 * h * C8p + 16 * NP - grp];  // class 16 NP + grp
+          dmma(acc[0][NT - 1][0], acc[0][NT - 1][1], af.x, bl);
+          dmma(acc[1][NT - 1][0], acc[1][NT - 1][1], af.y, bl);
+        }
       }
+      // release the slot; the last warp out refills it
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[st]);
+      if (lane == 0) {
+        __threadfence_block();
+        if (atomicAdd(&rel_cnt[st], 1) == kLinWarps - 1) {
+          rel_cnt[st] = 0;
+          __threadfence_block();
+          if (q + kLinStages < total) issue(q + kLinStages);
+        }
+      }
     }
     if (r0 >= a.N) continue;
 
     // ---- epilogue: softmax over the C classes of each row (held by a quad)
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
-      const int64_t row = r0 + 8 * mt + grp;
+      const int64_t row = r0 + 2 * grp + mt;
       const bool valid = row < a.N;
       const int yc = valid ? (a.y ? a.y[row] : a.y_scalar) - 1 : 0;
       double m = -INFINITY;
@@ -484,7 +513,7 @@ __global__ void __launch_bounds__(kLinThreads, 1)
       for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const int c = 8 * nt + 2 * tig + j;
+          const int c = lin_class<NT>(nt, 2 * tig + j);
           double v = acc[mt][nt][j] + alpha_s[c];
           acc[mt][nt][j] = v;
           if (c < a.C) {
@@ -498,7 +527,7 @@ __global__ void __launch_bounds__(kLinThreads, 1)
       for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const int c = 8 * nt + 2 * tig + j;
+          const int c = lin_class<NT>(nt, 2 * tig + j);
           const double e = c < a.C ? exp(acc[mt][nt][j] - m) : 0.0;
           acc[mt][nt][j] = e;
           se += e;
@@ -506,24 +535,37 @@ __global__ void __launch_bounds__(kLinThreads, 1)
       se = quad_sum(se);
       lin_y = quad_sum(lin_y);
       const double inv = 1.0 / se;
-      if (valid) {
-        if (tig == 0) {
-          const double t = (log(inv) - m) + lin_y;  // L106, L110-116
-          lp_acc += t;
-          bad_acc += isfinite(t) ? 0.0 : 1.0;
-        }
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int c = 8 * nt + 2 * tig + j;
-            double t = acc[mt][nt][j] * -inv;  // neg_softmax_lin, L158-159
-            if (c == yc) t += 1.0;             // the "+1 at class y_i" scatters
-            if (c >= a.C) t = 0.0;
-            a.T[(size_t)c * a.ldT + row] = t;
-            dal[nt][j] += t;
-          }
+      if (valid && tig == 0) {
+        const double t = (log(inv) - m) + lin_y;  // L106, L110-116
+        lp_acc += t;
+        bad_acc += isfinite(t) ? 0.0 : 1.0;
       }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int c = lin_class<NT>(nt, 2 * tig + j);
+          double t = acc[mt][nt][j] * -inv;  // neg_softmax_lin, L158-159
+          if (c == yc) t += 1.0;             // the "+1 at class y_i" scatters
+          if (c >= a.C || !valid) t = 0.0;
+          acc[mt][nt][j] = t;
+          dal[nt][j] += t;
+        }
+    }
+    // T rows 2 grp, 2 grp + 1 of a class are adjacent: one 16-byte store
+    {
+      const int64_t row = r0 + 2 * grp;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int c = lin_class<NT>(nt, 2 * tig + j);
+          double* tp = a.T + (size_t)c * a.ldT + row;
+          if (row + 1 < a.N)
+            *reinterpret_cast<double2*>(tp) = make_double2(acc[0][nt][j], acc[1][nt][j]);
+          else if (row < a.N)
+            *tp = acc[0][nt][j];
+        }
     }
   }
 
@@ -553,7 +595,8 @@ __global__ void __launch_bounds__(kLinThreads, 1)
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-      for (int j = 0; j < 2; ++j) red_s[warp * rs + 2 + 8 * nt + 2 * tig + j] = dal[nt][j];
+      for (int j = 0; j < 2; ++j)
+        red_s[warp * rs + 2 + lin_class<NT>(nt, 2 * tig + j)] = dal[nt][j];
   }
   __syncthreads();
   for (int j = tid; j < rs; j += kLinThreads) {
@@ -795,6 +838,10 @@ int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
   while (ks_lin > 8
          && 4 * ((size_t)ks_lin * (2 * kLinBox + C8p) * 8 + 16) + lin_fixed > 216 * 1024)
     ks_lin /= 2;
+  if (const char* e = getenv("SMC_CAT_KS")) {  // tuning knob: attributes per stage
+    const int v = atoi(e);
+    if (v == 8 || v == 16 || (v == 32 && ks_lin == 32)) ks_lin = v;
+  }
   const size_t lin_stage = (size_t)ks_lin * (2 * kLinBox + C8p) * 8;
   a.lin_stages = (int)((216 * 1024 - lin_fixed) / (lin_stage + 16));
   if (a.lin_stages > 12) a.lin_stages = 12;

@@ -376,6 +376,7 @@ static int copy_rows(smc_matrix* m, int64_t row0, int64_t nrows, void* host,
   if (to_device) {
     m->lgamma_valid = false;
     m->range_valid = false;
+    m->version += 1;
     SMC_CUDA(cudaMemcpy2DAsync(dev, (size_t)m->ld * es, host,
                                (size_t)ld_host * es, (size_t)nrows * es,
                                (size_t)m->cols, cudaMemcpyHostToDevice,
@@ -415,6 +416,7 @@ int smc_matrix_zero(smc_matrix* m) {
   if (m->rows == 0 || m->cols == 0) return SMC_OK;
   m->lgamma_valid = false;
   m->range_valid = false;
+  m->version += 1;
   const size_t es = elem_size(m->dtype);
   SMC_CUDA(cudaMemset2DAsync(m->data, (size_t)m->ld * es, 0, (size_t)m->rows * es,
                              (size_t)m->cols, ctx().stream));
@@ -429,6 +431,7 @@ int smc_matrix_copy(smc_matrix* dst, const smc_matrix* src) {
   if (dst->rows == 0 || dst->cols == 0) return SMC_OK;
   dst->lgamma_valid = false;
   dst->range_valid = false;
+  dst->version += 1;
   const size_t es = elem_size(dst->dtype);
   SMC_CUDA(cudaMemcpy2DAsync(dst->data, (size_t)dst->ld * es, src->data,
                              (size_t)src->ld * es, (size_t)src->rows * es,
@@ -485,6 +488,7 @@ int smc_matrix_fill_synthetic(smc_matrix* m, uint64_t seed, int64_t row0,
   if (total == 0) return SMC_OK;
   m->lgamma_valid = false;
   m->range_valid = false;
+  m->version += 1;
   const double c = scale / sqrt(4294967295.0 / 3.0);
   fill_synth_kernel<<<grid_for(total, 256), 256, 0, ctx().stream>>>(
       m->data, m->ld, m->rows, m->cols, m->dtype, seed, row0, kind, c, lo, hi);

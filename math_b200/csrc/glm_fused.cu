@@ -25,7 +25,7 @@
 // Reference semantics (value + partials): stan/math/prim/prob/
 //   normal_id_glm_lpdf.hpp L122-213, bernoulli_logit_glm_lpmf.hpp L105-164,
 //   poisson_log_glm_lpmf.hpp L107-161, neg_binomial_2_log_glm_lpmf.hpp L143-244,
-//   ordered_logistic_glm_lpmf.hpp L108-207.
+//   ordered_logistic_glm_lpmf.hpp L108-207, binomial_logit_glm_lpmf.hpp L104-154.
 #include <cmath>
 #include <cstring>
 
@@ -67,7 +67,11 @@ __device__ __forceinline__ RowRaw load_row(const FusedArgs& a, int64_t row) {
         r.yi = static_cast<const int*>(a.y)[row];
     }
     if (a.alpha_vec) r.alpha = a.alpha_vec[row];
-    if (a.aux_vec) r.aux = a.aux_vec[row];
+    if constexpr (FAM == kBinomial) {
+      if (a.aux_ivec) r.aux = (double)a.aux_ivec[row];
+    } else {
+      if (a.aux_vec) r.aux = a.aux_vec[row];
+    }
   }
   return r;
 }
@@ -556,6 +560,8 @@ int launch_glm_fused(const GlmCall& c) {
       return launch_t<kNegBinomial>(tmap, a, grid, threads, smem);
     case kOrdered:
       return launch_t<kOrdered>(tmap, a, grid, threads, smem);
+    case kBinomial:
+      return launch_t<kBinomial>(tmap, a, grid, threads, smem);
   }
   return fail(SMC_ERR_INVALID_ARGUMENT, "unknown family %d", c.family);
 }

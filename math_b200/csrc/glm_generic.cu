@@ -27,7 +27,10 @@ int prepare_args(const GlmCall& c, FusedArgs* ap) {
   a.y_scalar = c.y_scalar;
   a.alpha_vec = c.alpha_vec ? static_cast<const double*>(c.alpha_vec->data) : nullptr;
   a.alpha = c.alpha;
-  a.aux_vec = c.aux_vec ? static_cast<const double*>(c.aux_vec->data) : nullptr;
+  if (c.family == kBinomial)
+    a.aux_ivec = c.aux_vec ? static_cast<const int*>(c.aux_vec->data) : nullptr;
+  else
+    a.aux_vec = c.aux_vec ? static_cast<const double*>(c.aux_vec->data) : nullptr;
   a.aux = c.aux;
   a.d_alpha_vec = c.d_alpha_vec ? static_cast<double*>(c.d_alpha_vec->data) : nullptr;
   a.d_aux_vec = c.d_aux_vec ? static_cast<double*>(c.d_aux_vec->data) : nullptr;
@@ -80,6 +83,20 @@ int prepare_args(const GlmCall& c, FusedArgs* ap) {
       }
       break;
     }
+    case kBinomial: {
+      // sum binomial_coefficient_log(N, n) [* N when both are broadcast scalars],
+      // binomial_logit_glm_lpmf.hpp L124-127; n and N are data: cached
+      if (!propto) {
+        bool ok = true;
+        double bc = 0.0;
+        const int64_t cnt = (c.y || c.aux_vec) ? a.N : 1;
+        if (int rc = binom_stats(c.y, (int)c.y_scalar, c.aux_vec, (int)c.aux, cnt, &ok,
+                                 &bc))
+          return rc;
+        a.c0 += bc * (cnt == a.N ? 1.0 : Nd);
+      }
+      break;
+    }
     default:
       break;
   }
@@ -120,7 +137,10 @@ __global__ void __launch_bounds__(kGenThreads)
     else
       in.y = a.y ? (double)static_cast<const int*>(a.y)[row] : a.y_scalar;
     in.alpha = a.alpha_vec ? a.alpha_vec[row] : a.alpha;
-    in.aux = a.aux_vec ? a.aux_vec[row] : a.aux;
+    if constexpr (FAM == kBinomial)
+      in.aux = a.aux_ivec ? (double)a.aux_ivec[row] : a.aux;
+    else
+      in.aux = a.aux_vec ? a.aux_vec[row] : a.aux;
     double d1 = 0, d2 = 0;
     const double d = link_row<FAM>(a, xb, in, true, true, row, racc, tab, d1, d2);
     dvec[row] = d;
@@ -243,6 +263,9 @@ int launch_glm_generic(const GlmCall& c) {
       break;
     case kOrdered:
       rc = run_rows<kOrdered>(a, params, dvec, d1v, d2v, bp, grid);
+      break;
+    case kBinomial:
+      rc = run_rows<kBinomial>(a, params, dvec, d1v, d2v, bp, grid);
       break;
     default:
       return fail(SMC_ERR_INVALID_ARGUMENT, "unknown family %d", c.family);

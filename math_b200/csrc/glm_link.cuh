@@ -3,7 +3,7 @@
 // (glm_generic.cu).  Each follows the reference's branches line by line:
 //   normal_id_glm_lpdf.hpp L122-213, bernoulli_logit_glm_lpmf.hpp L105-164,
 //   poisson_log_glm_lpmf.hpp L107-161, neg_binomial_2_log_glm_lpmf.hpp L143-244,
-//   ordered_logistic_glm_lpmf.hpp L108-207.
+//   ordered_logistic_glm_lpmf.hpp L108-207, binomial_logit_glm_lpmf.hpp L104-154.
 #pragma once
 #include "device_math.cuh"
 #include "smc_internal.h"
@@ -24,6 +24,7 @@ struct FusedArgs {
   const double* alpha_vec;
   double alpha;
   const double* aux_vec;
+  const int* aux_ivec;  // binomial: per-row number of trials (else `aux`)
   double aux, log_aux, digamma_aux;
   const double* params_dev;  // beta[K] then cuts[ncuts]; NULL -> inline_params
   double* d_alpha_vec;
@@ -127,6 +128,20 @@ __device__ __forceinline__ double link_d(const FusedArgs& a, double xb,
     st.v0 = t;
     st.v1 = e;
     if (lead && valid && a.d_alpha_vec) a.d_alpha_vec[row] = d;
+  } else if constexpr (FAM == kBinomial) {
+    // binomial_logit_glm_lpmf.hpp L104-115, L131-132.  exp(-|theta|) serves both
+    // log_inv_logit (log_inv_logit.hpp L52-58) and log1m_inv_logit
+    // (log1m_inv_logit.hpp L44-50): their log1p_exp arguments are -|theta|
+    const double th = xb + in.alpha;
+    const double l = log1p(exp(-fabs(th)));
+    const double lil = th < 0.0 ? th - l : -l;
+    d = in.y - in.aux * exp(lil);
+    bad = !isfinite(th);
+    st.v0 = th;
+    st.v1 = l;
+    st.v2 = in.y;
+    st.v3 = in.aux;
+    if (lead && valid && a.d_alpha_vec) a.d_alpha_vec[row] = d;
   } else if constexpr (FAM == kPoisson) {
     const double th = xb + in.alpha;
     const double e = exp(th);
@@ -216,6 +231,11 @@ __device__ __forceinline__ void link_lp(const FusedArgs& a, const LinkStash<FAM>
   if constexpr (FAM == kBernoulli) {
     const double t = st.v0, e = st.v1;
     acc.lp += t > 20.0 ? -e : (t < -20.0 ? t : -log1p(e));  // L120-126
+  } else if constexpr (FAM == kBinomial) {
+    const double th = st.v0, l = st.v1, n = st.v2, nt = st.v3;
+    const double lil = th < 0.0 ? th - l : -l;
+    const double l1m = th > 0.0 ? -th - l : -l;
+    acc.lp += n * lil + (nt - n) * l1m;  // L114-115
   } else if constexpr (FAM == kNegBinomial) {
     const double th = st.v0, te = st.v1, y = st.v2, ph = st.v3;
     const double ypp = y + ph;

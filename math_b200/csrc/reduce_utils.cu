@@ -5,6 +5,7 @@
 // parameter-free term of the poisson / neg-binomial log density
 // (poisson_log_glm_lpmf.hpp L126-128, neg_binomial_2_log_glm_lpmf.hpp L163-169).
 #include <climits>
+#include <cmath>
 
 #include "smc_internal.h"
 
@@ -88,6 +89,158 @@ static int compute_stats(const smc_matrix* yc) {
   y->lgamma_sum = lg;
   y->range_valid = true;
   y->lgamma_valid = true;
+  return SMC_OK;
+}
+
+// ------------------------------------------------- binomial pair statistics
+// Device restatement of binomial_coefficient_log(N, n) for integer 0 <= n <= N
+// (prim/fun/binomial_coefficient_log.hpp L79-115) and what it calls: lbeta
+// (lbeta.hpp L64-118), lgamma_stirling_diff (lgamma_stirling_diff.hpp L44-76),
+// lgamma_stirling (lgamma_stirling.hpp L27-29).  Same branches, same constants.
+constexpr double kHalfLogTwoPi = 0.91893853320467274178032973640561764;
+constexpr double kStirlingUseful = 10.0;
+
+__host__ __device__ inline double lgamma_stirling_diff_dev(double x) {
+  if (x == 0.0) return (double)INFINITY;
+  if (x < kStirlingUseful) return lgamma(x) - (kHalfLogTwoPi + (x - 0.5) * log(x) - x);
+  const double series[6]
+      = {0.0833333333333333333333333,   -0.00277777777777777777777778,
+         0.000793650793650793650793651, -0.000595238095238095238095238,
+         0.000841750841750841750841751, -0.00191752691752691752691753};
+  double result = 0.0;
+  double multiplier = 1.0 / x;
+  const double inv_x_squared = multiplier * multiplier;
+#pragma unroll
+  for (int n = 0; n < 6; ++n) {
+    if (n > 0) multiplier *= inv_x_squared;
+    result += series[n] * multiplier;
+  }
+  return result;
+}
+
+__host__ __device__ inline double lbeta_dev(double a, double b) {
+  const double x = a < b ? a : b, y = a < b ? b : a;  // x is the smaller
+  if (x == 0.0) return (double)INFINITY;
+  if (y < kStirlingUseful) return lgamma(x) + lgamma(y) - lgamma(x + y);
+  const double x_over_xy = x / (x + y);
+  if (x < kStirlingUseful) {
+    const double sd = lgamma_stirling_diff_dev(y) - lgamma_stirling_diff_dev(x + y);
+    const double st = (y - 0.5) * log1p(-x_over_xy) + x * (1.0 - log(x + y));
+    return st + lgamma(x) + sd;
+  }
+  const double sd = lgamma_stirling_diff_dev(x) + lgamma_stirling_diff_dev(y)
+                    - lgamma_stirling_diff_dev(x + y);
+  const double st = (x - 0.5) * log(x_over_xy) + y * log1p(-x_over_xy) + kHalfLogTwoPi
+                    - 0.5 * log(y);
+  return st + sd;
+}
+
+__host__ __device__ inline double binomial_coefficient_log_dev(double n, double k) {
+  if (k > n / 2.0 + 1e-8) k = n - k;  // the more stable symmetric branch, L89-91
+  const double n_plus_1 = n + 1.0;
+  const double n_plus_1_mk = n_plus_1 - k;
+  if (k == 0.0) return 0.0;
+  if (n_plus_1 < kStirlingUseful)
+    return lgamma(n_plus_1) - lgamma(k + 1.0) - lgamma(n_plus_1_mk);
+  return -lbeta_dev(n_plus_1_mk, k + 1.0) - log1p(n);
+}
+
+__global__ void binom_stats_kernel(const int* __restrict__ n, int n_scalar,
+                                   const int* __restrict__ trials, int trials_scalar,
+                                   int64_t count, int* __restrict__ bad_out,
+                                   double* __restrict__ sum_out) {
+  __shared__ int s_bad[kRedThreads / 32];
+  __shared__ double s_sum[kRedThreads / 32];
+  int bad = 0;
+  double sum = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int ni = n ? n[i] : n_scalar;
+    const int Ni = trials ? trials[i] : trials_scalar;
+    if (ni < 0 || ni > Ni || Ni < 0)  // check_bounded / check_nonnegative, L98-99
+      bad = 1;
+    else
+      sum += binomial_coefficient_log_dev((double)Ni, (double)ni);
+  }
+  for (int o = 16; o; o >>= 1) {
+    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  }
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    s_bad[w] = bad;
+    s_sum[w] = sum;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int j = 1; j < kRedThreads / 32; ++j) {
+      bad |= s_bad[j];
+      sum += s_sum[j];
+    }
+    bad_out[blockIdx.x] = bad;
+    sum_out[blockIdx.x] = sum;
+  }
+}
+
+int binom_stats(const smc_matrix* n, int n_scalar, const smc_matrix* trials,
+                int trials_scalar, int64_t count, bool* in_support,
+                double* coef_sum) {
+  *in_support = true;
+  *coef_sum = 0.0;
+  if (count <= 0) return SMC_OK;
+  // the cache lives on whichever operand is a matrix (n first)
+  smc_matrix* owner = const_cast<smc_matrix*>(n ? n : trials);
+  if (!owner) {  // two broadcast scalars: one pair, evaluated on the host
+    *in_support = !(n_scalar < 0 || n_scalar > trials_scalar || trials_scalar < 0);
+    if (*in_support)
+      *coef_sum = binomial_coefficient_log_dev((double)trials_scalar, (double)n_scalar);
+    return SMC_OK;
+  }
+  const smc_matrix* partner = n ? trials : nullptr;
+  const int partner_scalar = n ? trials_scalar : n_scalar;
+  if (owner && owner->binom_valid && owner->binom_self_version == owner->version
+      && owner->binom_partner == (partner ? partner->data : nullptr)
+      && (partner ? owner->binom_partner_version == partner->version
+                  : owner->binom_partner_scalar == partner_scalar)) {
+    *in_support = owner->binom_in_support;
+    *coef_sum = owner->binom_coef_sum;
+    return SMC_OK;
+  }
+  if (int rc = ensure_ctx()) return rc;
+  Context& c = ctx();
+  int grid = (int)((count + kRedThreads - 1) / kRedThreads);
+  if (grid > c.sm_count * 8) grid = c.sm_count * 8;
+  const size_t bytes = (size_t)grid * 16;
+  if (int rc = ensure_scratch(bytes)) return rc;
+  if (int rc = ensure_out(bytes)) return rc;
+  double* sum_d = c.scratch;
+  int* bad_d = reinterpret_cast<int*>(c.scratch + grid);
+  binom_stats_kernel<<<grid, kRedThreads, 0, c.stream>>>(
+      n ? static_cast<const int*>(n->data) : nullptr, n_scalar,
+      trials ? static_cast<const int*>(trials->data) : nullptr, trials_scalar, count,
+      bad_d, sum_d);
+  SMC_CUDA(cudaGetLastError());
+  SMC_CUDA(cudaMemcpyAsync(c.out_host, c.scratch, bytes, cudaMemcpyDeviceToHost,
+                           c.stream));
+  SMC_CUDA(cudaStreamSynchronize(c.stream));
+  const int* bad_h = reinterpret_cast<const int*>(c.out_host + grid);
+  bool ok = true;
+  double sum = 0.0;
+  for (int b = 0; b < grid; ++b) {
+    ok = ok && bad_h[b] == 0;
+    sum += c.out_host[b];
+  }
+  *in_support = ok;
+  *coef_sum = sum;
+  if (owner) {
+    owner->binom_valid = true;
+    owner->binom_self_version = owner->version;
+    owner->binom_partner = partner ? partner->data : nullptr;
+    owner->binom_partner_version = partner ? partner->version : 0;
+    owner->binom_partner_scalar = partner_scalar;
+    owner->binom_in_support = ok;
+    owner->binom_coef_sum = sum;
+  }
   return SMC_OK;
 }
 

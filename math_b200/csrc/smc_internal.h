@@ -24,7 +24,8 @@ enum Family {
   kBernoulli = 1,
   kPoisson = 2,
   kNegBinomial = 3,
-  kOrdered = 4
+  kOrdered = 4,
+  kBinomial = 5
 };
 
 // Per-host-thread state: device, stream, reusable workspace.
@@ -83,8 +84,8 @@ struct GlmCall {
   double y_scalar = 0;
   const smc_matrix* alpha_vec = nullptr;
   double alpha = 0;
-  const smc_matrix* aux_vec = nullptr;  // sigma / phi vector
-  double aux = 0;                       // sigma / phi scalar
+  const smc_matrix* aux_vec = nullptr;  // sigma / phi vector (f64); binomial: trials (i32)
+  double aux = 0;                       // sigma / phi / trials scalar
   const double* beta_host = nullptr;    // K (by-value path)
   const double* cuts_host = nullptr;    // ncuts
   const double* params_dev = nullptr;   // beta[K] (+cuts) already on device
@@ -108,6 +109,13 @@ int launch_glm_generic(const GlmCall& c);
 int y_lgamma_sum(const smc_matrix* y, double* sum);
 // min / max of an i32 device vector (cached on the matrix).
 int y_range(const smc_matrix* y, int* lo, int* hi);
+// binomial_logit_glm_lpmf's data-only pieces over the successes n and the trials
+// N (each a device vector or a broadcast scalar; `count` = number of pairs):
+// *in_support = every 0 <= n_i <= N_i, *coef_sum = sum_i
+// binomial_coefficient_log(N_i, n_i).  Cached on the n (else N) handle.
+int binom_stats(const smc_matrix* n, int n_scalar, const smc_matrix* trials,
+                int trials_scalar, int64_t count, bool* in_support,
+                double* coef_sum);
 
 int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
                        const double* alpha_host, const double* beta_host,
@@ -133,4 +141,14 @@ struct smc_matrix {
   // cached min / max of an integer data vector (eager y-range checks)
   bool range_valid = false;
   int imin = 0, imax = 0;
+  // bumped by every call that writes the matrix: keys caches that involve a
+  // second matrix (the binomial pair statistics below)
+  uint64_t version = 0;
+  // cached binom_stats() of (this, partner): valid while both versions match
+  bool binom_valid = false;
+  const void* binom_partner = nullptr;
+  uint64_t binom_partner_version = 0, binom_self_version = 0;
+  int binom_partner_scalar = 0;
+  bool binom_in_support = false;
+  double binom_coef_sum = 0;
 };

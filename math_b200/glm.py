@@ -106,6 +106,29 @@ def poisson_log_glm_lpmf(y, x, alpha, beta, propto=False, var=("alpha", "beta"))
     return _glm4(lib().smc_poisson_log_glm, y, x, alpha, beta, propto, var)
 
 
+def binomial_logit_glm_lpmf(n, trials, x, alpha, beta, propto=False,
+                            var=("alpha", "beta")):
+    """prim/prob/binomial_logit_glm_lpmf.hpp L54-160: `n` successes out of
+    `trials` (the reference's N), each a scalar or an i32 MatrixCuda."""
+    flags = _flags(propto, var)
+    nv, ns = _split(n, int, "n")
+    tv, ts = _split(trials, int, "trials")
+    av, a0 = _split(alpha, float, "alpha")
+    b = _beta(beta, x.cols)
+    logp = C.c_double()
+    d_alpha = C.c_double()
+    d_beta = np.zeros(x.cols)
+    d_av = _vec_out(av is not None and flags & VAR_ALPHA, x.rows)
+    d_x = _dx_out(flags, x)
+    check(lib().smc_binomial_logit_glm(
+        _h(nv), ns, _h(tv), ts, x.handle, _h(av), a0, _dp(b), flags,
+        C.byref(logp), C.byref(d_alpha), _h(d_av), _dp(d_beta), _h(d_x)))
+    return GlmResult(logp.value,
+                     (d_av if av is not None else d_alpha.value)
+                     if flags & VAR_ALPHA else None,
+                     d_beta if flags & VAR_BETA else None, None, d_x)
+
+
 def normal_id_glm_lpdf(y, x, alpha, beta, sigma, propto=False,
                        var=("alpha", "beta", "sigma")):
     """prim/prob/normal_id_glm_lpdf.hpp L54-216."""

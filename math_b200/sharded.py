@@ -24,7 +24,7 @@ import numpy as np
 from ._lib import OUT_HEADER, check, lib
 
 FAMILY = {"normal_id": 0, "bernoulli_logit": 1, "poisson_log": 2,
-          "neg_binomial_2_log": 3, "ordered_logistic": 4}
+          "neg_binomial_2_log": 3, "ordered_logistic": 4, "binomial_logit": 5}
 
 
 def shard_rows(n_rows, world_size, rank):

@@ -627,3 +627,155 @@ int oracle_categorical_logit_glm(long N, long K, long C, const int* y, long ny,
   free(inv);
   return 0;
 }
+
+/* ----- binomial_logit_glm_lpmf ---------------------------------------------------
+ * (the seventh GLM)
+ * reference: prim/prob/binomial_logit_glm_lpmf.hpp L54-160 and the scalar
+ * kernels it uses: prim/fun/log_inv_logit.hpp L52-58, log1m_inv_logit.hpp L44-50,
+ * binomial_coefficient_log.hpp L79-141, lbeta.hpp L64-118,
+ * lgamma_stirling_diff.hpp L44-76, lgamma_stirling.hpp L27-29. */
+
+/* log_inv_logit.hpp L52-58 */
+double oracle_log_inv_logit(double u) {
+  if (u < 0.0) return u - oracle_log1p_exp(u);
+  return -oracle_log1p_exp(-u);
+}
+/* log1m_inv_logit.hpp L44-50 */
+double oracle_log1m_inv_logit(double u) {
+  if (u > 0.0) return -u - oracle_log1p_exp(-u);
+  return -oracle_log1p_exp(u);
+}
+
+#define HALF_LOG_TWO_PI 0.91893853320467274178032973640561764
+#define STIRLING_DIFF_USEFUL 10.0
+
+/* lgamma_stirling_diff.hpp L44-76 (x >= 0) */
+static double lgamma_stirling_diff(double x) {
+  static const double series[6]
+      = {0.0833333333333333333333333,   -0.00277777777777777777777778,
+         0.000793650793650793650793651, -0.000595238095238095238095238,
+         0.000841750841750841750841751, -0.00191752691752691752691753};
+  if (isnan(x)) return NAN;
+  if (x == 0) return INFINITY;
+  if (x < STIRLING_DIFF_USEFUL) /* lgamma(x) - lgamma_stirling(x) */
+    return oracle_lgamma(x) - (HALF_LOG_TWO_PI + (x - 0.5) * log(x) - x);
+  double result = 0.0;
+  double multiplier = 1.0 / x;
+  const double inv_x_squared = multiplier * multiplier;
+  for (int n = 0; n < 6; ++n) {
+    if (n > 0) multiplier *= inv_x_squared;
+    result += series[n] * multiplier;
+  }
+  return result;
+}
+
+/* lbeta.hpp L64-118 (a, b >= 0) */
+static double lbeta(double a, double b) {
+  if (isnan(a) || isnan(b)) return NAN;
+  double x, y; /* x is the smaller of the two */
+  if (a < b) {
+    x = a;
+    y = b;
+  } else {
+    x = b;
+    y = a;
+  }
+  if (x == 0) return INFINITY;
+  if (isinf(y)) return -INFINITY;
+  if (y < STIRLING_DIFF_USEFUL) /* both small */
+    return oracle_lgamma(x) + oracle_lgamma(y) - oracle_lgamma(x + y);
+  const double x_over_xy = x / (x + y);
+  if (x < STIRLING_DIFF_USEFUL) { /* y large, x small */
+    const double sd = lgamma_stirling_diff(y) - lgamma_stirling_diff(x + y);
+    const double st = (y - 0.5) * log1p(-x_over_xy) + x * (1 - log(x + y));
+    return st + oracle_lgamma(x) + sd;
+  }
+  /* both large */
+  const double sd = lgamma_stirling_diff(x) + lgamma_stirling_diff(y)
+                    - lgamma_stirling_diff(x + y);
+  const double st = (x - 0.5) * log(x_over_xy) + y * log1p(-x_over_xy)
+                    + HALF_LOG_TWO_PI - 0.5 * log(y);
+  return st + sd;
+}
+
+/* binomial_coefficient_log.hpp L79-115, value only; the GLM has already
+ * checked 0 <= k <= n, so the function's own domain checks cannot fire */
+double oracle_binomial_coefficient_log(double n, double k) {
+  if (isnan(n) || isnan(k)) return NAN;
+  if (n > -1 && k > n / 2.0 + 1e-8) /* the more stable symmetric branch */
+    return oracle_binomial_coefficient_log(n, n - k);
+  const double n_plus_1 = n + 1;
+  const double n_plus_1_mk = n_plus_1 - k;
+  if (k == 0) return 0;
+  if (n_plus_1 < STIRLING_DIFF_USEFUL)
+    return oracle_lgamma(n_plus_1) - oracle_lgamma(k + 1)
+           - oracle_lgamma(n_plus_1_mk);
+  return -lbeta(n_plus_1_mk, k + 1) - log1p(n);
+}
+
+/* n: successes (nn = 1 or N), Nt: trials (nNt = 1 or N) */
+int oracle_binomial_logit_glm(long N, long K, const int* n, long nn,
+                              const int* Nt, long nNt, const double* x, long ldx,
+                              const double* alpha, long nalpha,
+                              const double* beta, unsigned flags, double* logp,
+                              double* d_alpha, double* d_beta, double* d_x) {
+  /* size_zero(n, N, alpha, beta, x) L76-78: tested BEFORE the size checks */
+  if (N == 0 || K == 0 || nn == 0 || nNt == 0 || nalpha == 0) {
+    if (logp) *logp = 0;
+    return 0;
+  }
+  if ((flags & F_PROPTO)
+      && !(flags & (F_VAR_X | F_VAR_ALPHA | F_VAR_BETA))) { /* L80-82 */
+    if (logp) *logp = 0;
+    return 0;
+  }
+  if ((nn != 1 && nNt != 1 && nn != nNt) || bad_len(nn, N) || bad_len(nNt, N)
+      || bad_len(nalpha, N))
+    return 1; /* L88-93 */
+  const long nb = nn > nNt ? nn : nNt;
+  for (long i = 0; i < nb; ++i) /* check_bounded(n, 0, N) L98 */
+    if (BR(n, nn, i) < 0 || BR(n, nn, i) > BR(Nt, nNt, i)) return 2;
+  for (long i = 0; i < nNt; ++i) /* check_nonnegative(N) L99 */
+    if (Nt[i] < 0) return 2;
+  double* th = (double*)malloc(sizeof(double) * (size_t)N);
+  double* d = (double*)malloc(sizeof(double) * (size_t)N);
+  xbeta(N, K, x, ldx, beta, th);
+  acc_t lp = {0, 0};
+  for (long i = 0; i < N; ++i) {
+    const double ni = BR(n, nn, i), Ni = BR(Nt, nNt, i);
+    th[i] += BR(alpha, nalpha, i); /* L104-109 */
+    const double lil = oracle_log_inv_logit(th[i]); /* L112 */
+    acc_add(&lp, ni * lil + (Ni - ni) * oracle_log1m_inv_logit(th[i])); /* L114-115 */
+    d[i] = ni - Ni * exp(lil); /* L131-132 */
+  }
+  double lpv = acc_get(&lp);
+  if (!isfinite(lpv)) { /* L118-122: beta, alpha, x itself */
+    int ok = all_finite(beta, K) && all_finite(alpha, nalpha);
+    for (long k = 0; ok && k < K; ++k)
+      ok = all_finite(x + (size_t)k * (size_t)ldx, N);
+    if (!ok) {
+      free(th);
+      free(d);
+      return 2;
+    }
+  }
+  if (!(flags & F_PROPTO)) { /* include_summand<propto, T_n, T_N> L124-127 */
+    acc_t bc = {0, 0};
+    for (long i = 0; i < nb; ++i)
+      acc_add(&bc, oracle_binomial_coefficient_log(BR(Nt, nNt, i), BR(n, nn, i)));
+    const double broadcast_n = nb == N ? 1.0 : (double)N;
+    lpv += acc_get(&bc) * broadcast_n;
+  }
+  if (logp) *logp = lpv;
+  xt_d(N, K, x, ldx, d, d_beta); /* L139 */
+  outer_bd(N, K, beta, d, d_x);  /* L148-150 */
+  if (d_alpha) {                 /* L152-154 */
+    if (nalpha == 1)
+      d_alpha[0] = sum_vec(d, N);
+    else
+      memcpy(d_alpha, d, sizeof(double) * (size_t)N);
+  }
+  free(th);
+  free(d);
+  return 0;
+}

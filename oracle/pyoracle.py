@@ -51,9 +51,12 @@ def oracle_lib():
             build_oracle()
         _oracle = C.CDLL(path)
         for n in ("oracle_lgamma", "oracle_digamma", "oracle_log1p_exp",
-                  "oracle_log1m_exp"):
+                  "oracle_log1m_exp", "oracle_log_inv_logit",
+                  "oracle_log1m_inv_logit"):
             getattr(_oracle, n).restype = C.c_double
             getattr(_oracle, n).argtypes = [C.c_double]
+        _oracle.oracle_binomial_coefficient_log.restype = C.c_double
+        _oracle.oracle_binomial_coefficient_log.argtypes = [C.c_double, C.c_double]
     return _oracle
 
 
@@ -66,9 +69,12 @@ def ref_lib(mt=False):
     if mt not in _ref:
         name = "libstan_ref_mt.so" if mt else "libstan_ref.so"
         lib = C.CDLL(os.path.join(HERE, "_ref", name))
-        for n in ("ref_digamma", "ref_lgamma", "ref_log1p_exp", "ref_log1m_exp"):
+        for n in ("ref_digamma", "ref_lgamma", "ref_log1p_exp", "ref_log1m_exp",
+                  "ref_log_inv_logit", "ref_log1m_inv_logit"):
             getattr(lib, n).restype = C.c_double
             getattr(lib, n).argtypes = [C.c_double]
+        lib.ref_binomial_coefficient_log.restype = C.c_double
+        lib.ref_binomial_coefficient_log.argtypes = [C.c_double, C.c_double]
         lib.ref_time_glm.restype = C.c_double
         lib.ref_time_glm.argtypes = [C.c_int, _L, _L, C.c_void_p, _dp,
                                      C.c_double, _dp, C.c_double, C.c_int, _dp,
@@ -142,6 +148,35 @@ def bernoulli_logit_glm(y, x, alpha, beta, flags=VAR_ALPHA | VAR_BETA,
 
 def poisson_log_glm(y, x, alpha, beta, flags=VAR_ALPHA | VAR_BETA, impl="oracle"):
     return bernoulli_logit_glm(y, x, alpha, beta, flags, impl, poisson=True)
+
+
+def binomial_logit_glm(n, trials, x, alpha, beta, flags=VAR_ALPHA | VAR_BETA,
+                       impl="oracle"):
+    """binomial_logit_glm_lpmf(n | N, x, alpha, beta): `n` successes, `trials`
+    the population sizes N (each a scalar or an N-vector)."""
+    x = _prep_x(x)
+    N, K = x.shape
+    n = _vec(n, np.int32)
+    trials = _vec(trials, np.int32)
+    alpha = _vec(alpha, np.float64)
+    beta = _vec(beta, np.float64)
+    assert beta.size == K
+    logp = np.zeros(1)
+    d_alpha = np.zeros(alpha.size)
+    d_beta = np.zeros(K)
+    d_x = np.zeros((N, K), order="F") if flags & VAR_X else None
+    if impl == "oracle":
+        rc = oracle_lib().oracle_binomial_logit_glm(
+            _L(N), _L(K), _i(n), _L(n.size), _i(trials), _L(trials.size), _d(x),
+            _L(max(N, 1)), _d(alpha), _L(alpha.size), _d(beta), C.c_uint(flags),
+            _d(logp), _d(d_alpha), _d(d_beta), _d(d_x))
+    else:
+        propto, dv = _ref_flags(flags | VAR_AUX)
+        rc = ref_lib().ref_binomial_logit_glm(
+            _L(N), _L(K), _i(n), _L(n.size), _i(trials), _L(trials.size), _d(x),
+            _d(alpha), _L(alpha.size), _d(beta), propto, dv, _d(logp),
+            _d(d_alpha), _d(d_beta), _d(d_x))
+    return _finish(rc, logp, d_alpha=d_alpha, d_beta=d_beta, d_x=d_x)
 
 
 def normal_id_glm(y, x, alpha, beta, sigma, flags=ALL_PARAMS, impl="oracle"):

@@ -414,6 +414,68 @@ int ref_categorical_logit_glm(long N, long K, long C, const int* y, long ny,
   });
 }
 
+// ----------------------------------------------------------------- binomial
+// reference: stan/math/prim/prob/binomial_logit_glm_lpmf.hpp L54-160
+// n: successes (nn = 1 or N), Nt: trials (nNt = 1 or N).
+int ref_binomial_logit_glm(long N, long K, const int* n, long nn, const int* Nt,
+                           long nNt, const double* x, const double* alpha,
+                           long nalpha, const double* beta, int propto,
+                           int data_var, double* logp, double* d_alpha,
+                           double* d_beta, double* d_x) {
+  return guarded([&] {
+    with_bool(propto, [&](auto P) {
+      with_bool(data_var, [&](auto XV) {
+        with_bool(nalpha != 1, [&](auto AV) {
+          with_bool(nn != 1, [&](auto YV) {
+            with_bool(nNt != 1, [&](auto TV) {
+              using TX = std::conditional_t<decltype(XV)::value, var, double>;
+              auto xm = make_mat<TX>(x, N, K);
+              VecV b = make_vec<var>(beta, K);
+              auto run = [&](const auto& ns, const auto& Ns, const auto& aa) {
+                var lp = stan::math::binomial_logit_glm_lpmf<decltype(P)::value>(
+                    ns, Ns, xm, aa, b);
+                lp.grad();
+                if (logp) *logp = lp.val();
+                put_mat(d_beta, b);
+                if constexpr (decltype(XV)::value) put_mat(d_x, xm);
+                if constexpr (decltype(AV)::value)
+                  put_mat(d_alpha, aa);
+                else
+                  put(d_alpha, aa);
+              };
+              auto with_alpha = [&](const auto& ns, const auto& Ns) {
+                if constexpr (decltype(AV)::value) {
+                  VecV a = make_vec<var>(alpha, nalpha);
+                  run(ns, Ns, a);
+                } else {
+                  var a = alpha[0];
+                  run(ns, Ns, a);
+                }
+              };
+              auto with_trials = [&](const auto& ns) {
+                if constexpr (decltype(TV)::value) {
+                  VecI Ns(Nt, Nt + nNt);
+                  with_alpha(ns, Ns);
+                } else {
+                  int Ns = Nt[0];
+                  with_alpha(ns, Ns);
+                }
+              };
+              if constexpr (decltype(YV)::value) {
+                VecI ns(n, n + nn);
+                with_trials(ns);
+              } else {
+                int ns = n[0];
+                with_trials(ns);
+              }
+            });
+          });
+        });
+      });
+    });
+  });
+}
+
 // ------------------------------------------------------------ scalar helpers
 // reference: prim/fun/digamma.hpp L47-49, lgamma.hpp L63-67, log1p_exp.hpp
 // L45-52, log1m_exp.hpp L47-57 -- exposed so the C restatement of each scalar
@@ -422,6 +484,13 @@ double ref_digamma(double x) { return stan::math::digamma(x); }
 double ref_lgamma(double x) { return stan::math::lgamma(x); }
 double ref_log1p_exp(double x) { return stan::math::log1p_exp(x); }
 double ref_log1m_exp(double x) { return stan::math::log1m_exp(x); }
+// log_inv_logit.hpp L52-58, log1m_inv_logit.hpp L44-50,
+// binomial_coefficient_log.hpp L79-141 (binomial_logit_glm_lpmf's kernels)
+double ref_log_inv_logit(double x) { return stan::math::log_inv_logit(x); }
+double ref_log1m_inv_logit(double x) { return stan::math::log1m_inv_logit(x); }
+double ref_binomial_coefficient_log(double n, double k) {
+  return stan::math::binomial_coefficient_log(n, k);
+}
 
 // ------------------------------------------------------------------- timing
 // CPU baseline #1: the reference prim path, single call on

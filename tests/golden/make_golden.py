@@ -47,6 +47,9 @@ def run(fam, d, flags):
         return po.normal_id_glm(d["y"], d["x"], d["alpha"], d["beta"], d["sigma"], flags, "ref")
     if fam == "neg_binomial":
         return po.neg_binomial_2_log_glm(d["y"], d["x"], d["alpha"], d["beta"], d["phi"], flags, "ref")
+    if fam == "binomial":
+        return po.binomial_logit_glm(d["y"], d["trials"], d["x"], d["alpha"], d["beta"],
+                                     flags, "ref")
     if fam == "ordered":
         return po.ordered_logistic_glm(d["y"], d["x"], d["beta"], d["cuts"], flags, "ref")
     return po.categorical_logit_glm(d["y"], d["x"], d["alpha"], d["beta"], flags, "ref")
@@ -70,15 +73,32 @@ def fixed_cases():
     ]
 
 
-def random_cases():
+def binomial_fixed_cases():
+    """Inputs of test/unit/math/opencl/rev/binomial_logit_glm_lpmf_test.cpp
+    (small_simple: n = {0, 1, 0}, N = {1, 2, 3}) and scalar broadcasts."""
+    x = np.array([[-12, 46], [-42, 24], [25, 27]], float) / 100
+    return [
+        ("binomial", "ref_test_fixed", dict(y=[0, 1, 0], trials=[1, 2, 3], x=x, alpha=0.3,
+                                            beta=[0.3, 2.0])),
+        ("binomial", "broadcast_trials", dict(y=[0, 11, 30], trials=[30], x=x, alpha=0.3,
+                                              beta=[0.3, 2.0])),
+        ("binomial", "broadcast_both", dict(y=[7], trials=[19], x=x, alpha=-0.2,
+                                            beta=[0.3, 2.0])),
+        ("binomial", "saturated_tails", dict(y=[3, 0, 500], trials=[3, 8, 1000],
+                                             x=x * 100, alpha=0.3, beta=[0.3, 2.0])),
+    ]
+
+
+def random_cases(families=("bernoulli", "poisson", "normal", "neg_binomial", "ordered",
+                           "categorical")):
     cases = []
-    for fam in ("bernoulli", "poisson", "normal", "neg_binomial", "ordered", "categorical"):
-        big = (153, 71, 43, "big") if fam in ("bernoulli", "neg_binomial",
+    for fam in families:
+        big = (153, 71, 43, "big") if fam in ("bernoulli", "neg_binomial", "binomial",
                                                "categorical") else (64, 17, 9, "big")
         for (N, K, C, tag) in ((3, 2, 3, "small_simple"), big,
                                (40, 5, 4, "mid"), (17, 1, 2, "one_attribute")):
             for vec in ((False, True) if fam in ("bernoulli", "poisson", "normal",
-                                                 "neg_binomial") else (False,)):
+                                                 "neg_binomial", "binomial") else (False,)):
                 if tag == "big" and vec:
                     continue
                 d = make_inputs(fam, N, K, seed=1000 + N * 7 + K, C=C, vec_alpha=vec,
@@ -87,6 +107,8 @@ def random_cases():
         # broadcast_y: one scalar response for every instance
         d = make_inputs(fam, 9, 3, seed=77, C=4)
         d["y"] = [float(d["y"][0])] if fam == "normal" else [int(d["y"][0])]
+        if fam == "binomial":
+            d["trials"] = np.maximum(d["trials"], d["y"][0])
         cases.append((fam, "broadcast_y", d))
     return cases
 
@@ -95,8 +117,17 @@ def main():
     if not po.ref_available():
         raise SystemExit("oracle/_ref/libstan_ref.so missing: run `make -C oracle ref` "
                          "in the container that has /root/reference")
+    if len(sys.argv) > 1 and sys.argv[1] == "binomial":
+        # the seventh GLM has its own fixture: python tests/golden/make_golden.py binomial
+        write(binomial_fixed_cases() + random_cases(("binomial",)),
+              os.path.join(os.path.dirname(OUT), "binomial_golden.json"))
+    else:
+        write(fixed_cases() + random_cases(), OUT)
+
+
+def write(all_cases, path):
     out = []
-    for fam, tag, d in fixed_cases() + random_cases():
+    for fam, tag, d in all_cases:
         variants = []
         for propto in (False, True):
             for xvar in (False, True):
@@ -113,12 +144,12 @@ def main():
                     "beta_shape": list(np.asarray(d["beta"]).shape),
                     "inputs": {k: tolist(v) for k, v in d.items()},
                     "variants": variants})
-    with open(OUT, "w") as f:
+    with open(path, "w") as f:
         json.dump({"generator": "tests/golden/make_golden.py",
                    "reference": "stan-dev/math 5.0.x at /root/reference, prim GLMs under "
                                 "reverse-mode var (oracle/ref_driver.cpp)",
                    "cases": out}, f)
-    print(f"wrote {len(out)} cases x variants to {OUT} ({os.path.getsize(OUT)/1e6:.2f} MB)")
+    print(f"wrote {len(out)} cases x variants to {path} ({os.path.getsize(path)/1e6:.2f} MB)")
 
 
 if __name__ == "__main__":

@@ -4,12 +4,18 @@ import os
 
 import numpy as np
 
-PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "glm_golden.json")
+HERE = os.path.dirname(os.path.abspath(__file__))
+PATH = os.path.join(HERE, "golden", "glm_golden.json")
+# the seventh GLM has its own fixture, same generator
+PATH_BINOMIAL = os.path.join(HERE, "golden", "binomial_golden.json")
 
 
 def load():
-    with open(PATH) as f:
-        return json.load(f)["cases"]
+    cases = []
+    for p in (PATH, PATH_BINOMIAL):
+        with open(p) as f:
+            cases += json.load(f)["cases"]
+    return cases
 
 
 def inputs_of(case):
@@ -21,7 +27,7 @@ def inputs_of(case):
             a = a.reshape((N, K), order="F")
         elif k == "beta" and len(case["beta_shape"]) == 2:
             a = a.reshape(tuple(case["beta_shape"]), order="F")
-        elif k == "y" and case["family"] != "normal":
+        elif k in ("y", "trials") and case["family"] != "normal":
             a = a.astype(np.int32)
         d[k] = a
     return d

@@ -35,6 +35,10 @@ def test_cuda_matches_reference_golden(gpu, case):
         if fam in ("bernoulli", "poisson"):
             fn = gpu.bernoulli_logit_glm_lpmf if fam == "bernoulli" else gpu.poisson_log_glm_lpmf
             r = fn(y, x, _dev(gpu, d["alpha"]), d["beta"], propto=v["propto"], var=var)
+        elif fam == "binomial":
+            r = gpu.binomial_logit_glm_lpmf(y, _dev(gpu, d["trials"]), x,
+                                            _dev(gpu, d["alpha"]), d["beta"],
+                                            propto=v["propto"], var=var)
         elif fam == "normal":
             r = gpu.normal_id_glm_lpdf(y, x, _dev(gpu, d["alpha"]), d["beta"],
                                        _dev(gpu, d["sigma"]), propto=v["propto"],

@@ -27,6 +27,9 @@ def run_oracle(fam, d, flags, impl="oracle"):
     if fam == "neg_binomial":
         return po.neg_binomial_2_log_glm(d["y"], d["x"], d["alpha"], d["beta"], d["phi"],
                                          flags, impl)
+    if fam == "binomial":
+        return po.binomial_logit_glm(d["y"], d["trials"], d["x"], d["alpha"], d["beta"],
+                                     flags, impl)
     if fam == "ordered":
         return po.ordered_logistic_glm(d["y"], d["x"], d["beta"], d["cuts"], flags, impl)
     return po.categorical_logit_glm(d["y"], d["x"], d["alpha"], d["beta"], flags, impl)
@@ -121,7 +124,7 @@ def test_zero_sizes():
 
 @pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref not built here")
 @pytest.mark.parametrize("fam", ["bernoulli", "poisson", "normal", "neg_binomial",
-                                 "ordered", "categorical"])
+                                 "ordered", "categorical", "binomial"])
 def test_oracle_matches_reference_live(fam):
     for seed, (N, K) in enumerate([(11, 3), (200, 17), (1000, 40)]):
         d = make_inputs(fam, N, K, seed=seed, C=5)
@@ -152,3 +155,49 @@ def test_scalar_kernels_match_reference():
         assert lib.oracle_log1p_exp(x) == ref.ref_log1p_exp(x)
         if x < 0:
             assert lib.oracle_log1m_exp(x) == ref.ref_log1m_exp(x)
+
+
+@pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref not built here")
+def test_binomial_scalar_kernels_match_reference():
+    """log_inv_logit / log1m_inv_logit bit for bit; binomial_coefficient_log over
+    every branch of lbeta (both small, one large, both large) and the symmetric
+    k > n/2 fold."""
+    lib, ref = po.oracle_lib(), po.ref_lib()
+    for u in np.concatenate([np.linspace(-60, 60, 241), [0.0, -0.0, 1e-300, -745.0, 710.0]]):
+        assert lib.oracle_log_inv_logit(u) == ref.ref_log_inv_logit(u)
+        assert lib.oracle_log1m_inv_logit(u) == ref.ref_log1m_inv_logit(u)
+    for n in [0, 1, 2, 8, 9, 10, 11, 18, 19, 20, 25, 100, 1000, 123456, 2_000_000_000]:
+        ks = sorted({0, 1, 2, n // 3, n // 2, n // 2 + 1, max(n - 9, 0), max(n - 1, 0), n})
+        for k in ks:
+            if k > n:
+                continue
+            a = lib.oracle_binomial_coefficient_log(float(n), float(k))
+            b = ref.ref_binomial_coefficient_log(float(n), float(k))
+            assert abs(a - b) <= 1e-14 * max(1.0, abs(b)), (n, k, a, b)
+
+
+def test_binomial_known_answers_and_errors():
+    """Exact small cases: log C(N, n) + n log p + (N - n) log(1 - p), and the
+    reference's error kinds (binomial_logit_glm_lpmf.hpp L88-99)."""
+    from math import comb, log
+    x = np.array([[0.5, -1.0], [0.25, 2.0], [-1.5, 0.75]])
+    beta, alpha = np.array([0.3, -0.2]), 0.1
+    n, trials = np.array([0, 3, 7]), np.array([4, 3, 12])
+    th = x @ beta + alpha
+    p = 1 / (1 + np.exp(-th))
+    want = sum(log(comb(int(N), int(k))) + k * log(pi) + (N - k) * log(1 - pi)
+               for k, N, pi in zip(n, trials, p))
+    r = po.binomial_logit_glm(n, trials, x, alpha, beta)
+    assert r["rc"] == 0 and r["logp"] == pytest.approx(want, rel=1e-13)
+    np.testing.assert_allclose(r["d_beta"], x.T @ (n - trials * p), rtol=1e-12)
+    assert r["d_alpha"][0] == pytest.approx(float(np.sum(n - trials * p)), rel=1e-12)
+    # propto drops the binomial coefficient only
+    r2 = po.binomial_logit_glm(n, trials, x, alpha, beta, flags=po.PROPTO | po.VAR_BETA)
+    coef = sum(log(comb(int(N), int(k))) for k, N in zip(n, trials))
+    assert r2["logp"] == pytest.approx(want - coef, rel=1e-13)
+    assert po.binomial_logit_glm([0, 5, 1], [4, 3, 12], x, alpha, beta)["rc"] == 2  # n > N
+    assert po.binomial_logit_glm([0, -1, 1], [4, 3, 12], x, alpha, beta)["rc"] == 2
+    assert po.binomial_logit_glm([0, 1], [4, 3, 12], x, alpha, beta)["rc"] == 1
+    assert po.binomial_logit_glm([0, 1, 1], [4, 3], x, alpha, beta)["rc"] == 1
+    assert po.binomial_logit_glm(n, trials, x, np.inf, beta)["rc"] == 2
+    assert po.binomial_logit_glm(n, trials, np.zeros((3, 0)), alpha, [])["logp"] == 0.0

@@ -40,6 +40,13 @@ def make_inputs(family, N, K, seed=12345, C=None, vec_alpha=False, vec_aux=False
     d = dict(x=x, beta=beta, alpha=alpha)
     if family == "bernoulli":
         d["y"] = (rng.random(N) < 1 / (1 + np.exp(-theta))).astype(np.int32)
+    elif family == "binomial":
+        # trials span both sides of binomial_coefficient_log's N + 1 < 10 switch
+        # and its lbeta branches (small/small, small/large, large/large)
+        trials = np.where(rng.random(N) < 0.5, rng.integers(0, 12, N),
+                          rng.integers(12, 400, N)).astype(np.int32)
+        d["trials"] = trials
+        d["y"] = rng.binomial(trials, 1 / (1 + np.exp(-theta))).astype(np.int32)
     elif family in ("poisson", "neg_binomial"):
         d["y"] = rng.integers(0, 5, N).astype(np.int32)
         if family == "neg_binomial":
