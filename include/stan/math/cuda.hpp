@@ -14,6 +14,7 @@
 #include <stan/math/cuda/rev/copy.hpp>
 #include <stan/math/cuda/rev/operands_and_partials.hpp>
 #include <stan/math/cuda/prim/bernoulli_logit_glm_lpmf.hpp>
+#include <stan/math/cuda/prim/binomial_logit_glm_lpmf.hpp>
 #include <stan/math/cuda/prim/poisson_log_glm_lpmf.hpp>
 #include <stan/math/cuda/prim/normal_id_glm_lpdf.hpp>
 #include <stan/math/cuda/prim/neg_binomial_2_log_glm_lpmf.hpp>
