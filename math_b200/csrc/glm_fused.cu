@@ -76,7 +76,9 @@ __device__ __forceinline__ RowRaw load_row(const FusedArgs& a, int64_t row) {
   return r;
 }
 
-template <int FAM, int G>
+// DX: d_x = beta (x) d is written (x is an autodiff variable); a compile-time
+// switch because the two cases want the per-row loads in different places.
+template <int FAM, int G, bool DX>
 __global__ void __launch_bounds__(256, 1)
     glm_fused_kernel(const __grid_constant__ CUtensorMap tmap,
                      const __grid_constant__ FusedArgs a) {
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(256, 1)
   double cacc[kCutsPerThread] = {0, 0, 0, 0};
   RowAcc racc;
   const bool need_beta = a.flags & SMC_VAR_BETA;
-  const bool need_dx = (a.flags & SMC_VAR_X) && a.d_x;
+  constexpr bool need_dx = DX;
   const bool need_cuts = FAM == kOrdered && (a.flags & SMC_VAR_AUX);
 
   // Thread 0 doubles as the TMA producer (a ninth warp would put three warps
@@ -204,6 +206,8 @@ __global__ void __launch_bounds__(256, 1)
       const int st = it % kStages;
       const int par = it & 1;
       const int tile = blockIdx.x + it * gridDim.x;
+      // per-row inputs of this tile: in flight while the partials are formed
+      if (!need_dx) nxt = load_row<FAM>(a, (int64_t)tile * R + rloc);
       if (tid == 0 && it >= 1) {
         // refill the slot tile it-1 occupied, once every warp has released it
         const int64_t nt = (int64_t)tile + (int64_t)(kStages - 1) * gridDim.x;
@@ -215,8 +219,6 @@ __global__ void __launch_bounds__(256, 1)
                       &full_bar[rs], pol);
         }
       }
-      // per-row inputs of this tile: in flight while the partials are formed
-      nxt = load_row<FAM>(a, (int64_t)tile * R + rloc);
       mbar_wait(&full_bar[st], (uint32_t)(it / kStages) & 1u);
       const double* xs
           = tiles + (size_t)st * (stage_bytes / 8) + (size_t)(32 * s) * R + rloc;
@@ -241,7 +243,10 @@ __global__ void __launch_bounds__(256, 1)
       }
     };
 
-    if (my_tiles > 0) stage_a(0);
+    if (my_tiles > 0) {
+      if (need_dx) nxt = load_row<FAM>(a, (int64_t)blockIdx.x * R + rloc);
+      stage_a(0);
+    }
     for (int it = 0; it < my_tiles; ++it) {
       const int par = it & 1;
       const int tile = blockIdx.x + it * gridDim.x;
@@ -249,6 +254,11 @@ __global__ void __launch_bounds__(256, 1)
       const bool valid = row < a.N;
       const bool lead = (it % S) == s;
       const RowRaw cur = nxt;
+      // d_x is written: the per-row inputs of the NEXT tile are requested before
+      // this tile's 32 streaming stores per thread, not behind them (ncu: 17 % of
+      // the samples waited for y at the top of this loop)
+      if (need_dx && it + 1 < my_tiles)
+        nxt = load_row<FAM>(a, row + (int64_t)gridDim.x * R);
       RowIn<FAM> in;
       if constexpr (FAM == kNormal)
         in.y = cur.y;
@@ -461,21 +471,29 @@ static int get_tmap(const smc_matrix* xc, int R, int CW, CUtensorMap* out) {
   return SMC_OK;
 }
 
-template <int FAM, int G>
-static int launch_tg(const CUtensorMap& tmap, const FusedArgs& a, int grid,
+template <int FAM, int G, bool DX>
+static int launch_tgx(const CUtensorMap& tmap, const FusedArgs& a, int grid,
                      int threads, size_t smem) {
   static size_t attr_smem[16] = {};
   Context& c = ctx();
   if (attr_smem[c.device & 15] < smem) {
-    SMC_CUDA(cudaFuncSetAttribute(glm_fused_kernel<FAM, G>,
+    SMC_CUDA(cudaFuncSetAttribute(glm_fused_kernel<FAM, G, DX>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     attr_smem[c.device & 15] = smem;
   }
-  glm_fused_kernel<FAM, G><<<grid, threads, smem, c.stream>>>(tmap, a);
+  glm_fused_kernel<FAM, G, DX><<<grid, threads, smem, c.stream>>>(tmap, a);
   SMC_CUDA(cudaGetLastError());
   c.launches += 1;
   return SMC_OK;
+}
+
+template <int FAM, int G>
+static int launch_tg(const CUtensorMap& tmap, const FusedArgs& a, int grid,
+                     int threads, size_t smem) {
+  return ((a.flags & SMC_VAR_X) && a.d_x)
+             ? launch_tgx<FAM, G, true>(tmap, a, grid, threads, smem)
+             : launch_tgx<FAM, G, false>(tmap, a, grid, threads, smem);
 }
 
 template <int FAM>

@@ -73,6 +73,30 @@ __device__ __forceinline__ void ordered_class_entry(const double* cuts, int ncut
   e[3] = 1.0 / (1.0 - ed);
 }
 
+// The first and last class of the ordered link carry +-inf cut points
+// (ordered_logistic_glm_lpmf.hpp L111-120), so with end classes in the data
+// nearly every warp holds a lane whose exp(-|cut|) is exactly 0 -- and a zero
+// numerator sends the WHOLE warp through the out-of-line slow path of the FP64
+// division, directly (0 / (1 + 0)) and inside log1p (0 / (2 + 0)); ncu showed
+// 15 % of the kernel's samples in that subroutine, called by 98 % of the warps.
+// These helpers divide / take log1p of a harmless 1.0 on such lanes and select
+// the exact result (0) afterwards: same bits, inline path only.  The empty asm
+// keeps the compiler from folding the select back into the division.
+__device__ __forceinline__ double opaque(double v) {
+  asm volatile("" : "+d"(v));
+  return v;
+}
+__device__ __forceinline__ double div_or_zero(double num, double den) {
+  const bool z = num == 0.0;
+  const double q = opaque(z ? 1.0 : num) / den;
+  return z ? 0.0 : q;
+}
+__device__ __forceinline__ double log1p_or_zero(double e) {
+  const bool z = e == 0.0;
+  const double l = log1p(opaque(z ? 1.0 : e));
+  return z ? 0.0 : l;
+}
+
 // Fills everything in `a` that does not depend on the kernel variant: shapes,
 // pointers, flags, host-side constants of the log density (c0, log phi, ...).
 int prepare_args(const GlmCall& c, FusedArgs* a);
@@ -198,8 +222,8 @@ __device__ __forceinline__ double link_d(const FusedArgs& a, double xb,
     // cut <= 0 it IS exp(cut) -- same argument, same bits
     const double e1 = exp(-fabs(cut1)), e2 = exp(-fabs(cut2));
     // (one division per select: the numerator is chosen, the quotient is the same)
-    const double d1 = (cut2 > 0.0 ? e2 : 1.0) / (1.0 + e2) - ce[2];
-    const double d2 = ce[3] - (cut1 > 0.0 ? e1 : 1.0) / (1.0 + e1);
+    const double d1 = div_or_zero(cut2 > 0.0 ? e2 : 1.0, 1.0 + e2) - ce[2];
+    const double d2 = ce[3] - div_or_zero(cut1 > 0.0 ? e1 : 1.0, 1.0 + e1);
     d = d1 - d2;
     d1o = d1;
     d2o = d2;
@@ -269,8 +293,8 @@ __device__ __forceinline__ void link_lp(const FusedArgs& a, const LinkStash<FAM>
   } else if constexpr (FAM == kOrdered) {
     const double cut1 = st.v0, cut2 = st.v1, e1 = st.v2, e2 = st.v3;
     const int C = a.ncuts + 1;
-    const double A = (cut1 > 0.0 ? -cut1 : 0.0) - log1p(e1);
-    const double B = (cut2 <= 0.0 ? cut2 : 0.0) - log1p(e2);
+    const double A = (cut1 > 0.0 ? -cut1 : 0.0) - log1p_or_zero(e1);
+    const double B = (cut2 <= 0.0 ? cut2 : 0.0) - log1p_or_zero(e2);
     if (st.c == 1)
       acc.lp += A;
     else if (st.c == C)
