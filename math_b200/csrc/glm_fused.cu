@@ -34,7 +34,8 @@
 
 namespace smc {
 
-constexpr int kStages = 3;
+constexpr int kStagesX = 3, kStagesDx = 2;
+constexpr uint32_t kSlabBytes = 32 * 32 * 8;  // one warp's 32 rows x 32 columns
 constexpr int kCutsPerThread = 4;
 constexpr int kFastCuts = 16;  // up to this many cut points: lane-private d_cuts slots
 
@@ -81,7 +82,11 @@ __device__ __forceinline__ RowRaw load_row(const FusedArgs& a, int64_t row) {
 template <int FAM, int G, bool DX>
 __global__ void __launch_bounds__(256, 1)
     glm_fused_kernel(const __grid_constant__ CUtensorMap tmap,
+                     const __grid_constant__ CUtensorMap tmap_dx,
                      const __grid_constant__ FusedArgs a) {
+  // d_x leaves through per-warp staging slabs and TMA bulk stores; the ring gives
+  // up one stage to make room for them
+  constexpr int kStages = DX ? kStagesDx : kStagesX;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int S = a.S;
   constexpr int R = 32 * G;
@@ -92,6 +97,8 @@ __global__ void __launch_bounds__(256, 1)
   // shared-memory carve-up
   double* tiles = reinterpret_cast<double*>(smem_raw);
   unsigned char* p = smem_raw + (size_t)kStages * stage_bytes;
+  double* dx_stage = reinterpret_cast<double*>(p);  // [warps][32 cols][32 rows]
+  if (DX) p += (size_t)n_cons_warps * kSlabBytes;
   double* beta_s = reinterpret_cast<double*>(p);  // CW doubles
   p += (size_t)CW * 8;
   double* cuts_s = reinterpret_cast<double*>(p);  // ncuts (padded) doubles
@@ -172,6 +179,7 @@ __global__ void __launch_bounds__(256, 1)
   // on one SM sub-partition and cap every thread at 168 registers).  Prologue:
   // fill the ring.
   uint64_t pol = 0;
+  const uint64_t pol_dx = DX && lane == 0 ? policy_evict_first() : 0;
   if (tid == 0) {
     pol = policy_evict_first();
     for (int j = 0; j < kStages; ++j) {
@@ -290,11 +298,22 @@ __global__ void __launch_bounds__(256, 1)
 #pragma unroll
         for (int kk = 0; kk < kColsPerThread; ++kk) acc[kk] = fma(xv[kk], d, acc[kk]);
       }
-      if (need_dx && valid) {
-        double* dx = a.d_x + (size_t)(32 * s) * a.ld_dx + row;
+      if constexpr (DX) {
+        // d_x = beta (x) d: the warp fills its staging slab (lane = row, conflict
+        // free) and hands it to ONE TMA bulk store -- no per-element addresses, no
+        // LSU store traffic; rows >= N and columns >= K are clipped by the map.
+        // The previous tile's store has long since read the slab.
+        double* xo = dx_stage + (size_t)warp * (kSlabBytes / 8);
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
 #pragma unroll
-        for (int kk = 0; kk < kColsPerThread; ++kk)
-          if (32 * s + kk < a.K) st_stream(dx + (size_t)kk * a.ld_dx, bs[kk] * d);
+        for (int kk = 0; kk < kColsPerThread; ++kk) xo[kk * 32 + lane] = bs[kk] * d;
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmap_dx, tile * R + 32 * g, 32 * s, xo, pol_dx);
+          bulk_commit();
+        }
       }
       if constexpr (FAM == kOrdered) {
         if (need_cuts && fast_cuts) {
@@ -342,6 +361,7 @@ __global__ void __launch_bounds__(256, 1)
   }
 
   // ------------------------------------------------ CTA-level reduction
+  if (DX && lane == 0) bulk_wait_read0();  // the last d_x slabs have left
   __syncthreads();  // every tile consumed; the ring is reusable as scratch
   double* red = tiles;  // [G][pstride]
   const int ps = a.pstride;
@@ -472,8 +492,8 @@ static int get_tmap(const smc_matrix* xc, int R, int CW, CUtensorMap* out) {
 }
 
 template <int FAM, int G, bool DX>
-static int launch_tgx(const CUtensorMap& tmap, const FusedArgs& a, int grid,
-                     int threads, size_t smem) {
+static int launch_tgx(const CUtensorMap& tmap, const CUtensorMap& tmap_dx,
+                      const FusedArgs& a, int grid, int threads, size_t smem) {
   static size_t attr_smem[16] = {};
   Context& c = ctx();
   if (attr_smem[c.device & 15] < smem) {
@@ -482,32 +502,32 @@ static int launch_tgx(const CUtensorMap& tmap, const FusedArgs& a, int grid,
                                   (int)smem));
     attr_smem[c.device & 15] = smem;
   }
-  glm_fused_kernel<FAM, G, DX><<<grid, threads, smem, c.stream>>>(tmap, a);
+  glm_fused_kernel<FAM, G, DX><<<grid, threads, smem, c.stream>>>(tmap, tmap_dx, a);
   SMC_CUDA(cudaGetLastError());
   c.launches += 1;
   return SMC_OK;
 }
 
 template <int FAM, int G>
-static int launch_tg(const CUtensorMap& tmap, const FusedArgs& a, int grid,
-                     int threads, size_t smem) {
+static int launch_tg(const CUtensorMap& tmap, const CUtensorMap& tmap_dx,
+                     const FusedArgs& a, int grid, int threads, size_t smem) {
   return ((a.flags & SMC_VAR_X) && a.d_x)
-             ? launch_tgx<FAM, G, true>(tmap, a, grid, threads, smem)
-             : launch_tgx<FAM, G, false>(tmap, a, grid, threads, smem);
+             ? launch_tgx<FAM, G, true>(tmap, tmap_dx, a, grid, threads, smem)
+             : launch_tgx<FAM, G, false>(tmap, tmap_dx, a, grid, threads, smem);
 }
 
 template <int FAM>
-static int launch_t(const CUtensorMap& tmap, const FusedArgs& a, int grid,
-                    int threads, size_t smem) {
+static int launch_t(const CUtensorMap& tmap, const CUtensorMap& tmap_dx,
+                    const FusedArgs& a, int grid, int threads, size_t smem) {
   switch (a.G) {
     case 1:
-      return launch_tg<FAM, 1>(tmap, a, grid, threads, smem);
+      return launch_tg<FAM, 1>(tmap, tmap_dx, a, grid, threads, smem);
     case 2:
-      return launch_tg<FAM, 2>(tmap, a, grid, threads, smem);
+      return launch_tg<FAM, 2>(tmap, tmap_dx, a, grid, threads, smem);
     case 4:
-      return launch_tg<FAM, 4>(tmap, a, grid, threads, smem);
+      return launch_tg<FAM, 4>(tmap, tmap_dx, a, grid, threads, smem);
     default:
-      return launch_tg<FAM, 8>(tmap, a, grid, threads, smem);
+      return launch_tg<FAM, 8>(tmap, tmap_dx, a, grid, threads, smem);
   }
 }
 
@@ -549,11 +569,18 @@ int launch_glm_fused(const GlmCall& c) {
   a.counter = cx.counter;
   a.out = c.out;
 
-  CUtensorMap tmap;
+  CUtensorMap tmap, tmap_dx;
   if (int rc = get_tmap(x, R, CW, &tmap)) return rc;
+  const bool dx = (a.flags & SMC_VAR_X) && c.d_x;
+  tmap_dx = tmap;  // unused unless d_x is written
+  if (dx) {
+    if (int rc = get_tmap(c.d_x, 32, 32, &tmap_dx)) return rc;
+  }
 
+  const int kStages = dx ? kStagesDx : kStagesX;
   const size_t stage_bytes = (size_t)R * CW * 8;
-  size_t smem = kStages * stage_bytes + (size_t)CW * 8
+  size_t smem = kStages * stage_bytes + (dx ? (size_t)a.S * a.G * kSlabBytes : 0)
+                + (size_t)CW * 8
                 + (size_t)((a.ncuts + 1) & ~1) * 8
                 + (size_t)link_tab_doubles(c.family, a.ncuts, a.tab_n) * 8
                 + (c.family == kOrdered && a.ncuts <= kFastCuts
@@ -569,17 +596,17 @@ int launch_glm_fused(const GlmCall& c) {
 
   switch (c.family) {
     case kNormal:
-      return launch_t<kNormal>(tmap, a, grid, threads, smem);
+      return launch_t<kNormal>(tmap, tmap_dx, a, grid, threads, smem);
     case kBernoulli:
-      return launch_t<kBernoulli>(tmap, a, grid, threads, smem);
+      return launch_t<kBernoulli>(tmap, tmap_dx, a, grid, threads, smem);
     case kPoisson:
-      return launch_t<kPoisson>(tmap, a, grid, threads, smem);
+      return launch_t<kPoisson>(tmap, tmap_dx, a, grid, threads, smem);
     case kNegBinomial:
-      return launch_t<kNegBinomial>(tmap, a, grid, threads, smem);
+      return launch_t<kNegBinomial>(tmap, tmap_dx, a, grid, threads, smem);
     case kOrdered:
-      return launch_t<kOrdered>(tmap, a, grid, threads, smem);
+      return launch_t<kOrdered>(tmap, tmap_dx, a, grid, threads, smem);
     case kBinomial:
-      return launch_t<kBinomial>(tmap, a, grid, threads, smem);
+      return launch_t<kBinomial>(tmap, tmap_dx, a, grid, threads, smem);
   }
   return fail(SMC_ERR_INVALID_ARGUMENT, "unknown family %d", c.family);
 }

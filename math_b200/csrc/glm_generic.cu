@@ -290,7 +290,9 @@ int launch_glm_generic(const GlmCall& c) {
 
 int launch_glm(const GlmCall& c) {
   const char* force = getenv("SMC_FORCE_GENERIC");
-  if (fused_supported(c.x) && !(force && force[0] == '1')
+  // (d_x leaves the fused kernel through TMA stores: same layout rules as x)
+  const bool dx_ok = !((c.flags & SMC_VAR_X) && c.d_x) || fused_supported(c.d_x);
+  if (fused_supported(c.x) && dx_ok && !(force && force[0] == '1')
       && c.ncuts <= 4 * 32 * ((c.x->cols + 31) / 32))
     return launch_glm_fused(c);
   return launch_glm_generic(c);
