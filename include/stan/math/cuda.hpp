@@ -20,5 +20,7 @@
 #include <stan/math/cuda/prim/neg_binomial_2_log_glm_lpmf.hpp>
 #include <stan/math/cuda/prim/ordered_logistic_glm_lpmf.hpp>
 #include <stan/math/cuda/prim/categorical_logit_glm_lpmf.hpp>
+#include <stan/math/cuda/rev/multiply.hpp>
+#include <stan/math/cuda/prim/unfused_lpmf.hpp>
 
 #endif

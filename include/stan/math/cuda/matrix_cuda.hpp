@@ -186,6 +186,16 @@ using require_matrix_cuda_t = require_t<is_matrix_cuda<T>>;
 template <typename T>
 using require_not_matrix_cuda_t = require_not_t<is_matrix_cuda<T>>;
 
+// A device matrix is a non-scalar "kernel expression" in the sense of
+// prim/meta/is_kernel_expression.hpp L33-41: that is the hook with which the
+// reference switches its host implementations OFF for device operands
+// (require_all_not_nonscalar_prim_or_rev_kernel_expression_t on every prim
+// density, e.g. prim/prob/bernoulli_logit_lpmf.hpp L34-36), leaving the device
+// overload as the only candidate.
+template <typename T>
+struct is_kernel_expression_and_not_scalar<T, require_matrix_cuda_t<T>>
+    : std::true_type {};
+
 // scalar_type / value_type of a device matrix is its element type, so that
 // return_type_t, partials_return_t and include_summand treat matrix_cuda<double>
 // as `double` data.

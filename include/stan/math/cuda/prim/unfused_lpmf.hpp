@@ -1,0 +1,168 @@
+#ifndef STAN_MATH_CUDA_PRIM_UNFUSED_LPMF_HPP
+#define STAN_MATH_CUDA_PRIM_UNFUSED_LPMF_HPP
+// The un-fused densities on a device-resident linear predictor (SURVEY.md
+// 8(f)3): bernoulli_logit_lpmf, poisson_log_lpmf, neg_binomial_2_log_lpmf and
+// ordered_logistic_lpmf for a theta that is a matrix_cuda<double> or a
+// var_value<matrix_cuda<double>> -- the B200 overloads of
+//   prim/prob/bernoulli_logit_lpmf.hpp L33-98      (opencl/prim/bernoulli_logit_lpmf.hpp)
+//   prim/prob/poisson_log_lpmf.hpp L27-100         (opencl/prim/poisson_log_lpmf.hpp)
+//   prim/prob/neg_binomial_2_log_lpmf.hpp L24-134  (opencl/prim/neg_binomial_2_log_lpmf.hpp)
+//   prim/prob/ordered_logistic_lpmf.hpp L72-214    (opencl/prim/ordered_logistic_lpmf.hpp)
+// for models that add terms to x * beta before the likelihood.  Same names,
+// template order and <propto>; value and d/dtheta come from one kernel over the
+// N-vector and are attached through make_partials_propagator(...).build(logp).
+// The prim templates are switched off for device operands by the reference's own
+// kernel-expression trait (see matrix_cuda.hpp).
+#include <stan/math/cuda/prim/glm_common.hpp>
+
+namespace stan {
+namespace math {
+
+namespace cuda_internal {
+/** Sizes of the random variable and the parameter agree (check_consistent_sizes). */
+template <typename T_n, typename T_theta>
+inline void check_rv_size(const char* function, const T_n& n, const T_theta& theta) {
+  if (!is_stan_scalar<T_n>::value) {
+    check_size_match(function, "Size of ", "Random variable", operand_size(n),
+                     "size of ", "parameter", operand_size(theta));
+  }
+}
+/** Device handle of the partials of a device-var edge, else NULL. */
+template <typename T, typename Edge>
+inline smc_matrix* dvec_handle(Edge& edge_partials) {
+  if constexpr (is_var_matrix_cuda<T>::value) {
+    return edge_partials.handle();
+  } else {
+    return nullptr;
+  }
+}
+}  // namespace cuda_internal
+
+template <bool propto, typename T_n, typename T_prob,
+          require_t<is_cuda_operand<T_prob>>* = nullptr>
+return_type_t<T_prob> bernoulli_logit_lpmf(const T_n& n, const T_prob& theta) {
+  using namespace cuda_internal;  // NOLINT
+  static constexpr const char* function = "bernoulli_logit_lpmf(CUDA)";
+  check_rv_size(function, n, theta);
+  if (theta.size() == 0 || operand_size(n) == 0) {
+    return 0.0;
+  }
+  row_operand<int, T_n> n_op(n);
+  auto ops_partials = make_partials_propagator(theta);
+  double logp = 0;
+  const unsigned flags = (propto ? SMC_PROPTO : 0u) | var_flag<T_prob>(SMC_VAR_ALPHA);
+  check_cuda_status(function,
+                    smc_bernoulli_logit_lpmf(n_op.handle(), n_op.scalar(),
+                                             x_handle(theta), flags, &logp,
+                                             dvec_handle<T_prob>(partials<0>(ops_partials))));
+  if (!include_summand<propto, T_prob>::value) {
+    return 0.0;
+  }
+  return ops_partials.build(logp);
+}
+
+template <bool propto, typename T_n, typename T_log_rate,
+          require_t<is_cuda_operand<T_log_rate>>* = nullptr>
+return_type_t<T_log_rate> poisson_log_lpmf(const T_n& n, const T_log_rate& alpha) {
+  using namespace cuda_internal;  // NOLINT
+  static constexpr const char* function = "poisson_log_lpmf(CUDA)";
+  check_rv_size(function, n, alpha);
+  row_operand<int, T_n> n_op(n);
+  if (n_op.handle() == nullptr) {
+    check_nonnegative(function, "Random variable", n_op.scalar());
+  }
+  if (alpha.size() == 0 || operand_size(n) == 0) {
+    return 0.0;
+  }
+  auto ops_partials = make_partials_propagator(alpha);
+  double logp = 0;
+  const unsigned flags
+      = (propto ? SMC_PROPTO : 0u) | var_flag<T_log_rate>(SMC_VAR_ALPHA);
+  check_cuda_status(function,
+                    smc_poisson_log_lpmf(n_op.handle(), n_op.scalar(), x_handle(alpha),
+                                         flags, &logp,
+                                         dvec_handle<T_log_rate>(partials<0>(ops_partials))));
+  if (!include_summand<propto, T_log_rate>::value) {
+    return 0.0;
+  }
+  return ops_partials.build(logp);
+}
+
+/** phi: an arithmetic or var scalar (a per-row phi goes through the GLM entry). */
+template <bool propto, typename T_n, typename T_log_location, typename T_precision,
+          require_t<is_cuda_operand<T_log_location>>* = nullptr,
+          require_stan_scalar_t<T_precision>* = nullptr>
+return_type_t<T_log_location, T_precision> neg_binomial_2_log_lpmf(
+    const T_n& n, const T_log_location& eta, const T_precision& phi) {
+  using namespace cuda_internal;  // NOLINT
+  static constexpr const char* function = "neg_binomial_2_log_lpmf(CUDA)";
+  check_rv_size(function, n, eta);
+  row_operand<int, T_n> n_op(n);
+  if (n_op.handle() == nullptr) {
+    check_nonnegative(function, "Failures variable", n_op.scalar());
+  }
+  check_positive_finite(function, "Precision parameter", value_of(phi));
+  if (eta.size() == 0 || operand_size(n) == 0) {
+    return 0.0;
+  }
+  auto ops_partials = make_partials_propagator(eta, phi);
+  double logp = 0, d_phi = 0;
+  const unsigned flags = (propto ? SMC_PROPTO : 0u)
+                         | var_flag<T_log_location>(SMC_VAR_ALPHA)
+                         | var_flag<T_precision>(SMC_VAR_AUX);
+  check_cuda_status(
+      function,
+      smc_neg_binomial_2_log_lpmf(n_op.handle(), n_op.scalar(), x_handle(eta), nullptr,
+                                  value_of(phi), flags, &logp,
+                                  dvec_handle<T_log_location>(partials<0>(ops_partials)),
+                                  &d_phi, nullptr));
+  if (!include_summand<propto, T_log_location, T_precision>::value) {
+    return 0.0;
+  }
+  if constexpr (!is_constant_all<T_precision>::value) {
+    partials<1>(ops_partials)[0] = d_phi;
+  }
+  return ops_partials.build(logp);
+}
+
+/** c: one host cut-point vector (Eigen column vector of double or var). */
+template <bool propto, typename T_y, typename T_loc, typename T_cut,
+          require_t<is_cuda_operand<T_loc>>* = nullptr,
+          require_col_vector_t<T_cut>* = nullptr>
+return_type_t<T_loc, T_cut> ordered_logistic_lpmf(const T_y& y, const T_loc& lambda,
+                                                  const T_cut& c) {
+  using namespace cuda_internal;  // NOLINT
+  static constexpr const char* function = "ordered_logistic_lpmf(CUDA)";
+  check_rv_size(function, y, lambda);
+  row_operand<int, T_y> y_op(y);
+  const Eigen::VectorXd cuts_val = host_values(c);
+  const int64_t n_cuts = operand_size(c);
+  auto ops_partials = make_partials_propagator(lambda, c);
+  double logp = 0;
+  Eigen::VectorXd d_cuts = Eigen::VectorXd::Zero(n_cuts);
+  const unsigned flags = (propto ? SMC_PROPTO : 0u) | var_flag<T_loc>(SMC_VAR_ALPHA)
+                         | var_flag<T_cut>(SMC_VAR_AUX);
+  if (lambda.size() == 0) {
+    return 0.0;
+  }
+  check_cuda_status(function,
+                    smc_ordered_logistic_lpmf(y_op.handle(), y_op.scalar(),
+                                              x_handle(lambda), cuts_val.data(), n_cuts,
+                                              flags, &logp,
+                                              dvec_handle<T_loc>(partials<0>(ops_partials)),
+                                              d_cuts.data()));
+  if (!include_summand<propto, T_loc, T_cut>::value) {
+    return 0.0;
+  }
+  if constexpr (!is_constant_all<T_cut>::value) {
+    store_host_partial<T_cut>(partials<1>(ops_partials), d_cuts.data(), n_cuts);
+  }
+  return ops_partials.build(logp);
+}
+
+// The propto = false forwarding overloads are the reference's own (last lines of
+// each prim/prob/*_lpmf.hpp): their <false> calls resolve to the overloads above.
+
+}  // namespace math
+}  // namespace stan
+#endif

@@ -120,6 +120,8 @@ int smc_matrix_copy(smc_matrix* dst, const smc_matrix* src);
  * (rev/functor/operands_and_partials.hpp L28-38). */
 int smc_matrix_axpy(smc_matrix* y, double a, const smc_matrix* x);
 /* Lazy value checks (cf. check_cl in opencl/prim/ *_glm_*.hpp). */
+/* y += a (every element) */
+int smc_matrix_add_scalar(smc_matrix* y, double a);
 int smc_matrix_all_finite(const smc_matrix* m, int* all_finite);
 int smc_matrix_int_range(const smc_matrix* m, int* min_out, int* max_out);
 /* Deterministic synthetic fill, identical on every GPU and reproducible on the
@@ -225,6 +227,50 @@ int smc_glm_eval_device(int family, const smc_matrix* y, double y_scalar,
                         double* out_dev, smc_matrix* d_alpha_vec,
                         smc_matrix* d_aux_vec, smc_matrix* d_y_vec,
                         smc_matrix* d_x);
+
+/* ---- the step either side of the GLMs ------------------ */
+/* Models that add terms to the linear predictor before the likelihood form
+ * theta on the device and call the un-fused density on it.  These replace what
+ * the OpenCL backend builds from its kernel generator: the matrix-vector
+ * product of opencl/prim/multiply.hpp + opencl/rev/multiply.hpp, and
+ * opencl/prim/{bernoulli_logit,poisson_log,neg_binomial_2_log,ordered_logistic}_lpmf.hpp. */
+
+/* theta_out[i] = sum_k x[i,k] beta[k] + alpha_i  (alpha_vec N x 1 or NULL ->
+ * the scalar alpha).  One sweep over x through the fused TMA kernel. */
+int smc_linear_predictor(const smc_matrix* x, const double* beta,
+                         const smc_matrix* alpha_vec, double alpha,
+                         smc_matrix* theta_out);
+/* Reverse sweep of the product: xt_v[k] = sum_i x[i,k] v[i] (K host doubles, may
+ * be NULL) and *sum_v = sum_i v[i] (may be NULL).  One sweep over x. */
+int smc_linear_predictor_adjoint(const smc_matrix* x, const smc_matrix* v,
+                                 double* xt_v, double* sum_v);
+/* *sum = sum_i v[i] of an f64 device vector (fixed-order, deterministic). */
+int smc_vector_sum(const smc_matrix* v, double* sum);
+
+/* Un-fused densities on a device N-vector parameter.  `n`/`y`: N x 1 i32 device
+ * vector or NULL -> the broadcast scalar.  SMC_VAR_ALPHA in `flags` marks the
+ * vector parameter (theta / alpha / eta / lambda) as an autodiff variable: its
+ * partial is written to the N x 1 device vector `d_*`; SMC_VAR_AUX marks phi /
+ * cuts.  Value and error semantics follow prim/prob/<name>.hpp. */
+/* prim/prob/bernoulli_logit_lpmf.hpp L33-98 */
+int smc_bernoulli_logit_lpmf(const smc_matrix* n, int n_scalar,
+                             const smc_matrix* theta, unsigned flags, double* logp,
+                             smc_matrix* d_theta);
+/* prim/prob/poisson_log_lpmf.hpp L27-100 */
+int smc_poisson_log_lpmf(const smc_matrix* n, int n_scalar, const smc_matrix* alpha,
+                         unsigned flags, double* logp, smc_matrix* d_alpha);
+/* prim/prob/neg_binomial_2_log_lpmf.hpp L24-134 (phi: N x 1 device vector or
+ * NULL -> scalar; d_phi host for a scalar phi, d_phi_vec device for a vector) */
+int smc_neg_binomial_2_log_lpmf(const smc_matrix* n, int n_scalar,
+                                const smc_matrix* eta, const smc_matrix* phi_vec,
+                                double phi, unsigned flags, double* logp,
+                                smc_matrix* d_eta, double* d_phi,
+                                smc_matrix* d_phi_vec);
+/* prim/prob/ordered_logistic_lpmf.hpp L72-214 (one cut-point vector, host) */
+int smc_ordered_logistic_lpmf(const smc_matrix* y, int y_scalar,
+                              const smc_matrix* lambda, const double* cuts,
+                              int64_t ncuts, unsigned flags, double* logp,
+                              smc_matrix* d_lambda, double* d_cuts);
 
 #ifdef __cplusplus
 }

@@ -8,4 +8,5 @@ from .glm import (GlmResult, bernoulli_logit_glm_lpmf, poisson_log_glm_lpmf,
                   normal_id_glm_lpdf, neg_binomial_2_log_glm_lpmf,
                   ordered_logistic_glm_lpmf, categorical_logit_glm_lpmf,
                   binomial_logit_glm_lpmf)
+from . import lpmf
 from . import runtime

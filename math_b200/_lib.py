@@ -76,6 +76,14 @@ SIGNATURES = {
                                       _DP, _P]),
     "smc_categorical_logit_glm": (_I, [_P, _I, _P, _DP, _DP, _I64, _U, _DP, _DP,
                                        _DP, _P]),
+    "smc_matrix_add_scalar": (_I, [_P, _D]),
+    "smc_linear_predictor": (_I, [_P, _DP, _P, _D, _P]),
+    "smc_linear_predictor_adjoint": (_I, [_P, _P, _DP, _DP]),
+    "smc_vector_sum": (_I, [_P, _DP]),
+    "smc_bernoulli_logit_lpmf": (_I, [_P, _I, _P, _U, _DP, _P]),
+    "smc_poisson_log_lpmf": (_I, [_P, _I, _P, _U, _DP, _P]),
+    "smc_neg_binomial_2_log_lpmf": (_I, [_P, _I, _P, _P, _D, _U, _DP, _P, _DP, _P]),
+    "smc_ordered_logistic_lpmf": (_I, [_P, _I, _P, _DP, _I64, _U, _DP, _P, _DP]),
     "smc_glm_eval_device": (_I, [_I, _P, _D, _P, _P, _D, _P, _D, _P, _I64, _U, _P,
                                  _P, _P, _P, _P]),
 }

@@ -174,6 +174,16 @@ __global__ void axpy_kernel(double* __restrict__ y, int64_t ldy,
   }
 }
 
+__global__ void add_scalar_kernel(double* __restrict__ y, int64_t ldy, int64_t rows,
+                                  int64_t cols, double a) {
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = i / rows, r = i - c * rows;
+    y[c * ldy + r] += a;
+  }
+}
+
 __global__ void all_finite_kernel(const double* __restrict__ x, int64_t ld,
                                   int64_t rows, int64_t cols, int* bad) {
   const int64_t total = rows * cols;
@@ -450,6 +460,19 @@ int smc_matrix_axpy(smc_matrix* y, double a, const smc_matrix* x) {
   axpy_kernel<<<grid_for(total, 256), 256, 0, ctx().stream>>>(
       static_cast<double*>(y->data), y->ld, static_cast<const double*>(x->data),
       x->ld, y->rows, y->cols, a);
+  SMC_CUDA(cudaGetLastError());
+  return SMC_OK;
+}
+
+int smc_matrix_add_scalar(smc_matrix* y, double a) {
+  if (!y || y->dtype != SMC_F64)
+    return fail(SMC_ERR_INVALID_ARGUMENT, "add_scalar: need an f64 matrix");
+  if (int rc = ensure_ctx()) return rc;
+  const int64_t total = y->rows * y->cols;
+  if (total == 0) return SMC_OK;
+  y->version++;
+  add_scalar_kernel<<<grid_for(total, 256), 256, 0, ctx().stream>>>(
+      static_cast<double*>(y->data), y->ld, y->rows, y->cols, a);
   SMC_CUDA(cudaGetLastError());
   return SMC_OK;
 }

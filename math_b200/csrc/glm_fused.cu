@@ -607,6 +607,8 @@ int launch_glm_fused(const GlmCall& c) {
       return launch_t<kOrdered>(tmap, tmap_dx, a, grid, threads, smem);
     case kBinomial:
       return launch_t<kBinomial>(tmap, tmap_dx, a, grid, threads, smem);
+    case kLinear:
+      return launch_t<kLinear>(tmap, tmap_dx, a, grid, threads, smem);
   }
   return fail(SMC_ERR_INVALID_ARGUMENT, "unknown family %d", c.family);
 }

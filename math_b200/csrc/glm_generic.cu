@@ -21,7 +21,7 @@ int prepare_args(const GlmCall& c, FusedArgs* ap) {
   a.K = (int)x->cols;
   a.x = static_cast<const double*>(x->data);
   a.ldx = x->ld;
-  a.flags = c.flags;
+  a.flags = c.flags | (c.unfused ? kFlagUnfused : 0u);
   a.ncuts = (int)c.ncuts;
   a.y = c.y ? c.y->data : nullptr;
   a.y_scalar = c.y_scalar;
@@ -52,8 +52,11 @@ int prepare_args(const GlmCall& c, FusedArgs* ap) {
       break;
     case kPoisson:
     case kNegBinomial: {
-      // -sum lgamma(y + 1): poisson L126-128, neg-binomial L163-169
-      if (!propto) {
+      // -sum lgamma(y + 1): poisson L126-128, neg-binomial L163-169.  The un-fused
+      // neg_binomial_2_log_lpmf carries it inside binomial_coefficient_log, which
+      // stays whenever phi is an autodiff variable (lpmf L111-113)
+      if (!propto
+          || (c.unfused && c.family == kNegBinomial && (c.flags & SMC_VAR_AUX))) {
         double lg = 0.0;
         if (c.y) {
           if (int rc = y_lgamma_sum(c.y, &lg)) return rc;
@@ -61,7 +64,8 @@ int prepare_args(const GlmCall& c, FusedArgs* ap) {
           // a broadcast scalar y: the poisson GLM sums lgamma(y + 1) over the
           // elements of y as passed (once), the neg-binomial GLM scales by N
           // (L165-168) -- both reproduced as the reference has them
-          lg = std::lgamma(c.y_scalar + 1.0) * (c.family == kPoisson ? 1.0 : Nd);
+          lg = std::lgamma(c.y_scalar + 1.0)
+               * (c.family == kPoisson && !c.unfused ? 1.0 : Nd);
         }
         a.c0 -= lg;
       }
@@ -76,10 +80,11 @@ int prepare_args(const GlmCall& c, FusedArgs* ap) {
         a.log_aux = std::log(c.aux);
         a.digamma_aux = digamma(c.aux);
         // N (phi log phi - lgamma phi), L177-182 (multiply_log(0,0) = 0)
-        if (!propto || (c.flags & SMC_VAR_AUX)) {
-          const double ml = (c.aux == 0.0) ? 0.0 : c.aux * std::log(c.aux);
+        const double ml = (c.aux == 0.0) ? 0.0 : c.aux * std::log(c.aux);
+        if (!propto || (c.flags & SMC_VAR_AUX))
           a.c0 += Nd * (ml - std::lgamma(c.aux));
-        }
+        else if (c.unfused)
+          a.c0 += Nd * ml;  // neg_binomial_2_log_lpmf.hpp L117-118 keeps it
       }
       break;
     }
@@ -143,7 +148,7 @@ __global__ void __launch_bounds__(kGenThreads)
       in.aux = a.aux_vec ? a.aux_vec[row] : a.aux;
     double d1 = 0, d2 = 0;
     const double d = link_row<FAM>(a, xb, in, true, true, row, racc, tab, d1, d2);
-    dvec[row] = d;
+    if (a.K > 0) dvec[row] = d;  // (K = 0: an un-fused density, no column pass)
     if constexpr (FAM == kOrdered) {
       d1v[row] = d1;
       d2v[row] = d2;
@@ -266,6 +271,9 @@ int launch_glm_generic(const GlmCall& c) {
       break;
     case kBinomial:
       rc = run_rows<kBinomial>(a, params, dvec, d1v, d2v, bp, grid);
+      break;
+    case kLinear:
+      rc = run_rows<kLinear>(a, params, dvec, d1v, d2v, bp, grid);
       break;
     default:
       return fail(SMC_ERR_INVALID_ARGUMENT, "unknown family %d", c.family);

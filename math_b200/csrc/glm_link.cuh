@@ -216,7 +216,10 @@ __device__ __forceinline__ double link_d(const FusedArgs& a, double xb,
     } else {
       ordered_class_entry(tab.cuts, a.ncuts, c, ce);
     }
-    const double cut2 = xb - ce[1], cut1 = xb - ce[0];  // L129-132
+    // (alpha is 0 for the GLM; the un-fused ordered_logistic_lpmf passes its
+    // location vector through it)
+    const double loc = xb + in.alpha;
+    const double cut2 = loc - ce[1], cut1 = loc - ce[0];  // L129-132
     // exp(-|cut|) serves both the stable log1p_exp forms (L135-138) and the
     // stable inv_logit selects (L168-174): for cut > 0 it IS exp(-cut), for
     // cut <= 0 it IS exp(cut) -- same argument, same bits
@@ -232,7 +235,13 @@ __device__ __forceinline__ double link_d(const FusedArgs& a, double xb,
     st.v2 = e1;
     st.v3 = e2;
     st.c = c;
-    s3 = xb;  // sum(location) for the lazy finiteness check, L124
+    s3 = loc;  // sum(location) for the lazy finiteness check, L124
+    if (lead && valid && a.d_alpha_vec) a.d_alpha_vec[row] = d;
+  } else if constexpr (FAM == kLinear) {
+    // theta = x beta + alpha goes out per row; d = v_i, so that the column
+    // reduction of the same sweep yields x^T v (and sum_i v_i)
+    d = in.aux;
+    if (lead && valid && a.d_alpha_vec) a.d_alpha_vec[row] = xb + in.alpha;
   }
   if (!valid) return 0.0;
   if (lead) {
@@ -278,6 +287,9 @@ __device__ __forceinline__ void link_lp(const FusedArgs& a, const LinkStash<FAM>
     if (inc_phi) {
       lp += in_tab ? tab.lg[yi] : lgamma(ypp);  // L189-195
       if (a.aux_vec) lp += multiply_log(ph, ph) - lgamma(ph);  // L171-176
+    } else if (a.aux_vec && (a.flags & kFlagUnfused)) {
+      // neg_binomial_2_log_lpmf.hpp L117-118 keeps phi log(phi) under propto
+      lp += multiply_log(ph, ph);
     }
     acc.lp += lp;
     if (a.flags & SMC_VAR_AUX) {

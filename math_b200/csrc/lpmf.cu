@@ -1,0 +1,359 @@
+// The step either side of the fused GLMs: models that add
+// terms to the linear predictor before the likelihood cannot call a *_glm_*
+// function; they form theta on the device and call the un-fused density on it.
+//
+//   smc_linear_predictor          theta = x beta (+ alpha)       one sweep over x
+//   smc_linear_predictor_adjoint  x^T v, sum v                   one sweep over x
+//   smc_<family>_lpmf             value + d/dtheta on an N-vector theta
+//
+// The products run through the fused TMA kernel (family kLinear), so they stream
+// x at the same rate as the GLMs; the densities run the GLM link functions with
+// K = 0 (glm_link.cuh follows the same formulas as prim/prob/<family>_lpmf.hpp:
+// bernoulli_logit_lpmf.hpp L60-95, poisson_log_lpmf.hpp L49-96,
+// neg_binomial_2_log_lpmf.hpp L50-130, ordered_logistic_lpmf.hpp L93-200).
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "smc_internal.h"
+
+using namespace smc;
+
+namespace {
+
+// An N x 0 design matrix: the GLM machinery with no columns.
+smc_matrix empty_design(int64_t N) {
+  smc_matrix x;
+  x.rows = N;
+  x.cols = 0;
+  x.ld = N > 0 ? N : 1;
+  x.dtype = SMC_F64;
+  return x;
+}
+
+bool is_vec(const smc_matrix* m) { return m->cols == 1 || m->rows == 1 || m->rows * m->cols == 0; }
+
+// theta must be an f64 vector; y (if a vector) and the other per-row operands
+// must have its length.
+int theta_shapes(const char* fn, const smc_matrix* theta, const smc_matrix* y,
+                 const smc_matrix* v1, smc_matrix* d_theta, smc_matrix* d_v1,
+                 int64_t* N) {
+  if (!theta || theta->dtype != SMC_F64 || !is_vec(theta))
+    return fail(SMC_ERR_INVALID_ARGUMENT, "%s: theta must be an f64 device vector", fn);
+  *N = theta->rows * theta->cols;
+  if (y && (y->dtype != SMC_I32 || y->rows * y->cols != *N || !is_vec(y)))
+    return fail(SMC_ERR_INVALID_ARGUMENT,
+                "%s: size of the random variable (%lld) does not match the size of "
+                "the parameter (%lld)",
+                fn, (long long)(y->rows * y->cols), (long long)*N);
+  const smc_matrix* vs[3] = {v1, d_theta, d_v1};
+  for (const smc_matrix* v : vs)
+    if (v && (v->dtype != SMC_F64 || v->rows * v->cols != *N))
+      return fail(SMC_ERR_INVALID_ARGUMENT,
+                  "%s: size of a per-row vector (%lld) does not match the size of "
+                  "the parameter (%lld)",
+                  fn, (long long)(v->rows * v->cols), (long long)*N);
+  return SMC_OK;
+}
+
+int run_sync(GlmCall& c, int n_out, const double** out) {
+  if (int rc = ensure_out(sizeof(double) * (size_t)n_out)) return rc;
+  c.out = ctx().out_host;
+  if (int rc = launch_glm(c)) return rc;
+  SMC_CUDA(cudaStreamSynchronize(ctx().stream));
+  *out = ctx().out_host;
+  return SMC_OK;
+}
+
+int int_bounds(const char* fn, const smc_matrix* y, int y_scalar, int lo, int hi,
+               bool check_hi) {
+  int mn = y_scalar, mx = y_scalar;
+  if (y) {
+    if (y->rows * y->cols == 0) return SMC_OK;
+    if (int rc = y_range(y, &mn, &mx)) return rc;
+  }
+  if (mn < lo || (check_hi && mx > hi))
+    return fail(SMC_ERR_DOMAIN, "%s: Random variable is out of range", fn);
+  return SMC_OK;
+}
+
+// Host copy of a device vector (rare paths only: the lazy value checks).
+int fetch(const smc_matrix* v, std::vector<double>* out) {
+  out->resize((size_t)(v->rows * v->cols));
+  if (out->empty()) return SMC_OK;
+  return smc_matrix_download(v, out->data(), v->rows);
+}
+
+}  // namespace
+
+extern "C" {
+
+int smc_linear_predictor(const smc_matrix* x, const double* beta,
+                         const smc_matrix* alpha_vec, double alpha,
+                         smc_matrix* theta_out) {
+  static const char* fn = "linear_predictor";
+  if (int rc = ensure_ctx()) return rc;
+  if (!x || x->dtype != SMC_F64)
+    return fail(SMC_ERR_INVALID_ARGUMENT, "%s: x must be an f64 device matrix", fn);
+  const int64_t N = x->rows, K = x->cols;
+  if (K > 0 && !beta) return fail(SMC_ERR_INVALID_ARGUMENT, "%s: NULL beta", fn);
+  if (!theta_out || theta_out->dtype != SMC_F64 || theta_out->rows * theta_out->cols != N)
+    return fail(SMC_ERR_INVALID_ARGUMENT, "%s: theta_out must hold rows(x) doubles", fn);
+  if (alpha_vec && (alpha_vec->dtype != SMC_F64 || alpha_vec->rows * alpha_vec->cols != N))
+    return fail(SMC_ERR_INVALID_ARGUMENT,
+                "%s: size of alpha (%lld) does not match rows of x (%lld)", fn,
+                (long long)(alpha_vec->rows * alpha_vec->cols), (long long)N);
+  if (N == 0) return SMC_OK;
+  GlmCall c;
+  c.family = kLinear;
+  c.x = x;
+  c.alpha_vec = alpha_vec;
+  c.alpha = alpha;
+  c.beta_host = beta;
+  c.flags = 0;
+  c.d_alpha_vec = theta_out;
+  theta_out->version++;
+  const double* o;
+  return run_sync(c, SMC_OUT_HEADER + (int)K, &o);
+}
+
+int smc_linear_predictor_adjoint(const smc_matrix* x, const smc_matrix* v,
+                                 double* xt_v, double* sum_v) {
+  static const char* fn = "linear_predictor_adjoint";
+  if (int rc = ensure_ctx()) return rc;
+  if (!x || x->dtype != SMC_F64)
+    return fail(SMC_ERR_INVALID_ARGUMENT, "%s: x must be an f64 device matrix", fn);
+  const int64_t N = x->rows, K = x->cols;
+  if (!v || v->dtype != SMC_F64 || v->rows * v->cols != N)
+    return fail(SMC_ERR_INVALID_ARGUMENT, "%s: v must hold rows(x) doubles", fn);
+  if (sum_v) *sum_v = 0.0;
+  if (xt_v) memset(xt_v, 0, sizeof(double) * K);
+  if (N == 0) return SMC_OK;
+  std::vector<double> zeros((size_t)K, 0.0);
+  GlmCall c;
+  c.family = kLinear;
+  c.x = x;
+  c.aux_vec = v;
+  c.beta_host = zeros.data();
+  c.flags = SMC_VAR_BETA;
+  const double* o;
+  if (int rc = run_sync(c, SMC_OUT_HEADER + (int)K, &o)) return rc;
+  if (sum_v) *sum_v = o[SMC_OUT_SUM_D];
+  if (xt_v) memcpy(xt_v, o + SMC_OUT_HEADER, sizeof(double) * K);
+  return SMC_OK;
+}
+
+int smc_vector_sum(const smc_matrix* v, double* sum) {
+  static const char* fn = "vector_sum";
+  if (int rc = ensure_ctx()) return rc;
+  if (!v || v->dtype != SMC_F64 || !is_vec(v) || !sum)
+    return fail(SMC_ERR_INVALID_ARGUMENT, "%s: need an f64 device vector", fn);
+  smc_matrix x0 = empty_design(v->rows * v->cols);
+  return smc_linear_predictor_adjoint(&x0, v, nullptr, sum);
+}
+
+int smc_bernoulli_logit_lpmf(const smc_matrix* n, int n_scalar,
+                             const smc_matrix* theta, unsigned flags, double* logp,
+                             smc_matrix* d_theta) {
+  static const char* fn = "bernoulli_logit_lpmf";
+  if (int rc = ensure_ctx()) return rc;
+  int64_t N;
+  if (int rc = theta_shapes(fn, theta, n, nullptr, d_theta, nullptr, &N)) return rc;
+  if (!logp) return fail(SMC_ERR_INVALID_ARGUMENT, "%s: NULL logp", fn);
+  *logp = 0.0;
+  if (N == 0) return SMC_OK;                                          // L52-54
+  if (int rc = int_bounds(fn, n, n_scalar, 0, 1, true)) return rc;    // L47
+  if ((flags & SMC_PROPTO) && !(flags & SMC_VAR_ALPHA)) return SMC_OK;  // L55-57
+  smc_matrix x0 = empty_design(N);
+  GlmCall c;
+  c.family = kBernoulli;
+  c.unfused = true;
+  c.x = &x0;
+  c.y = n;
+  c.y_scalar = n_scalar;
+  c.alpha_vec = theta;
+  c.flags = flags & (SMC_PROPTO | SMC_VAR_ALPHA);
+  c.d_alpha_vec = (flags & SMC_VAR_ALPHA) ? d_theta : nullptr;
+  if (c.d_alpha_vec) d_theta->version++;
+  const double* o;
+  if (int rc = run_sync(c, SMC_OUT_HEADER, &o)) return rc;
+  const double lp = o[SMC_OUT_LOGP];
+  if (o[SMC_OUT_NONFINITE] > 0) {
+    // check_not_nan(theta), L48-49: +-inf is a legal logit, NaN is not
+    std::vector<double> th;
+    if (int rc = fetch(theta, &th)) return rc;
+    for (double t : th)
+      if (std::isnan(t))
+        return fail(SMC_ERR_DOMAIN,
+                    "%s: Logit transformed probability parameter is nan", fn);
+  }
+  *logp = lp;
+  return SMC_OK;
+}
+
+int smc_poisson_log_lpmf(const smc_matrix* n, int n_scalar, const smc_matrix* alpha,
+                         unsigned flags, double* logp, smc_matrix* d_alpha) {
+  static const char* fn = "poisson_log_lpmf";
+  if (int rc = ensure_ctx()) return rc;
+  int64_t N;
+  if (int rc = theta_shapes(fn, alpha, n, nullptr, d_alpha, nullptr, &N)) return rc;
+  if (!logp) return fail(SMC_ERR_INVALID_ARGUMENT, "%s: NULL logp", fn);
+  *logp = 0.0;
+  if (int rc = int_bounds(fn, n, n_scalar, 0, 0, false)) return rc;  // L46
+  if (N == 0) return SMC_OK;  // (an empty alpha has no NaN to report) L49-51
+  const bool skip = (flags & SMC_PROPTO) && !(flags & SMC_VAR_ALPHA);  // L52-54
+  smc_matrix x0 = empty_design(N);
+  GlmCall c;
+  c.family = kPoisson;
+  c.unfused = true;
+  c.x = &x0;
+  c.y = n;
+  c.y_scalar = n_scalar;
+  c.alpha_vec = alpha;
+  c.flags = flags & (SMC_PROPTO | SMC_VAR_ALPHA);
+  c.d_alpha_vec = (flags & SMC_VAR_ALPHA) ? d_alpha : nullptr;
+  if (c.d_alpha_vec) d_alpha->version++;
+  const double* o;
+  if (int rc = run_sync(c, SMC_OUT_HEADER, &o)) return rc;
+  const double lp = o[SMC_OUT_LOGP];
+  if (o[SMC_OUT_NONFINITE] > 0) {
+    // check_not_nan(alpha) L47; then the two log(0) exits, L56-66
+    std::vector<double> th;
+    if (int rc = fetch(alpha, &th)) return rc;
+    std::vector<int> nv;
+    if (n) {
+      nv.resize((size_t)N);
+      if (int rc = smc_matrix_download(n, nv.data(), n->rows)) return rc;
+    }
+    for (double t : th)
+      if (std::isnan(t))
+        return fail(SMC_ERR_DOMAIN, "%s: Log rate parameter is nan", fn);
+    bool zero = false;
+    for (size_t i = 0; i < th.size(); ++i) {
+      if (th[i] == std::numeric_limits<double>::infinity()) zero = true;
+      if (th[i] == -std::numeric_limits<double>::infinity()
+          && (n ? nv[i] : n_scalar) != 0)
+        zero = true;
+    }
+    if (zero && !skip) {
+      // LOG_ZERO is returned as a constant: no partials
+      if (c.d_alpha_vec) {
+        if (int rc = smc_matrix_zero(d_alpha)) return rc;
+      }
+      *logp = -std::numeric_limits<double>::infinity();
+      return SMC_OK;
+    }
+  }
+  if (skip) {
+    if (c.d_alpha_vec) return smc_matrix_zero(d_alpha);
+    return SMC_OK;
+  }
+  *logp = lp;
+  return SMC_OK;
+}
+
+int smc_neg_binomial_2_log_lpmf(const smc_matrix* n, int n_scalar,
+                                const smc_matrix* eta, const smc_matrix* phi_vec,
+                                double phi, unsigned flags, double* logp,
+                                smc_matrix* d_eta, double* d_phi,
+                                smc_matrix* d_phi_vec) {
+  static const char* fn = "neg_binomial_2_log_lpmf";
+  if (int rc = ensure_ctx()) return rc;
+  int64_t N;
+  if (int rc = theta_shapes(fn, eta, n, phi_vec, d_eta, d_phi_vec, &N)) return rc;
+  if (!logp) return fail(SMC_ERR_INVALID_ARGUMENT, "%s: NULL logp", fn);
+  *logp = 0.0;
+  if (d_phi) *d_phi = 0.0;
+  if (int rc = int_bounds(fn, n, n_scalar, 0, 0, false)) return rc;  // L45
+  if (!phi_vec && (!(phi > 0.0) || !std::isfinite(phi)))            // L47
+    return fail(SMC_ERR_DOMAIN,
+                "%s: Precision parameter is %g, but must be positive finite", fn, phi);
+  if (N == 0) return SMC_OK;  // L49-51
+  const bool skip = (flags & SMC_PROPTO) && !(flags & (SMC_VAR_ALPHA | SMC_VAR_AUX));
+  smc_matrix x0 = empty_design(N);
+  GlmCall c;
+  c.family = kNegBinomial;
+  c.unfused = true;
+  c.x = &x0;
+  c.y = n;
+  c.y_scalar = n_scalar;
+  c.alpha_vec = eta;
+  c.aux_vec = phi_vec;
+  c.aux = phi;
+  c.flags = flags & (SMC_PROPTO | SMC_VAR_ALPHA | SMC_VAR_AUX);
+  c.d_alpha_vec = (flags & SMC_VAR_ALPHA) ? d_eta : nullptr;
+  c.d_aux_vec = (flags & SMC_VAR_AUX) ? d_phi_vec : nullptr;
+  if (c.d_alpha_vec) d_eta->version++;
+  if (c.d_aux_vec) d_phi_vec->version++;
+  const double* o;
+  if (int rc = run_sync(c, SMC_OUT_HEADER, &o)) return rc;
+  if (o[SMC_OUT_NONFINITE] > 0)  // check_finite(eta) L46, positive finite phi L47
+    return fail(SMC_ERR_DOMAIN,
+                "%s: Log location parameter or precision parameter is not finite", fn);
+  if (skip) return SMC_OK;  // L52-54
+  *logp = o[SMC_OUT_LOGP];
+  if (d_phi && (flags & SMC_VAR_AUX) && !phi_vec) *d_phi = o[SMC_OUT_AUX];
+  return SMC_OK;
+}
+
+int smc_ordered_logistic_lpmf(const smc_matrix* y, int y_scalar,
+                              const smc_matrix* lambda, const double* cuts,
+                              int64_t ncuts, unsigned flags, double* logp,
+                              smc_matrix* d_lambda, double* d_cuts) {
+  static const char* fn = "ordered_logistic_lpmf";
+  if (int rc = ensure_ctx()) return rc;
+  int64_t N;
+  if (int rc = theta_shapes(fn, lambda, y, nullptr, d_lambda, nullptr, &N)) return rc;
+  if (!logp || ncuts < 0 || (ncuts > 0 && !cuts))
+    return fail(SMC_ERR_INVALID_ARGUMENT, "%s: NULL cuts or logp", fn);
+  *logp = 0.0;
+  if (d_cuts && ncuts) memset(d_cuts, 0, sizeof(double) * ncuts);
+  if (N > 0) {  // check_finite(lambda), L105: before the size_zero exit
+    int ok = 1;
+    if (int rc = smc_matrix_all_finite(lambda, &ok)) return rc;
+    if (!ok) return fail(SMC_ERR_DOMAIN, "%s: Location parameter is not finite", fn);
+  }
+  if (N == 0) return SMC_OK;  // L106-108 (one cut vector is always present here)
+  const int64_t C = ncuts + 1;
+  if (int rc = int_bounds(fn, y, y_scalar, 1, (int)C, true)) return rc;  // L110
+  for (int64_t i = 1; i < ncuts; ++i)  // check_ordered, L115
+    if (!(cuts[i] > cuts[i - 1]))
+      return fail(SMC_ERR_DOMAIN, "%s: Cut-points are not a valid ordered vector", fn);
+  if (ncuts == 1 && std::isnan(cuts[0]))
+    return fail(SMC_ERR_DOMAIN, "%s: Cut-points are not a valid ordered vector", fn);
+  if (C > 1) {  // L116-121
+    if (C > 2 && !std::isfinite(cuts[C - 2]))
+      return fail(SMC_ERR_DOMAIN, "%s: Final cut-point is not finite", fn);
+    if (!std::isfinite(cuts[0]))
+      return fail(SMC_ERR_DOMAIN, "%s: First cut-point is not finite", fn);
+  }
+  if ((flags & SMC_PROPTO) && !(flags & (SMC_VAR_ALPHA | SMC_VAR_AUX)))
+    return SMC_OK;  // L123-125
+  if (ncuts == 0) {
+    // a single class: every term is log(1) = 0 and every partial is 0
+    if ((flags & SMC_VAR_ALPHA) && d_lambda) return smc_matrix_zero(d_lambda);
+    return SMC_OK;
+  }
+  smc_matrix x0 = empty_design(N);
+  GlmCall c;
+  c.family = kOrdered;
+  c.unfused = true;
+  c.x = &x0;
+  c.y = y;
+  c.y_scalar = y_scalar;
+  c.alpha_vec = lambda;
+  c.cuts_host = cuts;
+  c.ncuts = ncuts;
+  c.flags = flags & (SMC_PROPTO | SMC_VAR_ALPHA | SMC_VAR_AUX);
+  c.d_alpha_vec = (flags & SMC_VAR_ALPHA) ? d_lambda : nullptr;
+  if (c.d_alpha_vec) d_lambda->version++;
+  const double* o;
+  if (int rc = run_sync(c, SMC_OUT_HEADER + (int)ncuts, &o)) return rc;
+  *logp = o[SMC_OUT_LOGP];
+  if (d_cuts && (flags & SMC_VAR_AUX))
+    memcpy(d_cuts, o + SMC_OUT_HEADER, sizeof(double) * ncuts);
+  return SMC_OK;
+}
+
+}  // extern "C"

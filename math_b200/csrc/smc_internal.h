@@ -18,6 +18,8 @@ constexpr int kMaxFusedK = 256;   // columns one fused CTA tile can hold
 constexpr int kColsPerThread = 32;
 constexpr int kMaxParamDoubles = 256;  // by-value parameter block (beta)
 constexpr int kMaxCuts = 512;
+// internal flag bit (above the public SMC_* flags): un-fused density semantics
+constexpr unsigned kFlagUnfused = 1u << 16;
 
 enum Family {
   kNormal = 0,
@@ -25,7 +27,11 @@ enum Family {
   kPoisson = 2,
   kNegBinomial = 3,
   kOrdered = 4,
-  kBinomial = 5
+  kBinomial = 5,
+  // Not a density: theta = x beta + alpha written out per row, and / or
+  // x^T v for a per-row vector v (the matrix-vector products either side of an
+  // un-fused log density, lpmf.cu).
+  kLinear = 6
 };
 
 // Per-host-thread state: device, stream, reusable workspace.
@@ -91,6 +97,9 @@ struct GlmCall {
   const double* params_dev = nullptr;   // beta[K] (+cuts) already on device
   int64_t ncuts = 0;
   unsigned flags = 0;
+  // un-fused density on a device linear predictor (lpmf.cu): the constant terms
+  // of a broadcast scalar y follow prim/prob/<family>_lpmf.hpp, not the GLM
+  bool unfused = false;
   double* out = nullptr;  // packed result, device-accessible
   smc_matrix* d_alpha_vec = nullptr;
   smc_matrix* d_aux_vec = nullptr;

@@ -1,0 +1,99 @@
+"""Host-side mirror of the step either side of the fused GLMs.
+
+``multiply`` / ``multiply_adjoint`` are the device matrix-vector product and its
+reverse sweep (opencl/prim/multiply.hpp, opencl/rev/multiply.hpp); the
+``*_lpmf`` functions are the un-fused densities on a device N-vector parameter
+(prim/prob/bernoulli_logit_lpmf.hpp, poisson_log_lpmf.hpp,
+neg_binomial_2_log_lpmf.hpp, ordered_logistic_lpmf.hpp) for models that add
+terms to ``x * beta`` before the likelihood.  Values and partials come back in
+an ``LpmfResult`` (the C++ drop-in feeds them into the tape:
+include/stan/math/cuda/prim/unfused_lpmf.hpp, rev/multiply.hpp).
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from ._lib import PROPTO, VAR_ALPHA, VAR_AUX, check, lib
+from .glm import _beta, _dp, _h, _split
+from .matrix_cuda import MatrixCuda
+
+
+@dataclass
+class LpmfResult:
+    logp: float
+    d_theta: Optional[MatrixCuda] = None  # N x 1, partial w.r.t. the vector parameter
+    d_aux: Optional[object] = None        # d_phi (float) / d_cuts (ndarray)
+
+
+def multiply(x, beta, alpha=0.0):
+    """theta = x @ beta + alpha on the device (alpha: scalar or N x 1 MatrixCuda)."""
+    av, a0 = _split(alpha, float, "alpha")
+    b = _beta(beta, x.cols)
+    theta = MatrixCuda(x.rows, 1, np.float64)
+    check(lib().smc_linear_predictor(x.handle, _dp(b), _h(av), a0, theta.handle))
+    return theta
+
+
+def multiply_adjoint(x, v):
+    """(x.T @ v, sum(v)) for an N x 1 device vector v: the reverse sweep of multiply."""
+    g = np.zeros(x.cols)
+    s = C.c_double()
+    check(lib().smc_linear_predictor_adjoint(x.handle, v.handle, _dp(g), C.byref(s)))
+    return g, s.value
+
+
+def vector_sum(v):
+    s = C.c_double()
+    check(lib().smc_vector_sum(v.handle, C.byref(s)))
+    return s.value
+
+
+def _flags(propto, theta_var, aux_var=False):
+    return (PROPTO if propto else 0) | (VAR_ALPHA if theta_var else 0) \
+        | (VAR_AUX if aux_var else 0)
+
+
+def _theta_lpmf(fn, n, theta, propto, theta_var):
+    nv, ns = _split(n, int, "n")
+    flags = _flags(propto, theta_var)
+    d = MatrixCuda(theta.size(), 1, np.float64) if theta_var else None
+    logp = C.c_double()
+    check(fn(_h(nv), ns, theta.handle, flags, C.byref(logp), _h(d)))
+    return LpmfResult(logp.value, d)
+
+
+def bernoulli_logit_lpmf(n, theta, propto=False, theta_var=True):
+    """prim/prob/bernoulli_logit_lpmf.hpp L33-98."""
+    return _theta_lpmf(lib().smc_bernoulli_logit_lpmf, n, theta, propto, theta_var)
+
+
+def poisson_log_lpmf(n, alpha, propto=False, theta_var=True):
+    """prim/prob/poisson_log_lpmf.hpp L27-100."""
+    return _theta_lpmf(lib().smc_poisson_log_lpmf, n, alpha, propto, theta_var)
+
+
+def neg_binomial_2_log_lpmf(n, eta, phi, propto=False, theta_var=True, phi_var=True):
+    """prim/prob/neg_binomial_2_log_lpmf.hpp L24-134 (scalar phi)."""
+    nv, ns = _split(n, int, "n")
+    flags = _flags(propto, theta_var, phi_var)
+    d = MatrixCuda(eta.size(), 1, np.float64) if theta_var else None
+    logp, d_phi = C.c_double(), C.c_double()
+    check(lib().smc_neg_binomial_2_log_lpmf(_h(nv), ns, eta.handle, None, float(phi),
+                                            flags, C.byref(logp), _h(d),
+                                            C.byref(d_phi), None))
+    return LpmfResult(logp.value, d, d_phi.value if phi_var else None)
+
+
+def ordered_logistic_lpmf(y, lam, cuts, propto=False, theta_var=True, cuts_var=True):
+    """prim/prob/ordered_logistic_lpmf.hpp L72-214 (one cut-point vector)."""
+    yv, ys = _split(y, int, "y")
+    c = np.ascontiguousarray(np.atleast_1d(np.asarray(cuts, dtype=np.float64)).ravel())
+    flags = _flags(propto, theta_var, cuts_var)
+    d = MatrixCuda(lam.size(), 1, np.float64) if theta_var else None
+    logp = C.c_double()
+    d_cuts = np.zeros(c.size)
+    check(lib().smc_ordered_logistic_lpmf(_h(yv), ys, lam.handle, _dp(c), c.size,
+                                          flags, C.byref(logp), _h(d), _dp(d_cuts)))
+    return LpmfResult(logp.value, d, d_cuts if cuts_var else None)

@@ -1,0 +1,216 @@
+// CUDA-vs-CPU parity for the step either side of the fused GLMs (SURVEY.md
+// 8(f)3): the device matrix-vector product + add, and the un-fused densities on
+// a device linear predictor.  The oracle is the reference's own prim
+// implementation (bernoulli_logit_lpmf, poisson_log_lpmf,
+// neg_binomial_2_log_lpmf, ordered_logistic_lpmf) compiled into this binary;
+// the protocol is the one of test/unit/math/opencl/util.hpp L129-191.
+#include "cuda_test_util.hpp"
+
+using Eigen::Dynamic;
+using Eigen::Matrix;
+using Eigen::MatrixXd;
+using Eigen::VectorXd;
+using stan::math::matrix_cuda;
+using stan::math::var;
+using std::vector;
+using namespace cuda_test;  // NOLINT
+
+namespace {
+auto bern = [](const auto& n, const auto& theta) {
+  return stan::math::bernoulli_logit_lpmf(n, theta);
+};
+auto bern_propto = [](const auto& n, const auto& theta) {
+  return stan::math::bernoulli_logit_lpmf<true>(n, theta);
+};
+auto pois = [](const auto& n, const auto& alpha) {
+  return stan::math::poisson_log_lpmf(n, alpha);
+};
+auto pois_propto = [](const auto& n, const auto& alpha) {
+  return stan::math::poisson_log_lpmf<true>(n, alpha);
+};
+auto negb = [](const auto& n, const auto& eta, const auto& phi) {
+  return stan::math::neg_binomial_2_log_lpmf(n, eta, phi);
+};
+auto negb_propto = [](const auto& n, const auto& eta, const auto& phi) {
+  return stan::math::neg_binomial_2_log_lpmf<true>(n, eta, phi);
+};
+auto ordl = [](const auto& y, const auto& lambda, const auto& c) {
+  return stan::math::ordered_logistic_lpmf(y, lambda, c);
+};
+auto ordl_propto = [](const auto& y, const auto& lambda, const auto& c) {
+  return stan::math::ordered_logistic_lpmf<true>(y, lambda, c);
+};
+
+VectorXd random_theta(int N, double scale, unsigned seed) {
+  srand(seed);
+  return VectorXd::Random(N) * scale;
+}
+}  // namespace
+
+TEST(CudaUnfused, bernoulli_logit_lpmf) {
+  vector<int> n{1, 0, 1, 1, 0};
+  VectorXd theta(5);
+  theta << 0.3, -2.5, 25.0, -31.0, 0.0;  // both tails of the |theta| > 20 cut-off
+  compare_cpu_cuda_prim_rev(bern, std::make_tuple(DEV, DEV), n, theta);
+  compare_cpu_cuda_prim_rev(bern_propto, std::make_tuple(DEV, DEV), n, theta);
+  compare_cpu_cuda_prim_rev(bern, std::make_tuple(HOST, DEV), 1, theta);
+  int N = 4099;
+  vector<int> nb(N);
+  for (int i = 0; i < N; ++i) nb[i] = (i * 7) % 2;
+  compare_cpu_cuda_prim_rev(bern, std::make_tuple(DEV, DEV), nb, random_theta(N, 3.0, 1));
+  // +-inf is a legal logit, NaN is not; sizes must agree; n in {0, 1}
+  VectorXd t_inf(3), t_nan(3);
+  t_inf << INFINITY, -INFINITY, 0.5;
+  t_nan << 0.1, NAN, 0.5;
+  vector<int> n3{1, 0, 1}, n_bad{0, 2, 1};
+  matrix_cuda<int> n3_d(n3), n_bad_d(n_bad), n5_d(n);
+  matrix_cuda<double> t_inf_d(t_inf), t_nan_d(t_nan);
+  EXPECT_NEAR(stan::math::bernoulli_logit_lpmf(n3_d, t_inf_d),
+              stan::math::bernoulli_logit_lpmf(n3, t_inf), 1e-14);
+  EXPECT_THROW(stan::math::bernoulli_logit_lpmf(n3_d, t_nan_d), std::domain_error);
+  EXPECT_THROW(stan::math::bernoulli_logit_lpmf(n_bad_d, t_inf_d), std::domain_error);
+  EXPECT_THROW(stan::math::bernoulli_logit_lpmf(n5_d, t_inf_d), std::invalid_argument);
+  vector<int> e{};
+  compare_cpu_cuda_prim_rev(bern, std::make_tuple(DEV, DEV), e, VectorXd(0));
+}
+
+TEST(CudaUnfused, poisson_log_lpmf) {
+  vector<int> n{14, 0, 5, 2};
+  VectorXd alpha(4);
+  alpha << 0.3, -2.5, 1.7, 0.0;
+  compare_cpu_cuda_prim_rev(pois, std::make_tuple(DEV, DEV), n, alpha);
+  compare_cpu_cuda_prim_rev(pois_propto, std::make_tuple(DEV, DEV), n, alpha);
+  compare_cpu_cuda_prim_rev(pois, std::make_tuple(HOST, DEV), 3, alpha);
+  int N = 4099;
+  vector<int> nb(N);
+  for (int i = 0; i < N; ++i) nb[i] = (i * 7) % 9;
+  compare_cpu_cuda_prim_rev(pois, std::make_tuple(DEV, DEV), nb, random_theta(N, 2.0, 2));
+  // log(0) exits and value checks (poisson_log_lpmf.hpp L46-66)
+  VectorXd a_pinf(3), a_ninf(3), a_nan(3);
+  a_pinf << 0.1, INFINITY, 0.5;
+  a_ninf << 0.1, -INFINITY, 0.5;
+  a_nan << 0.1, NAN, 0.5;
+  vector<int> n3{1, 2, 1}, n_neg{0, -2, 1};
+  matrix_cuda<int> n3_d(n3), n_neg_d(n_neg);
+  matrix_cuda<double> a_pinf_d(a_pinf), a_ninf_d(a_ninf), a_nan_d(a_nan), a3_d(a_pinf);
+  EXPECT_EQ(stan::math::poisson_log_lpmf(n3_d, a_pinf_d), stan::math::LOG_ZERO);
+  EXPECT_EQ(stan::math::poisson_log_lpmf(n3_d, a_ninf_d), stan::math::LOG_ZERO);
+  EXPECT_THROW(stan::math::poisson_log_lpmf(n3_d, a_nan_d), std::domain_error);
+  EXPECT_THROW(stan::math::poisson_log_lpmf(n_neg_d, a3_d), std::domain_error);
+  matrix_cuda<int> n4_d(n);
+  EXPECT_THROW(stan::math::poisson_log_lpmf(n4_d, a3_d), std::invalid_argument);
+}
+
+TEST(CudaUnfused, neg_binomial_2_log_lpmf) {
+  vector<int> n{14, 0, 5, 2};
+  VectorXd eta(4);
+  eta << 0.3, -2.5, 1.7, 0.0;
+  double phi = 2.5;
+  compare_cpu_cuda_prim_rev(negb, std::make_tuple(DEV, DEV, HOST), n, eta, phi);
+  compare_cpu_cuda_prim_rev(negb_propto, std::make_tuple(DEV, DEV, HOST), n, eta, phi);
+  compare_cpu_cuda_prim_rev(negb, std::make_tuple(HOST, DEV, HOST), 3, eta, phi);
+  int N = 4099;
+  vector<int> nb(N);
+  for (int i = 0; i < N; ++i) nb[i] = (i * 7) % 9;
+  compare_cpu_cuda_prim_rev(negb, std::make_tuple(DEV, DEV, HOST), nb,
+                            random_theta(N, 2.0, 3), 0.7);
+  compare_cpu_cuda_prim_rev(negb_propto, std::make_tuple(DEV, DEV, HOST), nb,
+                            random_theta(N, 2.0, 3), 0.7);
+  VectorXd e_inf(4);
+  e_inf << 0.1, INFINITY, 0.5, 0.2;
+  matrix_cuda<int> n_d(n);
+  matrix_cuda<double> e_inf_d(e_inf), eta_d(eta);
+  EXPECT_THROW(stan::math::neg_binomial_2_log_lpmf(n_d, e_inf_d, phi), std::domain_error);
+  EXPECT_THROW(stan::math::neg_binomial_2_log_lpmf(n_d, eta_d, -1.0), std::domain_error);
+  vector<int> n_neg{0, -2, 1, 3};
+  matrix_cuda<int> n_neg_d(n_neg);
+  EXPECT_THROW(stan::math::neg_binomial_2_log_lpmf(n_neg_d, eta_d, phi), std::domain_error);
+}
+
+TEST(CudaUnfused, ordered_logistic_lpmf) {
+  vector<int> y{1, 1, 2, 4, 4, 3};
+  VectorXd lambda(6);
+  lambda << 1.9, 4.9, 7.9, 10.9, 3.6, -2.0;
+  VectorXd c(3);
+  c << 0.9, 1.1, 7;
+  compare_cpu_cuda_prim_rev(ordl, std::make_tuple(DEV, DEV, HOST), y, lambda, c);
+  compare_cpu_cuda_prim_rev(ordl_propto, std::make_tuple(DEV, DEV, HOST), y, lambda, c);
+  compare_cpu_cuda_prim_rev(ordl, std::make_tuple(HOST, DEV, HOST), 2, lambda, c);
+  int N = 4099;
+  vector<int> yb(N);
+  for (int i = 0; i < N; ++i) yb[i] = 1 + (i * 7) % 4;
+  compare_cpu_cuda_prim_rev(ordl, std::make_tuple(DEV, DEV, HOST), yb,
+                            random_theta(N, 3.0, 4), c);
+  matrix_cuda<int> y_d(y);
+  vector<int> y_bad{1, 1, 2, 5, 4, 3};
+  matrix_cuda<int> y_bad_d(y_bad);
+  matrix_cuda<double> l_d(lambda);
+  VectorXd l_inf = lambda, c_unordered(3);
+  l_inf[2] = INFINITY;
+  c_unordered << 0.9, 0.1, 7;
+  matrix_cuda<double> l_inf_d(l_inf);
+  EXPECT_THROW(stan::math::ordered_logistic_lpmf(y_bad_d, l_d, c), std::domain_error);
+  EXPECT_THROW(stan::math::ordered_logistic_lpmf(y_d, l_inf_d, c), std::domain_error);
+  EXPECT_THROW(stan::math::ordered_logistic_lpmf(y_d, l_d, c_unordered), std::domain_error);
+}
+
+TEST(CudaUnfused, multiply_add_then_density_matches_the_fused_glm) {
+  // y ~ bernoulli_logit(alpha + x * beta) built step by step on the device, against
+  // the same model on the host (the un-fused composition the reference's own GLM
+  // tests compare with) and against the fused device GLM
+  int N = 1531, K = 71;
+  srand(5);
+  MatrixXd x = MatrixXd::Random(N, K);
+  VectorXd beta = VectorXd::Random(K) / std::sqrt(K);
+  vector<int> y(N);
+  for (int i = 0; i < N; ++i) y[i] = (i * 11) % 2;
+  matrix_cuda<double> x_d(x);
+  matrix_cuda<int> y_d(y);
+
+  // all data
+  {
+    auto theta_d = stan::math::add(stan::math::multiply(x_d, beta), 0.3);
+    double dev = stan::math::bernoulli_logit_lpmf(y_d, theta_d);
+    double cpu = stan::math::bernoulli_logit_lpmf(y, ((x * beta).array() + 0.3).matrix());
+    expect_close("value", dev, cpu, kRelLogp, 0);
+  }
+  // alpha, beta autodiff
+  {
+    var a1 = 0.3, a2 = 0.3, a3 = 0.3;
+    Matrix<var, Dynamic, 1> b1 = beta, b2 = beta, b3 = beta;
+    var lp_dev = stan::math::bernoulli_logit_lpmf(
+        y_d, stan::math::add(stan::math::multiply(x_d, b1), a1));
+    Matrix<var, Dynamic, 1> th2 = stan::math::add(stan::math::multiply(x, b2), a2);
+    var lp_cpu = stan::math::bernoulli_logit_lpmf(y, th2);
+    var lp_glm = stan::math::bernoulli_logit_glm_lpmf(y_d, x_d, a3, b3);
+    (lp_dev + lp_cpu + lp_glm).grad();
+    expect_close("value vs host", lp_dev.val(), lp_cpu.val(), kRelLogp, 0);
+    expect_close("value vs fused", lp_dev.val(), lp_glm.val(), kRelLogp, 0);
+    expect_close("d_alpha", a1.adj(), a2.adj(), kRelGrad, std::fabs(a2.adj()));
+    expect_close("d_alpha vs fused", a1.adj(), a3.adj(), kRelGrad, std::fabs(a3.adj()));
+    const double scale = b2.adj().cwiseAbs().maxCoeff();
+    for (int k = 0; k < K; ++k) {
+      expect_close("d_beta", b1[k].adj(), b2[k].adj(), kRelGrad, scale);
+      expect_close("d_beta vs fused", b1[k].adj(), b3[k].adj(), kRelGrad, scale);
+    }
+    stan::math::recover_memory();
+  }
+  // var_value<vector> beta, poisson
+  {
+    vector<int> yp(N);
+    for (int i = 0; i < N; ++i) yp[i] = (i * 5) % 7;
+    matrix_cuda<int> yp_d(yp);
+    stan::math::var_value<VectorXd> b1(beta), b2(beta);
+    var lp_dev = stan::math::poisson_log_lpmf(
+        yp_d, stan::math::add(stan::math::multiply(x_d, b1), 0.1));
+    var lp_glm = stan::math::poisson_log_glm_lpmf(yp_d, x_d, 0.1, b2);
+    (lp_dev + lp_glm).grad();
+    expect_close("poisson value vs fused", lp_dev.val(), lp_glm.val(), kRelLogp, 0);
+    const double scale = b2.adj().cwiseAbs().maxCoeff();
+    for (int k = 0; k < K; ++k)
+      expect_close("poisson d_beta", b1.adj()[k], b2.adj()[k], kRelGrad, scale);
+    stan::math::recover_memory();
+  }
+  EXPECT_THROW(stan::math::multiply(x_d, VectorXd(VectorXd::Zero(K + 1))),
+               std::invalid_argument);
+}

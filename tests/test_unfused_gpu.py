@@ -1,0 +1,123 @@
+"""GPU parity of the step either side of the fused GLMs: the
+device matrix-vector product and the un-fused densities on a device linear
+predictor, against the CPU oracle.
+
+The oracle restates the GLMs; an un-fused density on theta is the same GLM with
+the predictor passed through the intercept vector (x = 0), or -- for the ordered
+family, which has no intercept -- through a one-column x = theta with beta = 1,
+whose d_x is d/dtheta.  The C++ suite (tests/cpp/unfused_lpmf_test.cpp) compares
+the same entry points with the reference's own prim *_lpmf implementations."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from tests.util import assert_grad, assert_logp, make_inputs
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(1, 1), (33, 7), (4099, 64), (20011, 256), (3001, 300)]
+
+
+@pytest.mark.parametrize("N,K", SIZES)
+def test_multiply_and_adjoint(gpu, N, K):
+    mb = gpu
+    d = make_inputs("bernoulli", N, K, seed=N + K, vec_alpha=True)
+    x = mb.to_matrix_cuda(d["x"])
+    theta = mb.lpmf.multiply(x, d["beta"], mb.to_matrix_cuda(d["alpha"]))
+    want = d["x"] @ d["beta"] + d["alpha"]
+    assert_grad(mb.from_matrix_cuda(theta).ravel(), want, "theta",
+                scale=np.abs(d["x"]).max() * np.abs(d["beta"]).sum())
+    theta0 = mb.lpmf.multiply(x, d["beta"], 0.25)
+    assert_grad(mb.from_matrix_cuda(theta0).ravel(), d["x"] @ d["beta"] + 0.25, "theta0",
+                scale=np.abs(d["x"]).max() * np.abs(d["beta"]).sum())
+    rng = np.random.default_rng(7)
+    v = rng.standard_normal(N)
+    g, s = mb.lpmf.multiply_adjoint(x, mb.to_matrix_cuda(v))
+    assert_grad(g, d["x"].T @ v, "x^T v", scale=np.abs(d["x"]).max() * np.abs(v).sum())
+    assert_logp(s, float(np.sum(v)) if abs(np.sum(v)) > 1e-6 else s, "sum v")
+    assert abs(s - np.sum(v)) <= 1e-12 * np.abs(v).sum()
+    assert abs(mb.lpmf.vector_sum(mb.to_matrix_cuda(v)) - np.sum(v)) <= 1e-12 * np.abs(v).sum()
+
+
+def _theta(N, seed, scale=2.0):
+    return np.random.default_rng(seed).standard_normal(N) * scale
+
+
+@pytest.mark.parametrize("N", [1, 257, 50021])
+@pytest.mark.parametrize("family", ["bernoulli", "poisson"])
+def test_theta_lpmf_matches_oracle(gpu, family, N):
+    mb = gpu
+    theta = _theta(N, N)
+    rng = np.random.default_rng(N + 1)
+    y = (rng.integers(0, 2, N) if family == "bernoulli" else rng.integers(0, 7, N)) \
+        .astype(np.int32)
+    zero_x = np.zeros((N, 1), order="F")
+    if family == "bernoulli":
+        o = po.bernoulli_logit_glm(y, zero_x, theta, [0.0])
+        r = mb.lpmf.bernoulli_logit_lpmf(mb.to_matrix_cuda(y), mb.to_matrix_cuda(theta))
+    else:
+        o = po.poisson_log_glm(y, zero_x, theta, [0.0])
+        r = mb.lpmf.poisson_log_lpmf(mb.to_matrix_cuda(y), mb.to_matrix_cuda(theta))
+    assert_logp(r.logp, o["logp"])
+    assert_grad(mb.from_matrix_cuda(r.d_theta).ravel(), o["d_alpha"], "d_theta")
+
+
+@pytest.mark.parametrize("N", [1, 257, 50021])
+def test_neg_binomial_lpmf_matches_oracle(gpu, N):
+    mb = gpu
+    eta = _theta(N, N)
+    y = np.random.default_rng(N + 2).integers(0, 9, N).astype(np.int32)
+    o = po.neg_binomial_2_log_glm(y, np.zeros((N, 1), order="F"), eta, [0.0], 2.5)
+    r = mb.lpmf.neg_binomial_2_log_lpmf(mb.to_matrix_cuda(y), mb.to_matrix_cuda(eta), 2.5)
+    assert_logp(r.logp, o["logp"])
+    assert_grad(mb.from_matrix_cuda(r.d_theta).ravel(), o["d_alpha"], "d_eta")
+    assert_grad(r.d_aux, np.asarray(o["d_phi"]).ravel()[0], "d_phi",
+                scale=np.abs(o["d_alpha"]).sum())
+
+
+@pytest.mark.parametrize("N", [1, 257, 50021])
+def test_ordered_logistic_lpmf_matches_oracle(gpu, N):
+    mb = gpu
+    lam = _theta(N, N, 3.0)
+    cuts = np.array([-1.5, -0.2, 0.4, 2.0])
+    y = np.random.default_rng(N + 3).integers(1, 6, N).astype(np.int32)
+    o = po.ordered_logistic_glm(y, np.asfortranarray(lam.reshape(N, 1)), [1.0], cuts,
+                                flags=po.VAR_BETA | po.VAR_AUX | po.VAR_X)
+    r = mb.lpmf.ordered_logistic_lpmf(mb.to_matrix_cuda(y), mb.to_matrix_cuda(lam), cuts)
+    assert_logp(r.logp, o["logp"])
+    assert_grad(mb.from_matrix_cuda(r.d_theta).ravel(), o["d_x"].ravel(), "d_lambda")
+    assert_grad(r.d_aux, o["d_cuts"], "d_cuts", scale=np.abs(o["d_x"]).sum())
+
+
+def test_unfused_pipeline_equals_fused_glm(gpu):
+    """multiply -> density -> multiply_adjoint gives the fused GLM's value and
+    gradient (three sweeps instead of one: what the fusion buys is in DESIGN.md)."""
+    mb = gpu
+    N, K = 30011, 128
+    d = make_inputs("bernoulli", N, K, seed=99)
+    x, y = mb.to_matrix_cuda(d["x"]), mb.to_matrix_cuda(d["y"])
+    fused = mb.bernoulli_logit_glm_lpmf(y, x, d["alpha"], d["beta"])
+    theta = mb.lpmf.multiply(x, d["beta"], d["alpha"])
+    un = mb.lpmf.bernoulli_logit_lpmf(y, theta)
+    g, s = mb.lpmf.multiply_adjoint(x, un.d_theta)
+    assert_logp(un.logp, fused.logp)
+    assert_grad(g, fused.d_beta, "d_beta")
+    assert_grad(s, fused.d_alpha, "d_alpha", scale=np.abs(fused.d_beta).max())
+
+
+def test_value_checks(gpu):
+    mb = gpu
+    y = mb.to_matrix_cuda(np.array([1, 0, 1], dtype=np.int32))
+    with pytest.raises(mb.DomainError):
+        mb.lpmf.bernoulli_logit_lpmf(y, mb.to_matrix_cuda(np.array([0.1, np.nan, 1.0])))
+    r = mb.lpmf.bernoulli_logit_lpmf(y, mb.to_matrix_cuda(np.array([np.inf, -np.inf, 1.0])))
+    assert np.isfinite(r.logp)
+    with pytest.raises(ValueError):
+        mb.lpmf.bernoulli_logit_lpmf(y, mb.to_matrix_cuda(np.zeros(4)))
+    r = mb.lpmf.poisson_log_lpmf(y, mb.to_matrix_cuda(np.array([0.1, np.inf, 1.0])))
+    assert r.logp == -np.inf
+    assert np.all(mb.from_matrix_cuda(r.d_theta) == 0)
+    with pytest.raises(mb.DomainError):
+        mb.lpmf.neg_binomial_2_log_lpmf(y, mb.to_matrix_cuda(np.array([0.1, np.inf, 1.0])), 2.0)
+    with pytest.raises(mb.DomainError):
+        mb.lpmf.ordered_logistic_lpmf(y, mb.to_matrix_cuda(np.zeros(3)), [0.5, 0.1])
