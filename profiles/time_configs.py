@@ -104,6 +104,24 @@ def main():
             cuts = np.linspace(-2, 2, 8)
             t = timeit(lambda: mb.ordered_logistic_glm_lpmf(y, x, beta, cuts), 20)
             byt, name = N * K * 8, "ordered_logistic N=1e7 K=64, 8 cuts"
+        elif cfg == "u2":
+            # the same model as config 2 built step by step on the
+            # device -- theta = x beta + alpha, bernoulli_logit_lpmf(y | theta),
+            # d_beta = x^T d_theta -- two sweeps over x instead of one
+            N, K = 10_000_000, 256
+            x, y = synth(N, K), ints(N, 0, 1)
+            beta = rng.standard_normal(K) / np.sqrt(K)
+
+            def unfused():
+                theta = mb.lpmf.multiply(x, beta, 0.1)
+                r = mb.lpmf.bernoulli_logit_lpmf(y, theta)
+                return mb.lpmf.multiply_adjoint(x, r.d_theta)
+            t = timeit(unfused, 20)
+            t_mul = timeit(lambda: mb.lpmf.multiply(x, beta, 0.1), 20)
+            byt, name = 2 * N * K * 8, ("un-fused bernoulli_logit N=1e7 K=256: multiply + "
+                                        "lpmf + multiply_adjoint (2 sweeps over x); "
+                                        f"multiply alone {t_mul*1e3:.3f} ms = "
+                                        f"{N*K*8/t_mul/1e9:.0f} GB/s")
         else:
             continue
         print(json.dumps({"config": cfg, "name": name, "ms_per_eval": t * 1e3,

@@ -95,3 +95,38 @@ TEST(CudaMatrix, var_value_eigen_and_std_vector) {
   for (int i = 0; i < 3; ++i) EXPECT_DOUBLE_EQ(sv[i].adj(), 3.0);
   stan::math::recover_memory();
 }
+
+// SURVEY.md 8(b) "Threading" / 8(f)4: several chains evaluate the same GLM
+// concurrently on ONE shared, read-only device x.  The C ABI keeps its stream and
+// workspace per host thread, so the calls are re-entrant; every thread must get
+// exactly what a lone call gets (the reductions are fixed-order).
+#include <thread>
+TEST(CudaMatrix, concurrent_chains_share_one_design_matrix) {
+  const int N = 20011, K = 96, T = 4, REPS = 8;
+  srand(11);
+  MatrixXd x = MatrixXd::Random(N, K);
+  std::vector<int> y(N);
+  for (int i = 0; i < N; ++i) y[i] = (i * 13) % 2;
+  matrix_cuda<double> x_d(x);
+  matrix_cuda<int> y_d(y);
+  std::vector<VectorXd> betas(T);
+  std::vector<double> want(T);
+  for (int t = 0; t < T; ++t) {
+    betas[t] = VectorXd::Random(K) / std::sqrt(K);
+    want[t] = stan::math::bernoulli_logit_glm_lpmf(y_d, x_d, 0.1 * t, betas[t]);
+    EXPECT_NEAR(want[t], stan::math::bernoulli_logit_glm_lpmf(y, x, 0.1 * t, betas[t]),
+                1e-10 * std::fabs(want[t]));
+  }
+  std::vector<int> mismatches(T, 0);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < T; ++t) {
+    pool.emplace_back([&, t]() {
+      for (int r = 0; r < REPS; ++r) {
+        const double got = stan::math::bernoulli_logit_glm_lpmf(y_d, x_d, 0.1 * t, betas[t]);
+        if (got != want[t]) ++mismatches[t];  // bit-identical, not merely close
+      }
+    });
+  }
+  for (auto& th : pool) th.join();
+  for (int t = 0; t < T; ++t) EXPECT_EQ(mismatches[t], 0) << "thread " << t;
+}

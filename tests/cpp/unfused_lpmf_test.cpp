@@ -6,6 +6,8 @@
 // the protocol is the one of test/unit/math/opencl/util.hpp L129-191.
 #include "cuda_test_util.hpp"
 
+#include <boost/random/mersenne_twister.hpp>
+
 using Eigen::Dynamic;
 using Eigen::Matrix;
 using Eigen::MatrixXd;
@@ -213,4 +215,52 @@ TEST(CudaUnfused, multiply_add_then_density_matches_the_fused_glm) {
   }
   EXPECT_THROW(stan::math::multiply(x_d, VectorXd(VectorXd::Zero(K + 1))),
                std::invalid_argument);
+}
+
+TEST(CudaUnfused, bernoulli_logit_glm_rng_draws_what_prim_draws) {
+  // same generator state in, same variates out
+  int N = 2003, K = 37;
+  srand(6);
+  MatrixXd x = MatrixXd::Random(N, K);
+  VectorXd beta = VectorXd::Random(K);
+  VectorXd alpha = VectorXd::Random(N);
+  matrix_cuda<double> x_d(x);
+  {
+    boost::random::mt19937 rng_cpu(1234), rng_dev(1234);
+    vector<int> cpu = stan::math::bernoulli_logit_glm_rng(x, alpha, beta, rng_cpu);
+    vector<int> dev = stan::math::bernoulli_logit_glm_rng(x_d, alpha, beta, rng_dev);
+    ASSERT_EQ(cpu.size(), dev.size());
+    int differ = 0, ones = 0;
+    for (int i = 0; i < N; ++i) {
+      differ += cpu[i] != dev[i];
+      ones += dev[i];
+    }
+    EXPECT_EQ(differ, 0);
+    EXPECT_GT(ones, N / 4);
+    EXPECT_LT(ones, 3 * N / 4);
+    EXPECT_EQ(rng_cpu(), rng_dev());  // the generators advanced in step
+  }
+  {  // std::vector intercepts and weights
+    boost::random::mt19937 rng_cpu(99), rng_dev(99);
+    vector<double> a(alpha.data(), alpha.data() + N), b(beta.data(), beta.data() + K);
+    EXPECT_EQ(stan::math::bernoulli_logit_glm_rng(x, a, b, rng_cpu),
+              stan::math::bernoulli_logit_glm_rng(x_d, a, b, rng_dev));
+  }
+  {  // error behaviour, prim L55-62
+    boost::random::mt19937 rng(1);
+    VectorXd beta_bad = beta, alpha_short = alpha.head(N - 1), beta_long(K + 1);
+    beta_bad[3] = INFINITY;
+    beta_long.setZero();
+    MatrixXd x_bad = x;
+    x_bad(5, 5) = NAN;
+    matrix_cuda<double> x_bad_d(x_bad);
+    EXPECT_THROW(stan::math::bernoulli_logit_glm_rng(x_d, alpha, beta_long, rng),
+                 std::invalid_argument);
+    EXPECT_THROW(stan::math::bernoulli_logit_glm_rng(x_d, alpha_short, beta, rng),
+                 std::invalid_argument);
+    EXPECT_THROW(stan::math::bernoulli_logit_glm_rng(x_d, alpha, beta_bad, rng),
+                 std::domain_error);
+    EXPECT_THROW(stan::math::bernoulli_logit_glm_rng(x_bad_d, alpha, beta, rng),
+                 std::domain_error);
+  }
 }
