@@ -1,13 +1,14 @@
 #ifndef STAN_MATH_CUDA_PRIM_UNFUSED_LPMF_HPP
 #define STAN_MATH_CUDA_PRIM_UNFUSED_LPMF_HPP
 // The un-fused densities on a device-resident linear predictor (SURVEY.md
-// 8(f)3): bernoulli_logit_lpmf, poisson_log_lpmf, neg_binomial_2_log_lpmf and
-// ordered_logistic_lpmf for a theta that is a matrix_cuda<double> or a
-// var_value<matrix_cuda<double>> -- the B200 overloads of
+// 8(f)3): bernoulli_logit_lpmf, poisson_log_lpmf, neg_binomial_2_log_lpmf,
+// ordered_logistic_lpmf and normal_lpdf for a theta that is a matrix_cuda<double>
+// or a var_value<matrix_cuda<double>> -- the B200 overloads of
 //   prim/prob/bernoulli_logit_lpmf.hpp L33-98      (opencl/prim/bernoulli_logit_lpmf.hpp)
 //   prim/prob/poisson_log_lpmf.hpp L27-100         (opencl/prim/poisson_log_lpmf.hpp)
 //   prim/prob/neg_binomial_2_log_lpmf.hpp L24-134  (opencl/prim/neg_binomial_2_log_lpmf.hpp)
 //   prim/prob/ordered_logistic_lpmf.hpp L72-214    (opencl/prim/ordered_logistic_lpmf.hpp)
+//   prim/prob/normal_lpdf.hpp L41-104              (opencl/prim/normal_lpdf.hpp)
 // for models that add terms to x * beta before the likelihood.  Same names,
 // template order and <propto>; value and d/dtheta come from one kernel over the
 // N-vector and are attached through make_partials_propagator(...).build(logp).
@@ -156,6 +157,53 @@ return_type_t<T_loc, T_cut> ordered_logistic_lpmf(const T_y& y, const T_loc& lam
   }
   if constexpr (!is_constant_all<T_cut>::value) {
     store_host_partial<T_cut>(partials<1>(ops_partials), d_cuts.data(), n_cuts);
+  }
+  return ops_partials.build(logp);
+}
+
+/** normal_lpdf(y | mu, sigma) with y and / or mu on the device (data or autodiff)
+ * and a host scalar sigma: prim/prob/normal_lpdf.hpp L41-104. */
+template <bool propto, typename T_y, typename T_loc, typename T_scale,
+          require_any_t<is_cuda_operand<T_y>, is_cuda_operand<T_loc>>* = nullptr,
+          require_stan_scalar_t<T_scale>* = nullptr>
+return_type_t<T_y, T_loc, T_scale> normal_lpdf(T_y&& y, T_loc&& mu, T_scale&& sigma) {
+  using namespace cuda_internal;  // NOLINT
+  using Ty = std::decay_t<T_y>;
+  using Tm = std::decay_t<T_loc>;
+  using Ts = std::decay_t<T_scale>;
+  static constexpr const char* function = "normal_lpdf(CUDA)";
+  if (!is_stan_scalar<Ty>::value && !is_stan_scalar<Tm>::value) {
+    check_size_match(function, "Size of ", "Random variable", operand_size(y),
+                     "size of ", "Location parameter", operand_size(mu));
+  }
+  static_assert(is_stan_scalar<Ty>::value || is_cuda_operand<Ty>::value,
+                "normal_lpdf(CUDA): y is a scalar or a device vector");
+  static_assert(is_stan_scalar<Tm>::value || is_cuda_operand<Tm>::value,
+                "normal_lpdf(CUDA): mu is a scalar or a device vector");
+  row_operand<double, Ty> y_op(y);
+  row_operand<double, Tm> mu_op(mu);
+  auto ops_partials = make_partials_propagator(y, mu, sigma);
+  double logp = 0, d_y = 0, d_mu = 0, d_sigma = 0;
+  const unsigned flags = (propto ? SMC_PROPTO : 0u) | var_flag<Ty>(SMC_VAR_Y)
+                         | var_flag<Tm>(SMC_VAR_ALPHA) | var_flag<Ts>(SMC_VAR_AUX);
+  check_cuda_status(
+      function,
+      smc_normal_lpdf(y_op.handle(), y_op.scalar(), mu_op.handle(), mu_op.scalar(),
+                      value_of(sigma), flags, &logp,
+                      dvec_handle<Ty>(partials<0>(ops_partials)), &d_y,
+                      dvec_handle<Tm>(partials<1>(ops_partials)), &d_mu, &d_sigma));
+  if (operand_size(y) == 0 || operand_size(mu) == 0
+      || !include_summand<propto, Ty, Tm, Ts>::value) {
+    return 0.0;
+  }
+  if constexpr (!is_constant_all<Ty>::value && is_stan_scalar<Ty>::value) {
+    partials<0>(ops_partials)[0] = d_y;
+  }
+  if constexpr (!is_constant_all<Tm>::value && is_stan_scalar<Tm>::value) {
+    partials<1>(ops_partials)[0] = d_mu;
+  }
+  if constexpr (!is_constant_all<Ts>::value) {
+    partials<2>(ops_partials)[0] = d_sigma;
   }
   return ops_partials.build(logp);
 }

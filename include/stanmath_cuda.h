@@ -266,6 +266,14 @@ int smc_neg_binomial_2_log_lpmf(const smc_matrix* n, int n_scalar,
                                 double phi, unsigned flags, double* logp,
                                 smc_matrix* d_eta, double* d_phi,
                                 smc_matrix* d_phi_vec);
+/* prim/prob/normal_lpdf.hpp L41-104.  y and mu: N x 1 f64 device vectors or NULL ->
+ * the broadcast scalars (at least one is a vector); sigma a host scalar.  Flags:
+ * SMC_VAR_Y (d_y_vec device / d_y host for a scalar y), SMC_VAR_ALPHA marks mu
+ * (d_mu_vec / d_mu), SMC_VAR_AUX marks sigma (d_sigma host). */
+int smc_normal_lpdf(const smc_matrix* y, double y_scalar, const smc_matrix* mu,
+                    double mu_scalar, double sigma, unsigned flags, double* logp,
+                    smc_matrix* d_y_vec, double* d_y, smc_matrix* d_mu_vec,
+                    double* d_mu, double* d_sigma);
 /* prim/prob/ordered_logistic_lpmf.hpp L72-214 (one cut-point vector, host) */
 int smc_ordered_logistic_lpmf(const smc_matrix* y, int y_scalar,
                               const smc_matrix* lambda, const double* cuts,

@@ -297,6 +297,81 @@ int smc_neg_binomial_2_log_lpmf(const smc_matrix* n, int n_scalar,
   return SMC_OK;
 }
 
+int smc_normal_lpdf(const smc_matrix* y, double y_scalar, const smc_matrix* mu,
+                    double mu_scalar, double sigma, unsigned flags, double* logp,
+                    smc_matrix* d_y_vec, double* d_y, smc_matrix* d_mu_vec,
+                    double* d_mu, double* d_sigma) {
+  static const char* fn = "normal_lpdf";
+  if (int rc = ensure_ctx()) return rc;
+  if (!y && !mu)
+    return fail(SMC_ERR_INVALID_ARGUMENT, "%s: y or mu must be a device vector", fn);
+  const smc_matrix* ref = mu ? mu : y;
+  if (ref->dtype != SMC_F64 || !is_vec(ref))
+    return fail(SMC_ERR_INVALID_ARGUMENT, "%s: operands must be f64 device vectors", fn);
+  const int64_t N = ref->rows * ref->cols;
+  const smc_matrix* vs[4] = {y, mu, d_y_vec, d_mu_vec};
+  for (const smc_matrix* v : vs)
+    if (v && (v->dtype != SMC_F64 || v->rows * v->cols != N))
+      return fail(SMC_ERR_INVALID_ARGUMENT,
+                  "%s: sizes of the random variable and the location parameter do not "
+                  "match",
+                  fn);
+  if (!logp) return fail(SMC_ERR_INVALID_ARGUMENT, "%s: NULL logp", fn);
+  *logp = 0.0;
+  if (d_y) *d_y = 0.0;
+  if (d_mu) *d_mu = 0.0;
+  if (d_sigma) *d_sigma = 0.0;
+  // scalars are checked at once, the vectors lazily below (L60-62)
+  if (!y && std::isnan(y_scalar))
+    return fail(SMC_ERR_DOMAIN, "%s: Random variable is nan", fn);
+  if (!mu && !std::isfinite(mu_scalar))
+    return fail(SMC_ERR_DOMAIN, "%s: Location parameter is not finite", fn);
+  if (!(sigma > 0.0))
+    return fail(SMC_ERR_DOMAIN, "%s: Scale parameter is %g, but must be positive", fn,
+                sigma);
+  if (N == 0) return SMC_OK;  // L64-66
+  const bool skip
+      = (flags & SMC_PROPTO) && !(flags & (SMC_VAR_Y | SMC_VAR_ALPHA | SMC_VAR_AUX));
+  smc_matrix x0 = empty_design(N);
+  GlmCall c;
+  c.family = kNormal;
+  c.unfused = true;
+  c.x = &x0;
+  c.y = y;
+  c.y_scalar = y_scalar;
+  c.alpha_vec = mu;
+  c.alpha = mu_scalar;
+  c.aux = sigma;
+  c.flags = flags & (SMC_PROPTO | SMC_VAR_Y | SMC_VAR_ALPHA | SMC_VAR_AUX);
+  c.d_alpha_vec = (flags & SMC_VAR_ALPHA) ? d_mu_vec : nullptr;
+  c.d_y_vec = (flags & SMC_VAR_Y) ? d_y_vec : nullptr;
+  if (c.d_alpha_vec) d_mu_vec->version++;
+  if (c.d_y_vec) d_y_vec->version++;
+  const double* o;
+  if (int rc = run_sync(c, SMC_OUT_HEADER, &o)) return rc;
+  const double lp = o[SMC_OUT_LOGP], sum_d = o[SMC_OUT_SUM_D], sum_r2 = o[SMC_OUT_AUX2];
+  if (!std::isfinite(sum_r2) && std::isfinite(sigma)) {
+    // some (y_i - mu_i) / sigma is not finite: check_not_nan(y), check_finite(mu)
+    int ok = 1;
+    if (mu) {
+      if (int rc = smc_matrix_all_finite(mu, &ok)) return rc;
+      if (!ok) return fail(SMC_ERR_DOMAIN, "%s: Location parameter is not finite", fn);
+    }
+    if (y) {
+      std::vector<double> yv;
+      if (int rc = fetch(y, &yv)) return rc;
+      for (double t : yv)
+        if (std::isnan(t)) return fail(SMC_ERR_DOMAIN, "%s: Random variable is nan", fn);
+    }
+  }
+  if (skip) return SMC_OK;  // L67-69
+  *logp = lp;
+  if (d_mu && (flags & SMC_VAR_ALPHA) && !mu) *d_mu = sum_d;
+  if (d_y && (flags & SMC_VAR_Y) && !y) *d_y = -sum_d;
+  if (d_sigma && (flags & SMC_VAR_AUX)) *d_sigma = (sum_r2 - (double)N) * (1.0 / sigma);
+  return SMC_OK;
+}
+
 int smc_ordered_logistic_lpmf(const smc_matrix* y, int y_scalar,
                               const smc_matrix* lambda, const double* cuts,
                               int64_t ncuts, unsigned flags, double* logp,

@@ -97,3 +97,24 @@ def ordered_logistic_lpmf(y, lam, cuts, propto=False, theta_var=True, cuts_var=T
     check(lib().smc_ordered_logistic_lpmf(_h(yv), ys, lam.handle, _dp(c), c.size,
                                           flags, C.byref(logp), _h(d), _dp(d_cuts)))
     return LpmfResult(logp.value, d, d_cuts if cuts_var else None)
+
+
+def normal_lpdf(y, mu, sigma, propto=False, var=("mu", "sigma")):
+    """prim/prob/normal_lpdf.hpp L41-104: y, mu scalars or N x 1 f64 MatrixCuda (at
+    least one a vector), sigma a scalar.  `var` names the autodiff operands;
+    returns (logp, d_y, d_mu, d_sigma) with device vectors for vector operands."""
+    yv, ys = _split(y, float, "y")
+    mv, ms = _split(mu, float, "mu")
+    n = (mv if mv is not None else yv).size()
+    flags = (PROPTO if propto else 0) | (VAR_ALPHA if "mu" in var else 0) \
+        | (VAR_AUX if "sigma" in var else 0) | (32 if "y" in var else 0)
+    d_yv = MatrixCuda(n, 1, np.float64) if ("y" in var and yv is not None) else None
+    d_mv = MatrixCuda(n, 1, np.float64) if ("mu" in var and mv is not None) else None
+    logp, d_y, d_mu, d_sigma = (C.c_double() for _ in range(4))
+    check(lib().smc_normal_lpdf(_h(yv), ys, _h(mv), ms, float(sigma), flags,
+                                C.byref(logp), _h(d_yv), C.byref(d_y), _h(d_mv),
+                                C.byref(d_mu), C.byref(d_sigma)))
+    return (logp.value,
+            (d_yv if yv is not None else d_y.value) if "y" in var else None,
+            (d_mv if mv is not None else d_mu.value) if "mu" in var else None,
+            d_sigma.value if "sigma" in var else None)

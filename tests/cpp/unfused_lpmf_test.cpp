@@ -156,6 +156,39 @@ TEST(CudaUnfused, ordered_logistic_lpmf) {
   EXPECT_THROW(stan::math::ordered_logistic_lpmf(y_d, l_d, c_unordered), std::domain_error);
 }
 
+TEST(CudaUnfused, normal_lpdf) {
+  auto norm = [](const auto& y, const auto& mu, const auto& sigma) {
+    return stan::math::normal_lpdf(y, mu, sigma);
+  };
+  auto norm_propto = [](const auto& y, const auto& mu, const auto& sigma) {
+    return stan::math::normal_lpdf<true>(y, mu, sigma);
+  };
+  VectorXd y(5), mu(5);
+  y << 14, 32, 21, -3.5, 0.25;
+  mu << 12.5, 30, 22, -3, 0;
+  double sigma = 1.7;
+  compare_cpu_cuda_prim_rev(norm, std::make_tuple(DEV, DEV, HOST), y, mu, sigma);
+  compare_cpu_cuda_prim_rev(norm_propto, std::make_tuple(DEV, DEV, HOST), y, mu, sigma);
+  compare_cpu_cuda_prim_rev(norm, std::make_tuple(DEV, HOST, HOST), y, 1.5, sigma);
+  compare_cpu_cuda_prim_rev(norm, std::make_tuple(HOST, DEV, HOST), 2.5, mu, sigma);
+  int N = 4099;
+  compare_cpu_cuda_prim_rev(norm, std::make_tuple(DEV, DEV, HOST), random_theta(N, 3.0, 7),
+                            random_theta(N, 2.0, 8), 0.6);
+  matrix_cuda<double> y_d(y), mu_d(mu);
+  VectorXd y_nan = y, mu_inf = mu, y_inf = y;
+  y_nan[1] = NAN;
+  mu_inf[2] = INFINITY;
+  y_inf[3] = INFINITY;
+  matrix_cuda<double> y_nan_d(y_nan), mu_inf_d(mu_inf), y_inf_d(y_inf), short_d(VectorXd(VectorXd::Zero(4)));
+  EXPECT_THROW(stan::math::normal_lpdf(y_nan_d, mu_d, sigma), std::domain_error);
+  EXPECT_THROW(stan::math::normal_lpdf(y_d, mu_inf_d, sigma), std::domain_error);
+  EXPECT_THROW(stan::math::normal_lpdf(y_d, mu_d, 0.0), std::domain_error);
+  EXPECT_THROW(stan::math::normal_lpdf(y_d, short_d, sigma), std::invalid_argument);
+  // an infinite observation is legal (check_not_nan only): -inf, as prim returns
+  EXPECT_EQ(stan::math::normal_lpdf(y_inf_d, mu_d, sigma),
+            stan::math::normal_lpdf(y_inf, mu, sigma));
+}
+
 TEST(CudaUnfused, multiply_add_then_density_matches_the_fused_glm) {
   // y ~ bernoulli_logit(alpha + x * beta) built step by step on the device, against
   // the same model on the host (the un-fused composition the reference's own GLM

@@ -89,6 +89,21 @@ def test_ordered_logistic_lpmf_matches_oracle(gpu, N):
     assert_grad(r.d_aux, o["d_cuts"], "d_cuts", scale=np.abs(o["d_x"]).sum())
 
 
+@pytest.mark.parametrize("N", [1, 257, 50021])
+def test_normal_lpdf_matches_oracle(gpu, N):
+    mb = gpu
+    rng = np.random.default_rng(N + 4)
+    mu = rng.standard_normal(N) * 2
+    y = mu + 1.3 * rng.standard_normal(N)
+    o = po.normal_id_glm(y, np.zeros((N, 1), order="F"), mu, [0.0], 1.3)
+    logp, _, d_mu, d_sigma = mb.lpmf.normal_lpdf(mb.to_matrix_cuda(y),
+                                                 mb.to_matrix_cuda(mu), 1.3)
+    assert_logp(logp, o["logp"])
+    assert_grad(mb.from_matrix_cuda(d_mu).ravel(), o["d_alpha"], "d_mu")
+    assert_grad(d_sigma, np.asarray(o["d_sigma"]).ravel()[0], "d_sigma",
+                scale=np.abs(o["d_alpha"]).sum())
+
+
 def test_unfused_pipeline_equals_fused_glm(gpu):
     """multiply -> density -> multiply_adjoint gives the fused GLM's value and
     gradient (three sweeps instead of one: what the fusion buys is in DESIGN.md)."""
