@@ -27,6 +27,11 @@ Context::~Context() {
   if (own_stream) cudaStreamDestroy(own_stream);
 }
 
+std::mutex& cache_mutex() {
+  static std::mutex m;
+  return m;
+}
+
 int fail(int status, const char* fmt, ...) {
   char buf[512];
   va_list ap;

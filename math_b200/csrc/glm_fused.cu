@@ -26,6 +26,7 @@
 //   normal_id_glm_lpdf.hpp L122-213, bernoulli_logit_glm_lpmf.hpp L105-164,
 //   poisson_log_glm_lpmf.hpp L107-161, neg_binomial_2_log_glm_lpmf.hpp L143-244,
 //   ordered_logistic_glm_lpmf.hpp L108-207, binomial_logit_glm_lpmf.hpp L104-154.
+#include <atomic>
 #include <cmath>
 #include <cstring>
 
@@ -473,6 +474,7 @@ bool fused_supported(const smc_matrix* x) {
 
 static int get_tmap(const smc_matrix* xc, int R, int CW, CUtensorMap* out) {
   smc_matrix* x = const_cast<smc_matrix*>(xc);
+  std::lock_guard<std::mutex> lock(cache_mutex());  // x is shared between chains
   if (x->tmap_rows == R && x->tmap_cols == CW) {
     *out = x->tmap;
     return SMC_OK;
@@ -494,7 +496,7 @@ static int get_tmap(const smc_matrix* xc, int R, int CW, CUtensorMap* out) {
 template <int FAM, int G, bool DX>
 static int launch_tgx(const CUtensorMap& tmap, const CUtensorMap& tmap_dx,
                       const FusedArgs& a, int grid, int threads, size_t smem) {
-  static size_t attr_smem[16] = {};
+  static std::atomic<size_t> attr_smem[16];
   Context& c = ctx();
   if (attr_smem[c.device & 15] < smem) {
     SMC_CUDA(cudaFuncSetAttribute(glm_fused_kernel<FAM, G, DX>,

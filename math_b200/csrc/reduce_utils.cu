@@ -53,6 +53,7 @@ __global__ void y_stats_kernel(const int* __restrict__ y, int64_t n,
 
 static int compute_stats(const smc_matrix* yc) {
   smc_matrix* y = const_cast<smc_matrix*>(yc);
+  std::lock_guard<std::mutex> lock(cache_mutex());
   if (y->range_valid && y->lgamma_valid) return SMC_OK;
   if (int rc = ensure_ctx()) return rc;
   Context& c = ctx();
@@ -198,6 +199,7 @@ int binom_stats(const smc_matrix* n, int n_scalar, const smc_matrix* trials,
   }
   const smc_matrix* partner = n ? trials : nullptr;
   const int partner_scalar = n ? trials_scalar : n_scalar;
+  std::lock_guard<std::mutex> lock(cache_mutex());
   if (owner && owner->binom_valid && owner->binom_self_version == owner->version
       && owner->binom_partner == (partner ? partner->data : nullptr)
       && (partner ? owner->binom_partner_version == partner->version

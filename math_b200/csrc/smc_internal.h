@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -64,6 +65,10 @@ struct Context {
 };
 
 Context& ctx();
+// Guards the caches that live ON a matrix (TMA descriptor, y statistics, binomial
+// pair statistics): several host threads -- chains -- share one read-only x / y,
+// and the first of them to need a cached item fills it in.
+std::mutex& cache_mutex();
 int ensure_ctx();  // lazily binds device 0 / creates the stream; returns smc_status
 int fail(int status, const char* fmt, ...);
 int ensure_partials(size_t bytes);

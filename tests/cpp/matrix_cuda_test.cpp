@@ -117,6 +117,21 @@ TEST(CudaMatrix, concurrent_chains_share_one_design_matrix) {
     EXPECT_NEAR(want[t], stan::math::bernoulli_logit_glm_lpmf(y, x, 0.1 * t, betas[t]),
                 1e-10 * std::fabs(want[t]));
   }
+  {
+    // first touch from all threads at once: the caches that live on the shared
+    // matrices (TMA descriptor of x, range of y) are filled in under a lock
+    matrix_cuda<double> x_cold(x);
+    matrix_cuda<int> y_cold(y);
+    std::vector<double> got(T, 0.0);
+    std::vector<std::thread> first;
+    for (int t = 0; t < T; ++t) {
+      first.emplace_back([&, t]() {
+        got[t] = stan::math::bernoulli_logit_glm_lpmf(y_cold, x_cold, 0.1 * t, betas[t]);
+      });
+    }
+    for (auto& th : first) th.join();
+    for (int t = 0; t < T; ++t) EXPECT_EQ(got[t], want[t]) << "cold thread " << t;
+  }
   std::vector<int> mismatches(T, 0);
   std::vector<std::thread> pool;
   for (int t = 0; t < T; ++t) {
