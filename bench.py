@@ -165,10 +165,20 @@ def cpu_baseline(rows_full, K, sample_rows, reps=3):
         sec = time.perf_counter() - t0
         how = "C oracle port, 1 thread"
     evals = (n / rows_full) / sec
-    return {"value": evals, "unit": UNIT, "cores": threads, "kind": kind,
-            "sample": f"{n} of {rows_full} rows x K={K} ({how}; best of {reps}; "
-                      f"{sec*1e3:.1f} ms per sample eval, scaled linearly in N)",
-            "sec_per_sample_eval": sec}
+    out = {"value": evals, "unit": UNIT, "cores": threads, "kind": kind,
+           "sample": f"{n} of {rows_full} rows x K={K} ({how}; best of {reps}; "
+                     f"{sec*1e3:.1f} ms per sample eval, scaled linearly in N)",
+           "sec_per_sample_eval": sec}
+    if kind == "reference" and threads > 1:
+        # the reference's plain single call on one core, same sample
+        try:
+            sec1, _, _ = po.ref_time("bernoulli", y, x, alpha, beta, reps=2,
+                                     single_call_in_mt_lib=True)
+            out["single_call"] = {"value": (n / rows_full) / sec1, "unit": UNIT,
+                                  "cores": 1, "sec_per_sample_eval": sec1}
+        except Exception as e:
+            out["single_call"] = {"value": None, "note": f"failed: {e}"}
+    return out
 
 
 def run_reference(args):

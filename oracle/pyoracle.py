@@ -291,9 +291,11 @@ FAMILY_ID = {"normal": 0, "bernoulli": 1, "poisson": 2, "neg_binomial": 3}
 
 
 def ref_time(family, y, x, alpha, beta, aux=1.0, reps=3, threads=1,
-             grainsize=None):
+             grainsize=None, single_call_in_mt_lib=False):
     """Seconds per lpdf+grad evaluation of the UNMODIFIED reference on the host
-    (beta/alpha(/aux) var, x data).  threads>1 -> reduce_sum over TBB."""
+    (beta/alpha(/aux) var, x data).  threads>1 -> reduce_sum over TBB.
+    single_call_in_mt_lib: take the plain single call from the STAN_THREADS build
+    (the two builds define the same symbols and must not share a process)."""
     x = _prep_x(x)
     N, K = x.shape
     fam = FAMILY_ID[family]
@@ -302,7 +304,8 @@ def ref_time(family, y, x, alpha, beta, aux=1.0, reps=3, threads=1,
     logp = np.zeros(1)
     d_beta = np.zeros(K)
     if threads <= 1:
-        t = ref_lib().ref_time_glm(fam, _L(N), _L(K), y.ctypes.data_as(C.c_void_p),
+        t = ref_lib(mt=single_call_in_mt_lib).ref_time_glm(
+            fam, _L(N), _L(K), y.ctypes.data_as(C.c_void_p),
                                    _d(x), float(alpha), _d(beta), float(aux),
                                    int(reps), _d(logp), _d(d_beta))
     else:
