@@ -8,7 +8,10 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libstanmath_cuda.so")
+# MATH_B200_LIB points at another build of the same library (A/B timing of two
+# kernel variants in one GPU session); it is never a different implementation.
+LIB_PATH = os.environ.get("MATH_B200_LIB") or os.path.join(HERE, "lib",
+                                                           "libstanmath_cuda.so")
 
 OK, ERR_INVALID_ARGUMENT, ERR_DOMAIN, ERR_CUDA, ERR_UNSUPPORTED = range(5)
 F64, I32 = 0, 1

@@ -46,6 +46,16 @@ __host__ __device__ inline int link_tab_doubles(int fam, int ncuts, int tab_n) {
   return 0;
 }
 
+// Families whose derivative part of the link is expensive enough (two exp and
+// two divisions per row for the ordered link) that evaluating it in every one of
+// the S warps of a row group costs more than a second exchange: only the tile's
+// lead warp runs the link and publishes d through shared memory + an mbarrier;
+// the other warps of the group pick it up (while the previous tile's lead is
+// still busy with its deferred log-density part).  The cheap links stay
+// redundant: no second exchange on their critical path.
+template <int FAM>
+constexpr bool kLeadOnlyLink = (FAM == kOrdered);
+
 // ------------------------------------------------------------------- the kernel
 // Raw per-row inputs, loaded one tile ahead so their DRAM latency overlaps the
 // current tile's arithmetic.
@@ -123,7 +133,9 @@ __global__ void __launch_bounds__(256, 1)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(p);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* part_bar = empty_bar + kStages;  // [G][2]: partial dot products published
-  double* hdr_s = reinterpret_cast<double*>(part_bar + 2 * G);  // [warps][8] row sums
+  uint64_t* d_bar = part_bar + 2 * G;        // [G][2]: d published by the lead warp
+  double* hdr_s = reinterpret_cast<double*>(d_bar + 2 * G);  // [warps][8] row sums
+  double* dv_s = hdr_s + (size_t)n_cons_warps * kHdr;  // [2][R] (lead-only links)
   __shared__ int s_last;
 
   const int tid = threadIdx.x;
@@ -160,6 +172,7 @@ __global__ void __launch_bounds__(256, 1)
       mbar_init(&empty_bar[st], n_cons_warps);
     }
     for (int j = 0; j < 2 * G; ++j) mbar_init(&part_bar[j], S);
+    for (int j = 0; j < 2 * G; ++j) mbar_init(&d_bar[j], 1);
     fence_barrier_init();
   }
   __syncthreads();
@@ -278,22 +291,33 @@ __global__ void __launch_bounds__(256, 1)
 
       // ---- stage C: every warp of the row group adds the S partials in the same
       // fixed tree, so all of them hold the identical theta
-      double xb;
-      if (S > 1) {
-        mbar_wait(&part_bar[g * 2 + par], (uint32_t)(it >> 1) & 1u);
-        double q[8];
-#pragma unroll
-        for (int ss = 0; ss < 8; ++ss)
-          q[ss] = ss < S ? partial_s[(par * S + ss) * R + rloc] : 0.0;
-        xb = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
-      } else {
-        xb = partial_s[par * R + rloc];
-      }
-
-      double d1 = 0, d2 = 0;
+      const bool shared_d = kLeadOnlyLink<FAM> && S > 1;
+      double d1 = 0, d2 = 0, d = 0;
       LinkStash<FAM> stash;
-      const double d
-          = link_d<FAM>(a, xb, in, valid, lead, row, racc, tab, d1, d2, stash);
+      if (!shared_d || lead) {
+        double xb;
+        if (S > 1) {
+          mbar_wait(&part_bar[g * 2 + par], (uint32_t)(it >> 1) & 1u);
+          double q[8];
+#pragma unroll
+          for (int ss = 0; ss < 8; ++ss)
+            q[ss] = ss < S ? partial_s[(par * S + ss) * R + rloc] : 0.0;
+          xb = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
+        } else {
+          xb = partial_s[par * R + rloc];
+        }
+        d = link_d<FAM>(a, xb, in, valid, lead, row, racc, tab, d1, d2, stash);
+      }
+      if (shared_d) {
+        if (lead) {
+          dv_s[par * R + rloc] = d;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&d_bar[g * 2 + par]);
+        } else {
+          mbar_wait(&d_bar[g * 2 + par], (uint32_t)(it >> 1) & 1u);
+          d = dv_s[par * R + rloc];
+        }
+      }
 
       if (need_beta) {
 #pragma unroll
@@ -590,7 +614,8 @@ int launch_glm_fused(const GlmCall& c) {
                        : 0)
                 + (size_t)2 * a.S * R * 8
                 + (size_t)4 * R * 8 + (size_t)2 * R * 4 + 8 + 2 * kStages * 8
-                + (size_t)2 * a.G * 8 + (size_t)a.S * a.G * kHdr * 8;
+                + (size_t)4 * a.G * 8 + (size_t)a.S * a.G * kHdr * 8
+                + (c.family == kOrdered && a.S > 1 ? (size_t)2 * R * 8 : 0);  // dv_s
   const size_t red_bytes = (size_t)a.G * a.pstride * 8;
   if (red_bytes > kStages * stage_bytes)
     return fail(SMC_ERR_UNSUPPORTED, "reduction scratch exceeds the tile ring");

@@ -43,6 +43,14 @@ def ints(N, lo, hi, seed=777):
 
 def main():
     which = sys.argv[1:] or ["1", "2", "3", "4", "5a", "5b"]
+    if len(which) > 1:
+        # one fresh process per config: within one process the timing of a config
+        # depends on what was allocated and freed before it (up to 15 % on the
+        # short kernels); fresh processes repeat to 0.1 %
+        import subprocess
+        for cfg in which:
+            subprocess.run([sys.executable, os.path.abspath(__file__), cfg], check=False)
+        return
     rng = np.random.default_rng(12345)
     mb.runtime.set_device(0)
     for cfg in which:
