@@ -429,8 +429,7 @@ __global__ void __launch_bounds__(kLinThreads, 1)
   // the moment the slot becomes free.
   const uint64_t pol = policy_evict_first();
   const uint64_t pol_keep = policy_evict_last();  // beta is re-read by every row block
-  auto issue = [&](int64_t q) {  // q-th stage load of this CTA
-    const int st = (int)(q % kLinStages);
+  auto issue = [&](int64_t q, int st) {  // q-th stage load of this CTA, into slot st
     const int64_t blk = blockIdx.x + (q / ksteps) * gridDim.x;
     const int ks = (int)(q % ksteps);
     double* dst = ring + (size_t)st * (stage_bytes / 8);
@@ -441,7 +440,7 @@ __global__ void __launch_bounds__(kLinThreads, 1)
     tma_load_2d(dst + 2 * xbox, &tmb, 0, ks * KS, &full_bar[st], pol_keep);
   };
   if (tid == 0)
-    for (int64_t q = 0; q < kLinStages && q < total; ++q) issue(q);
+    for (int64_t q = 0; q < kLinStages && q < total; ++q) issue(q, (int)q);
 
   double lp_acc = 0.0, bad_acc = 0.0;
   double dal[NT][2];
@@ -451,6 +450,8 @@ __global__ void __launch_bounds__(kLinThreads, 1)
   // this warp's 16 rows inside the stage: box (warp / 8), local row 16 (warp % 8)
   const int xoff = (warp >> 3) * xbox + 16 * (warp & 7) + 2 * grp;
   int64_t q = 0;
+  int st = 0;       // ring slot and mbarrier phase of stage load q, advanced by hand:
+  uint32_t ph = 0;  // q % stages and q / stages would be two integer divisions per step
   for (int64_t b = 0; b < my_blocks; ++b) {
     const int64_t r0 = (blockIdx.x + b * gridDim.x) * kLinRows + 16 * warp;
     double acc[2][NT][2];
@@ -460,8 +461,6 @@ __global__ void __launch_bounds__(kLinThreads, 1)
       for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
     for (int ks = 0; ks < ksteps; ++ks, ++q) {
-      const int st = (int)(q % kLinStages);
-      const uint32_t ph = (uint32_t)(q / kLinStages) & 1u;
       mbar_wait(&full_bar[st], ph);
       // A: x[r0 + 2 grp + {0, 1}][KS ks + 4 h + tig]      one double2
       // B: beta[KS ks + 4 h + tig][16 p + 2 grp + {0, 1}]  one double2 per pair
@@ -495,8 +494,12 @@ __global__ void __launch_bounds__(kLinThreads, 1)
         if (atomicAdd(&rel_cnt[st], 1) == kLinWarps - 1) {
           rel_cnt[st] = 0;
           __threadfence_block();
-          if (q + kLinStages < total) issue(q + kLinStages);
+          if (q + kLinStages < total) issue(q + kLinStages, st);
         }
+      }
+      if (++st == kLinStages) {
+        st = 0;
+        ph ^= 1u;
       }
     }
     if (r0 >= a.N) continue;
