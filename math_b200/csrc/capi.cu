@@ -61,6 +61,9 @@ int check_dx(const char* fn, unsigned flags, const smc_matrix* x,
   return SMC_OK;
 }
 
+}  // namespace
+
+namespace smc {
 // Runs the call with the packed result in pinned host memory; returns it.
 int run_sync(GlmCall& c, int n_out, const double** out) {
   if (int rc = ensure_out(sizeof(double) * (size_t)n_out)) return rc;
@@ -70,6 +73,9 @@ int run_sync(GlmCall& c, int n_out, const double** out) {
   *out = ctx().out_host;
   return SMC_OK;
 }
+}  // namespace smc
+
+namespace {
 
 int y_bounds(const char* fn, const smc_matrix* y, double y_scalar, int lo, int hi,
              bool check_hi) {

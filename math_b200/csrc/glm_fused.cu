@@ -452,18 +452,17 @@ __global__ void __launch_bounds__(256, 1)
     __threadfence();
     const int nb = gridDim.x;
     for (int j = tid; j < ps; j += blockDim.x) {
-      // fixed order over CTAs, four interleaved chains to shorten the
-      // dependency (still a fixed association)
-      double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+      // fixed order over CTAs in eight interleaved chains (still one fixed
+      // association), so that sixteen independent L2 loads are in flight per thread
+      double v8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       int b = 0;
-      for (; b + 3 < nb; b += 4) {
-        v0 += __ldcg(a.partials + (size_t)(b + 0) * ps + j);
-        v1 += __ldcg(a.partials + (size_t)(b + 1) * ps + j);
-        v2 += __ldcg(a.partials + (size_t)(b + 2) * ps + j);
-        v3 += __ldcg(a.partials + (size_t)(b + 3) * ps + j);
+#pragma unroll 2
+      for (; b + 7 < nb; b += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v8[u] += __ldcg(a.partials + (size_t)(b + u) * ps + j);
       }
-      for (; b < nb; ++b) v0 += __ldcg(a.partials + (size_t)b * ps + j);
-      double v = (v0 + v1) + (v2 + v3);
+      for (; b < nb; ++b) v8[0] += __ldcg(a.partials + (size_t)b * ps + j);
+      double v = ((v8[0] + v8[1]) + (v8[2] + v8[3])) + ((v8[4] + v8[5]) + (v8[6] + v8[7]));
       if (j == SMC_OUT_LOGP) v += a.c0;
       // packed output: header, d_beta[K], d_cuts[ncuts]
       if (j < kHdr)

@@ -57,15 +57,6 @@ int theta_shapes(const char* fn, const smc_matrix* theta, const smc_matrix* y,
   return SMC_OK;
 }
 
-int run_sync(GlmCall& c, int n_out, const double** out) {
-  if (int rc = ensure_out(sizeof(double) * (size_t)n_out)) return rc;
-  c.out = ctx().out_host;
-  if (int rc = launch_glm(c)) return rc;
-  SMC_CUDA(cudaStreamSynchronize(ctx().stream));
-  *out = ctx().out_host;
-  return SMC_OK;
-}
-
 int int_bounds(const char* fn, const smc_matrix* y, int y_scalar, int lo, int hi,
                bool check_hi) {
   int mn = y_scalar, mx = y_scalar;

@@ -114,6 +114,9 @@ struct GlmCall {
 
 // Launches the evaluation on ctx().stream; does not synchronise.
 int launch_glm(const GlmCall& c);
+// launch_glm with the packed result (n_out doubles) in the thread's pinned,
+// device-mapped buffer, then a stream synchronise; *out points at the result.
+int run_sync(GlmCall& c, int n_out, const double** out);
 // True when the single-pass TMA kernel can take this x.
 bool fused_supported(const smc_matrix* x);
 int launch_glm_fused(const GlmCall& c);
