@@ -21,6 +21,7 @@
 #include <stan/math/cuda/prim/ordered_logistic_glm_lpmf.hpp>
 #include <stan/math/cuda/prim/categorical_logit_glm_lpmf.hpp>
 #include <stan/math/cuda/rev/multiply.hpp>
+#include <stan/math/cuda/rev/indexing.hpp>
 #include <stan/math/cuda/prim/unfused_lpmf.hpp>
 #include <stan/math/cuda/prim/bernoulli_logit_glm_rng.hpp>
 

@@ -247,6 +247,16 @@ int smc_linear_predictor_adjoint(const smc_matrix* x, const smc_matrix* v,
 /* *sum = sum_i v[i] of an f64 device vector (fixed-order, deterministic). */
 int smc_vector_sum(const smc_matrix* v, double* sum);
 
+/* Hierarchical intercepts: out[i] = z[idx[i]] for a small host
+ * vector z (G doubles) and a resident i32 index vector (0-based, like
+ * opencl/kernel_generator/indexing.hpp), and the reverse sweep
+ * adj_z[g] += sum_{i : idx[i] == g} res_adj[i] (opencl/indexing_rev.hpp L24-60;
+ * deterministic here, fixed-order instead of atomics).  adj_z is ACCUMULATED
+ * into.  An index outside [0, G) is SMC_ERR_DOMAIN. */
+int smc_indexing(const double* z, int64_t G, const smc_matrix* idx, smc_matrix* out);
+int smc_indexing_rev(const smc_matrix* idx, const smc_matrix* res_adj, int64_t G,
+                     double* adj_z);
+
 /* Un-fused densities on a device N-vector parameter.  `n`/`y`: N x 1 i32 device
  * vector or NULL -> the broadcast scalar.  SMC_VAR_ALPHA in `flags` marks the
  * vector parameter (theta / alpha / eta / lambda) as an autodiff variable: its

@@ -83,6 +83,8 @@ SIGNATURES = {
     "smc_linear_predictor": (_I, [_P, _DP, _P, _D, _P]),
     "smc_linear_predictor_adjoint": (_I, [_P, _P, _DP, _DP]),
     "smc_vector_sum": (_I, [_P, _DP]),
+    "smc_indexing": (_I, [_DP, _I64, _P, _P]),
+    "smc_indexing_rev": (_I, [_P, _P, _I64, _DP]),
     "smc_bernoulli_logit_lpmf": (_I, [_P, _I, _P, _U, _DP, _P]),
     "smc_poisson_log_lpmf": (_I, [_P, _I, _P, _U, _DP, _P]),
     "smc_neg_binomial_2_log_lpmf": (_I, [_P, _I, _P, _P, _D, _U, _DP, _P, _DP, _P]),

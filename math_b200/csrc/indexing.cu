@@ -1,0 +1,168 @@
+// Device-side multi-indexing of a small host vector by a resident index vector,
+// and its reverse sweep: the hierarchical-intercept step in front of the GLMs
+// (alpha_i = z[group_i]).  Without it the N-vector intercept of a
+// hierarchical model crosses PCIe on every evaluation (N * 8 bytes up, N * 8 bytes
+// of partials down); with it G doubles go up and G doubles come down.
+//
+// Stands where opencl/kernel_generator/indexing.hpp (`indexing(mat, idx)`) and
+// opencl/indexing_rev.hpp L24-60 stand.  The reference's reverse kernels add
+// with atomics; this one is deterministic: every warp owns a contiguous row
+// range and a private accumulator per group in shared memory, collisions inside
+// a 32-row step are resolved in lane order, warps / CTAs are combined in index
+// order.
+#include <atomic>
+#include <cstring>
+#include <vector>
+
+#include "smc_internal.h"
+
+using namespace smc;
+
+namespace {
+
+constexpr int kIdxThreads = 256;
+constexpr int kIdxWarps = kIdxThreads / 32;
+constexpr int64_t kMaxGroupsFast = 2048;  // 8 warps x 2048 doubles = 128 KB of accumulators
+
+__global__ void indexing_kernel(const double* __restrict__ z, const int* __restrict__ idx,
+                                int64_t n, double* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = z[idx[i]];
+}
+
+__global__ void __launch_bounds__(kIdxThreads)
+    indexing_rev_kernel(const int* __restrict__ idx, const double* __restrict__ v,
+                        int64_t n, int G, int64_t rows_per_warp,
+                        double* __restrict__ partials) {
+  extern __shared__ double idx_smem[];
+  double* acc = idx_smem;                                  // [warps][G]
+  double* stage_v = acc + (size_t)kIdxWarps * G;           // [warps][32]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = threadIdx.x; j < kIdxWarps * G; j += kIdxThreads) acc[j] = 0.0;
+  __syncthreads();
+  double* my_acc = acc + (size_t)warp * G;
+  double* my_stage = stage_v + warp * 32;
+  const int64_t w = (int64_t)blockIdx.x * kIdxWarps + warp;
+  const int64_t lo = w * rows_per_warp;
+  int64_t hi = lo + rows_per_warp;
+  if (hi > n) hi = n;
+  for (int64_t r = lo; r < hi; r += 32) {
+    const int64_t i = r + lane;
+    const bool live = i < hi;
+    const int g = live ? idx[i] : -1;
+    my_stage[lane] = live ? v[i] : 0.0;
+    __syncwarp();
+    const unsigned peers = __match_any_sync(0xffffffffu, g);
+    if (live && lane == __ffs(peers) - 1) {
+      // the lowest lane of each group adds its peers' values in lane order
+      double s = 0.0;
+      for (unsigned m = peers; m; m &= m - 1) s += my_stage[__ffs(m) - 1];
+      my_acc[g] += s;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += kIdxThreads) {
+    double s = 0.0;
+    for (int ww = 0; ww < kIdxWarps; ++ww) s += acc[(size_t)ww * G + g];  // fixed order
+    partials[(size_t)blockIdx.x * G + g] = s;
+  }
+}
+
+__global__ void indexing_rev_final_kernel(const double* __restrict__ partials, int nblocks,
+                                          int G, double* __restrict__ out) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * G + g];  // fixed order
+  out[g] = s;
+}
+
+int check_index(const char* fn, const smc_matrix* idx, int64_t G) {
+  if (!idx || idx->dtype != SMC_I32 || (idx->cols != 1 && idx->rows != 1 && idx->rows * idx->cols))
+    return fail(SMC_ERR_INVALID_ARGUMENT, "%s: idx must be an i32 device vector", fn);
+  if (idx->rows * idx->cols == 0) return SMC_OK;
+  int lo, hi;
+  if (int rc = y_range(idx, &lo, &hi)) return rc;  // idx is data: cached
+  if (lo < 0 || hi >= G)
+    return fail(SMC_ERR_DOMAIN, "%s: index out of range [%d, %d] for %lld elements", fn,
+                lo, hi, (long long)G);
+  return SMC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int smc_indexing(const double* z, int64_t G, const smc_matrix* idx, smc_matrix* out) {
+  static const char* fn = "indexing";
+  if (int rc = ensure_ctx()) return rc;
+  if (int rc = check_index(fn, idx, G)) return rc;
+  const int64_t n = idx->rows * idx->cols;
+  if (!out || out->dtype != SMC_F64 || out->rows * out->cols != n)
+    return fail(SMC_ERR_INVALID_ARGUMENT, "%s: out must hold size(idx) doubles", fn);
+  if (n == 0) return SMC_OK;
+  if (!z || G <= 0) return fail(SMC_ERR_INVALID_ARGUMENT, "%s: empty source vector", fn);
+  Context& c = ctx();
+  if (int rc = ensure_params(sizeof(double) * (size_t)G)) return rc;
+  SMC_CUDA(cudaMemcpyAsync(c.params_dev, z, sizeof(double) * (size_t)G,
+                           cudaMemcpyHostToDevice, c.stream));
+  int grid = (int)((n + kIdxThreads - 1) / kIdxThreads);
+  if (grid > c.sm_count * 16) grid = c.sm_count * 16;
+  out->version++;
+  indexing_kernel<<<grid, kIdxThreads, 0, c.stream>>>(
+      c.params_dev, static_cast<const int*>(idx->data), n, static_cast<double*>(out->data));
+  SMC_CUDA(cudaGetLastError());
+  c.launches += 1;
+  return SMC_OK;
+}
+
+int smc_indexing_rev(const smc_matrix* idx, const smc_matrix* res_adj, int64_t G,
+                     double* adj_z) {
+  static const char* fn = "indexing_rev";
+  if (int rc = ensure_ctx()) return rc;
+  if (int rc = check_index(fn, idx, G)) return rc;
+  const int64_t n = idx->rows * idx->cols;
+  if (!res_adj || res_adj->dtype != SMC_F64 || res_adj->rows * res_adj->cols != n)
+    return fail(SMC_ERR_INVALID_ARGUMENT, "%s: res_adj must hold size(idx) doubles", fn);
+  if (n == 0 || G <= 0) return SMC_OK;
+  if (!adj_z) return fail(SMC_ERR_INVALID_ARGUMENT, "%s: NULL adj_z", fn);
+  Context& c = ctx();
+  if (G > kMaxGroupsFast) {
+    // more groups than the per-warp shared-memory accumulators hold: sequential
+    // host accumulation in row order (deterministic; N * 12 bytes over PCIe)
+    std::vector<double> v((size_t)n);
+    std::vector<int> id((size_t)n);
+    if (int rc = smc_matrix_download(res_adj, v.data(), res_adj->rows)) return rc;
+    if (int rc = smc_matrix_download(idx, id.data(), idx->rows)) return rc;
+    for (int64_t i = 0; i < n; ++i) adj_z[id[(size_t)i]] += v[(size_t)i];
+    return SMC_OK;
+  }
+  int grid = c.sm_count;
+  int64_t rows_per_warp = (n + (int64_t)grid * kIdxWarps - 1) / ((int64_t)grid * kIdxWarps);
+  rows_per_warp = (rows_per_warp + 31) / 32 * 32;
+  grid = (int)((n + rows_per_warp * kIdxWarps - 1) / (rows_per_warp * kIdxWarps));
+  const size_t smem = sizeof(double) * ((size_t)kIdxWarps * G + kIdxWarps * 32);
+  static std::atomic<size_t> attr[16];
+  if (attr[c.device & 15] < smem) {
+    SMC_CUDA(cudaFuncSetAttribute(indexing_rev_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr[c.device & 15] = smem;
+  }
+  if (int rc = ensure_partials(sizeof(double) * (size_t)grid * G)) return rc;
+  if (int rc = ensure_out(sizeof(double) * (size_t)G)) return rc;
+  indexing_rev_kernel<<<grid, kIdxThreads, smem, c.stream>>>(
+      static_cast<const int*>(idx->data), static_cast<const double*>(res_adj->data), n,
+      (int)G, rows_per_warp, c.partials);
+  SMC_CUDA(cudaGetLastError());
+  indexing_rev_final_kernel<<<(int)((G + 127) / 128), 128, 0, c.stream>>>(c.partials, grid,
+                                                                          (int)G, c.out_host);
+  SMC_CUDA(cudaGetLastError());
+  c.launches += 2;
+  SMC_CUDA(cudaStreamSynchronize(c.stream));
+  for (int64_t g = 0; g < G; ++g) adj_z[g] += c.out_host[g];
+  return SMC_OK;
+}
+
+}  // extern "C"

@@ -44,6 +44,22 @@ def multiply_adjoint(x, v):
     return g, s.value
 
 
+def indexing(z, idx):
+    """out[i] = z[idx[i]] (0-based) on the device: opencl/kernel_generator/indexing.hpp."""
+    zz = np.ascontiguousarray(np.atleast_1d(np.asarray(z, dtype=np.float64)).ravel())
+    out = MatrixCuda(idx.size(), 1, np.float64)
+    check(lib().smc_indexing(_dp(zz), zz.size, idx.handle, out.handle))
+    return out
+
+
+def indexing_rev(idx, res_adj, n_groups):
+    """adj_z[g] = sum over rows with idx == g of res_adj (deterministic):
+    opencl/indexing_rev.hpp L24-60."""
+    g = np.zeros(int(n_groups))
+    check(lib().smc_indexing_rev(idx.handle, res_adj.handle, int(n_groups), _dp(g)))
+    return g
+
+
 def vector_sum(v):
     s = C.c_double()
     check(lib().smc_vector_sum(v.handle, C.byref(s)))

@@ -297,3 +297,64 @@ TEST(CudaUnfused, bernoulli_logit_glm_rng_draws_what_prim_draws) {
                  std::domain_error);
   }
 }
+
+TEST(CudaUnfused, hierarchical_intercept_through_device_indexing) {
+  // y ~ poisson_log_glm(x, z[group], beta): the N-vector intercept is gathered on
+  // the device from G group effects and its partials are summed back per group
+  // there; oracle: the same model with a host Matrix<var> alpha
+  int N = 6007, K = 23, G = 37;
+  srand(9);
+  MatrixXd x = MatrixXd::Random(N, K);
+  VectorXd beta = VectorXd::Random(K) / std::sqrt(K), z = VectorXd::Random(G);
+  vector<int> y(N), group(N);
+  for (int i = 0; i < N; ++i) {
+    y[i] = (i * 5) % 7;
+    group[i] = (i * 31 + (i / 97)) % G;
+  }
+  matrix_cuda<double> x_d(x);
+  matrix_cuda<int> y_d(y), group_d(group);
+
+  // data only
+  VectorXd alpha_host(N);
+  for (int i = 0; i < N; ++i) alpha_host[i] = z[group[i]];
+  expect_close("value (data)",
+               stan::math::poisson_log_glm_lpmf(y_d, x_d, stan::math::indexing(z, group_d), beta),
+               stan::math::poisson_log_glm_lpmf(y, x, alpha_host, beta), kRelLogp, 0);
+
+  Matrix<var, Dynamic, 1> z1 = z, z2 = z, b1 = beta, b2 = beta;
+  var lp_dev = stan::math::poisson_log_glm_lpmf(y_d, x_d, stan::math::indexing(z1, group_d), b1);
+  Matrix<var, Dynamic, 1> alpha2(N);
+  for (int i = 0; i < N; ++i) alpha2[i] = z2[group[i]];
+  var lp_cpu = stan::math::poisson_log_glm_lpmf(y, x, alpha2, b2);
+  (lp_dev + lp_cpu).grad();
+  expect_close("value", lp_dev.val(), lp_cpu.val(), kRelLogp, 0);
+  const double zs = z2.adj().cwiseAbs().maxCoeff(), bs = b2.adj().cwiseAbs().maxCoeff();
+  for (int g = 0; g < G; ++g) expect_close("d_z", z1[g].adj(), z2[g].adj(), kRelGrad, zs);
+  for (int k = 0; k < K; ++k) expect_close("d_beta", b1[k].adj(), b2[k].adj(), kRelGrad, bs);
+  stan::math::recover_memory();
+
+  // more groups than the shared-memory accumulators hold (host route), and a bad index
+  {
+    int G2 = 5000;
+    VectorXd zz = VectorXd::Random(G2);
+    vector<int> grp(N);
+    for (int i = 0; i < N; ++i) grp[i] = (i * 7919) % G2;
+    matrix_cuda<int> grp_d(grp);
+    stan::math::var_value<VectorXd> zv1(zz), zv2(zz);
+    var a = stan::math::bernoulli_logit_lpmf(
+        matrix_cuda<int>(vector<int>(N, 1)), stan::math::indexing(zv1, grp_d));
+    Matrix<var, Dynamic, 1> th(N);
+    for (int i = 0; i < N; ++i) th[i] = zv2.coeff(grp[i]);
+    var b = stan::math::bernoulli_logit_lpmf(vector<int>(N, 1), th);
+    (a + b).grad();
+    expect_close("value (many groups)", a.val(), b.val(), kRelLogp, 0);
+    const double s = zv2.adj().cwiseAbs().maxCoeff();
+    for (int g = 0; g < G2; ++g)
+      expect_close("d_z (many groups)", zv1.adj()[g], zv2.adj()[g], kRelGrad, s);
+    stan::math::recover_memory();
+  }
+  vector<int> bad = group;
+  bad[100] = G;
+  matrix_cuda<int> bad_d(bad);
+  EXPECT_THROW(stan::math::indexing(z, bad_d), std::out_of_range);
+}

@@ -104,6 +104,27 @@ def test_normal_lpdf_matches_oracle(gpu, N):
                 scale=np.abs(o["d_alpha"]).sum())
 
 
+@pytest.mark.parametrize("N,G", [(1, 1), (1000, 7), (50021, 300), (200003, 2048), (30011, 5000)])
+def test_indexing_and_reverse(gpu, N, G):
+    mb = gpu
+    rng = np.random.default_rng(N + G)
+    z = rng.standard_normal(G)
+    idx = rng.integers(0, G, N).astype(np.int32)
+    idx_d = mb.to_matrix_cuda(idx)
+    out = mb.from_matrix_cuda(mb.lpmf.indexing(z, idx_d)).ravel()
+    assert np.array_equal(out, z[idx])
+    v = rng.standard_normal(N)
+    v_d = mb.to_matrix_cuda(v)
+    g1 = mb.lpmf.indexing_rev(idx_d, v_d, G)
+    g2 = mb.lpmf.indexing_rev(idx_d, v_d, G)
+    assert np.array_equal(g1, g2)  # deterministic
+    want = np.zeros(G)
+    np.add.at(want, idx, v)
+    assert_grad(g1, want, "indexing_rev", scale=np.abs(v).sum() / max(G, 1))
+    with pytest.raises(mb.DomainError):
+        mb.lpmf.indexing(z, mb.to_matrix_cuda(np.array([0, G], dtype=np.int32)))
+
+
 def test_unfused_pipeline_equals_fused_glm(gpu):
     """multiply -> density -> multiply_adjoint gives the fused GLM's value and
     gradient (three sweeps instead of one: what the fusion buys is in DESIGN.md)."""
