@@ -240,6 +240,24 @@ def workload_config(args, extra=None):
     return c
 
 
+def cpp_drop_in(rows, cols, steps, warmup):
+    """The same evaluation through the C++ drop-in a Stan model calls
+    (stan::math::bernoulli_logit_glm_lpmf on matrix_cuda with var alpha / beta,
+    grad(), recover_memory()): tests/cpp/_build/glm_bench, built against the
+    reference's own headers where /root/reference exists."""
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "glm_bench")
+    if not os.path.exists(exe):
+        return {"value": None, "note": "tests/cpp/_build/glm_bench not built"}
+    try:
+        p = subprocess.run([exe, str(rows), str(cols), str(steps), str(warmup)],
+                           capture_output=True, text=True, timeout=600)
+        r = json.loads(p.stdout.strip().splitlines()[-1])
+        return {"value": r["evals_per_s"], "unit": UNIT, "ms_per_eval": r["ms_per_eval"],
+                "call": r["call"], "logp_per_row": r["logp_per_row"]}
+    except Exception as e:
+        return {"value": None, "note": f"failed: {e}"}
+
+
 # ----------------------------------------------------------------------- ours
 def run_ours(args):
     import torch
@@ -359,6 +377,12 @@ def run_ours(args):
             "check": {"logp_per_row": float(out_host[0]) / (N * world),
                       "nonfinite_rows": float(out_host[3])},
         }
+        if world == 1:
+            # frees this process's 20 GB first: the C++ binary allocates its own x
+            del glm, x, y
+            mb.runtime.synchronize()
+            _lib.lib().smc_trim_cache()
+            line["e2e"]["cpp_drop_in"] = cpp_drop_in(N, K, args.steps, args.warmup)
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(N, K, args.cpu_rows)
