@@ -556,12 +556,35 @@ static int launch_t(const CUtensorMap& tmap, const CUtensorMap& tmap_dx,
   }
 }
 
+// Dynamic shared memory of one CTA for a tile shape (mirrors the kernel's carve-up).
+static size_t fused_smem_bytes(const GlmCall& c, const FusedArgs& a, bool dx) {
+  const int R = 32 * a.G, CW = 32 * a.S;
+  const int kStages = dx ? kStagesDx : kStagesX;
+  const size_t stage_bytes = (size_t)R * CW * 8;
+  return kStages * stage_bytes + (dx ? (size_t)a.S * a.G * kSlabBytes : 0)
+         + (size_t)CW * 8
+         + (size_t)((a.ncuts + 1) & ~1) * 8
+         + (size_t)link_tab_doubles(c.family, a.ncuts, a.tab_n) * 8
+         + (c.family == kOrdered && a.ncuts <= kFastCuts ? (size_t)a.G * a.ncuts * 32 * 8
+                                                         : 0)
+         + (size_t)2 * a.S * R * 8
+         + (size_t)4 * R * 8 + (size_t)2 * R * 4 + 8 + 2 * kStages * 8
+         + (size_t)4 * a.G * 8 + (size_t)a.S * a.G * kHdr * 8
+         + (c.family == kOrdered && a.S > 1 ? (size_t)2 * R * 8 : 0);  // dv_s
+}
+
+constexpr size_t kMaxDynamicSmem = 227 * 1024;  // opt-in limit per CTA on sm_100
+
 int launch_glm_fused(const GlmCall& c) {
   Context& cx = ctx();
   const smc_matrix* x = c.x;
   FusedArgs a;
   if (int rc = prepare_args(c, &a)) return rc;
+  const bool dx = (a.flags & SMC_VAR_X) && c.d_x;
   tile_shape(a.K, &a.S, &a.G);
+  // fewer row groups if the per-group tables push the CTA over the shared-memory
+  // limit (many cut points, or the widest tiles with every optional buffer)
+  while (a.G > 1 && fused_smem_bytes(c, a, dx) > kMaxDynamicSmem) a.G /= 2;
   const int R = 32 * a.G, CW = 32 * a.S;
   a.ntiles = (int)((a.N + R - 1) / R);
   if (a.ncuts > kCutsPerThread * 32 * a.S || a.ncuts > kMaxCuts)
@@ -596,7 +619,6 @@ int launch_glm_fused(const GlmCall& c) {
 
   CUtensorMap tmap, tmap_dx;
   if (int rc = get_tmap(x, R, CW, &tmap)) return rc;
-  const bool dx = (a.flags & SMC_VAR_X) && c.d_x;
   tmap_dx = tmap;  // unused unless d_x is written
   if (dx) {
     if (int rc = get_tmap(c.d_x, 32, 32, &tmap_dx)) return rc;
@@ -604,17 +626,10 @@ int launch_glm_fused(const GlmCall& c) {
 
   const int kStages = dx ? kStagesDx : kStagesX;
   const size_t stage_bytes = (size_t)R * CW * 8;
-  size_t smem = kStages * stage_bytes + (dx ? (size_t)a.S * a.G * kSlabBytes : 0)
-                + (size_t)CW * 8
-                + (size_t)((a.ncuts + 1) & ~1) * 8
-                + (size_t)link_tab_doubles(c.family, a.ncuts, a.tab_n) * 8
-                + (c.family == kOrdered && a.ncuts <= kFastCuts
-                       ? (size_t)a.G * a.ncuts * 32 * 8
-                       : 0)
-                + (size_t)2 * a.S * R * 8
-                + (size_t)4 * R * 8 + (size_t)2 * R * 4 + 8 + 2 * kStages * 8
-                + (size_t)4 * a.G * 8 + (size_t)a.S * a.G * kHdr * 8
-                + (c.family == kOrdered && a.S > 1 ? (size_t)2 * R * 8 : 0);  // dv_s
+  const size_t smem = fused_smem_bytes(c, a, dx);
+  if (smem > kMaxDynamicSmem)
+    return fail(SMC_ERR_UNSUPPORTED, "fused kernel: %zu bytes of shared memory needed",
+                smem);
   const size_t red_bytes = (size_t)a.G * a.pstride * 8;
   if (red_bytes > kStages * stage_bytes)
     return fail(SMC_ERR_UNSUPPORTED, "reduction scratch exceeds the tile ring");
