@@ -472,7 +472,14 @@ __global__ void __launch_bounds__(256, 1)
       } else if (j - kHdr - CW < a.ncuts)
         a.out[kHdr + a.K + (j - kHdr - CW)] = v;
     }
-    if (tid == 0) *a.counter = 0;  // ready for the next launch on this stream
+    __syncthreads();  // (uniform: s_last is shared) every store to out is issued
+    if (tid == 0) {
+      *a.counter = 0;  // ready for the next launch on this stream
+      if (a.done_flag) {
+        __threadfence_system();  // the packed result is visible to the host first
+        *reinterpret_cast<volatile unsigned long long*>(a.done_flag) = a.done_val;
+      }
+    }
   }
 }
 
@@ -616,6 +623,9 @@ int launch_glm_fused(const GlmCall& c) {
   a.partials = cx.partials;
   a.counter = cx.counter;
   a.out = c.out;
+  a.done_flag = c.done_flag;
+  a.done_val = c.done_val;
+  cx.flag_armed = c.done_flag != nullptr;
 
   CUtensorMap tmap, tmap_dx;
   if (int rc = get_tmap(x, R, CW, &tmap)) return rc;

@@ -36,6 +36,11 @@ struct FusedArgs {
   int pstride;
   unsigned int* counter;
   double* out;
+  // host-visible completion flag (pinned, mapped): the last CTA stores done_val
+  // after the packed result, so a synchronous caller can poll instead of paying
+  // the wake-up latency of a stream synchronise; NULL = not used
+  unsigned long long* done_flag;
+  unsigned long long done_val;
   double c0;
   int tab_n;  // neg-binomial, scalar phi: rows with y < tab_n read lgamma / digamma
               // of (y + phi) from a per-CTA table instead of evaluating them

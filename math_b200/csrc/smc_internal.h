@@ -53,6 +53,8 @@ struct Context {
   double* scratch = nullptr;   // generic device scratch (N-vectors for fallbacks)
   size_t scratch_bytes = 0;
   int64_t launches = 0;
+  unsigned long long sync_seq = 0;  // value the next polled completion flag takes
+  bool flag_armed = false;          // the last launch will store its completion flag
   // Recycled device blocks, keyed by exact size.  An HMC run allocates the same
   // arena buffers (N-vector partials, the N x K d_x of an autodiff x) on every
   // evaluation: a freed block goes here and the next create of that size takes
@@ -106,6 +108,8 @@ struct GlmCall {
   // of a broadcast scalar y follow prim/prob/<family>_lpmf.hpp, not the GLM
   bool unfused = false;
   double* out = nullptr;  // packed result, device-accessible
+  unsigned long long* done_flag = nullptr;  // see FusedArgs::done_flag
+  unsigned long long done_val = 0;
   smc_matrix* d_alpha_vec = nullptr;
   smc_matrix* d_aux_vec = nullptr;
   smc_matrix* d_y_vec = nullptr;
