@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(256, 1)
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&tmap_dx, tile * R + 32 * g, 32 * s, xo, pol_dx);
+          tma_store_2d_plain(&tmap_dx, tile * R + 32 * g, 32 * s, xo);
           bulk_commit();
         }
       }

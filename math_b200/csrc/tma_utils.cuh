@@ -62,6 +62,14 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int
       "r"(c0), "r"(c1), "r"(smem_u32(src)), "l"(policy)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d_plain(const CUtensorMap* map, int c0, int c1,
+                                                   const void* src) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+          reinterpret_cast<uint64_t>(map)),
+      "r"(c0), "r"(c1), "r"(smem_u32(src))
+      : "memory");
+}
 __device__ __forceinline__ void bulk_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
