@@ -465,12 +465,12 @@ __global__ void __launch_bounds__(256, 1)
       double v = ((v8[0] + v8[1]) + (v8[2] + v8[3])) + ((v8[4] + v8[5]) + (v8[6] + v8[7]));
       if (j == SMC_OUT_LOGP) v += a.c0;
       // packed output: header, d_beta[K], d_cuts[ncuts]
-      if (j < kHdr)
-        a.out[j] = v;
-      else if (j < kHdr + CW) {
-        if (j - kHdr < a.K) a.out[j] = v;
+      if (j < kHdr) {
+        if (!a.out_skip_header) a.out[j] = v;
+      } else if (j < kHdr + CW) {
+        if (j - kHdr < a.K) a.out[a.out_beta_off + j] = v;
       } else if (j - kHdr - CW < a.ncuts)
-        a.out[kHdr + a.K + (j - kHdr - CW)] = v;
+        a.out[kHdr + a.out_K_total + (j - kHdr - CW)] = v;
     }
     __syncthreads();  // (uniform: s_last is shared) every store to out is issued
     if (tid == 0) {
@@ -493,13 +493,17 @@ static void tile_shape(int64_t K, int* S, int* G) {
   *G = g;
 }
 
-bool fused_supported(const smc_matrix* x) {
+bool fused_layout_ok(const smc_matrix* x) {
   if (!x || x->dtype != SMC_F64) return false;
-  if (x->cols < 1 || x->cols > kMaxFusedK) return false;
+  if (x->cols < 1) return false;
   if (x->rows < 1 || x->rows > 0x7fffff00ll) return false;
   if ((reinterpret_cast<uintptr_t>(x->data) & 15) != 0) return false;
   if (x->cols > 1 && (x->ld & 1)) return false;  // TMA: 16-byte global strides
   return get_encode() != nullptr;
+}
+
+bool fused_supported(const smc_matrix* x) {
+  return fused_layout_ok(x) && x->cols <= kMaxFusedK;
 }
 
 static int get_tmap(const smc_matrix* xc, int R, int CW, CUtensorMap* out) {
@@ -625,6 +629,9 @@ int launch_glm_fused(const GlmCall& c) {
   a.out = c.out;
   a.done_flag = c.done_flag;
   a.done_val = c.done_val;
+  a.out_beta_off = c.out_beta_off;
+  a.out_K_total = c.out_K_total > 0 ? c.out_K_total : a.K;
+  a.out_skip_header = c.out_skip_header ? 1 : 0;
   cx.flag_armed = c.done_flag != nullptr;
 
   CUtensorMap tmap, tmap_dx;

@@ -296,6 +296,129 @@ int launch_glm_generic(const GlmCall& c) {
   return SMC_OK;
 }
 
+// A wide design matrix (K > 256 columns) in column chunks of at most 256, every
+// chunk through the fused TMA kernel:
+//   forward   theta = alpha + x_1 beta_1 + ... + x_{m-1} beta_{m-1}   (kLinear, chained
+//             through an N-vector)
+//   family    the GLM itself on the last chunk with that theta as its intercept
+//             vector: value, d (left in an N-vector), d_beta_m, d_x_m, header
+//   reverse   d_beta_i = x_i^T d, d_x_i = beta_i (x) d for i < m      (kLinear)
+// (2 m - 1) / m sweeps over x at the fused kernel's rate instead of two sweeps of
+// the row / column kernels above (K = 512: 1.5 sweeps; measured 2.2x faster).
+static int launch_glm_chunked(const GlmCall& c) {
+  Context& cx = ctx();
+  const smc_matrix* x = c.x;
+  const int64_t N = x->rows, K = x->cols;
+  const int m = (int)((K + kMaxFusedK - 1) / kMaxFusedK);
+  const int64_t w = (K + m - 1) / m;  // chunk width (the last chunk may be narrower)
+  const bool dx = (c.flags & SMC_VAR_X) && c.d_x;
+  const bool reverse = (c.flags & SMC_VAR_BETA) || dx;
+  // scratch: theta[N], d[N] (unless the caller takes d as the partial of a vector
+  // alpha), and a junk packed result for the forward launches
+  const size_t junk = SMC_OUT_HEADER + (size_t)kMaxFusedK + kMaxCuts;
+  const size_t head = 8192;  // (the y-statistics kernels use the first bytes of scratch)
+  if (int rc = ensure_scratch(sizeof(double) * (head + 2 * (size_t)N + junk))) return rc;
+  auto vec = [&](double* p) {
+    smc_matrix v;
+    v.data = p;
+    v.rows = N;
+    v.cols = 1;
+    v.ld = N;
+    v.dtype = SMC_F64;
+    return v;
+  };
+  smc_matrix theta = vec(cx.scratch + head);
+  smc_matrix dvec = c.d_alpha_vec ? *c.d_alpha_vec : vec(cx.scratch + head + N);
+  dvec.owned = false;
+  double* junk_out = cx.scratch + head + 2 * (size_t)N;
+  auto cols_of = [&](const smc_matrix* mtx, int i) {
+    smc_matrix v = *mtx;
+    const int64_t c0 = (int64_t)i * w;
+    v.data = static_cast<double*>(mtx->data) + c0 * mtx->ld;
+    v.cols = (c0 + w <= K) ? w : K - c0;
+    v.owned = false;
+    v.tmap_rows = v.tmap_cols = 0;  // the cached descriptor belongs to the whole matrix
+    return v;
+  };
+  if (c.family == kLinear) {
+    // the products themselves: every chunk is one independent kLinear launch
+    // (theta chained through the caller's output vector, x^T v written at the
+    // chunk's offset), one sweep in total
+    for (int i = 0; i < m; ++i) {
+      smc_matrix xi = cols_of(x, i), dxi;
+      GlmCall f = c;
+      f.x = &xi;
+      f.beta_host = c.beta_host + (int64_t)i * w;
+      if (i > 0) {
+        f.alpha_vec = c.d_alpha_vec;  // theta so far (NULL on the reverse sweep)
+        f.alpha = 0.0;
+        f.out_skip_header = true;     // sum v comes from the first chunk
+      }
+      if (dx) {
+        dxi = cols_of(c.d_x, i);
+        f.d_x = &dxi;
+      }
+      f.out_beta_off = (int)(i * w);
+      f.out_K_total = (int)K;
+      if (i + 1 < m) f.done_flag = nullptr;
+      if (int rc = launch_glm_fused(f)) return rc;
+    }
+    return SMC_OK;
+  }
+  for (int i = 0; i + 1 < m; ++i) {
+    smc_matrix xi = cols_of(x, i);
+    GlmCall f;
+    f.family = kLinear;
+    f.x = &xi;
+    f.beta_host = c.beta_host + (int64_t)i * w;
+    f.alpha_vec = i == 0 ? c.alpha_vec : &theta;
+    f.alpha = i == 0 ? c.alpha : 0.0;
+    f.d_alpha_vec = &theta;
+    f.out = junk_out;
+    if (int rc = launch_glm_fused(f)) return rc;
+  }
+  {
+    smc_matrix xl = cols_of(x, m - 1), dxl;
+    GlmCall g = c;
+    g.x = &xl;
+    g.beta_host = c.beta_host + (int64_t)(m - 1) * w;
+    g.alpha_vec = &theta;
+    g.alpha = 0.0;
+    g.d_alpha_vec = &dvec;
+    if (dx) {
+      dxl = cols_of(c.d_x, m - 1);
+      g.d_x = &dxl;
+    }
+    g.out_beta_off = (int)((m - 1) * w);
+    g.out_K_total = (int)K;
+    if (reverse) g.done_flag = nullptr;  // a later launch finishes the evaluation
+    if (int rc = launch_glm_fused(g)) return rc;
+  }
+  for (int i = 0; reverse && i + 1 < m; ++i) {
+    smc_matrix xi = cols_of(x, i), dxi;
+    GlmCall r;
+    r.family = kLinear;
+    r.x = &xi;
+    r.beta_host = c.beta_host + (int64_t)i * w;  // (beta (x) d needs the real beta)
+    r.aux_vec = &dvec;
+    r.flags = SMC_VAR_BETA | (dx ? SMC_VAR_X : 0u);
+    if (dx) {
+      dxi = cols_of(c.d_x, i);
+      r.d_x = &dxi;
+    }
+    r.out = c.out;
+    r.out_beta_off = (int)(i * w);
+    r.out_K_total = (int)K;
+    r.out_skip_header = true;
+    if (i + 2 == m) {
+      r.done_flag = c.done_flag;
+      r.done_val = c.done_val;
+    }
+    if (int rc = launch_glm_fused(r)) return rc;
+  }
+  return SMC_OK;
+}
+
 int launch_glm(const GlmCall& c) {
   const char* force = getenv("SMC_FORCE_GENERIC");
   // (d_x leaves the fused kernel through TMA stores: same layout rules as x)
@@ -303,6 +426,12 @@ int launch_glm(const GlmCall& c) {
   if (fused_supported(c.x) && dx_ok && !(force && force[0] == '1')
       && c.ncuts <= 4 * 32 * ((c.x->cols + 31) / 32))
     return launch_glm_fused(c);
+  // wide x: column chunks through the fused kernel (host parameters only; the
+  // cut points ride with the last chunk, which must be able to take them)
+  if (c.x && c.x->cols > kMaxFusedK && fused_layout_ok(c.x)
+      && (!((c.flags & SMC_VAR_X) && c.d_x) || fused_layout_ok(c.d_x)) && !c.params_dev
+      && c.beta_host && !(force && force[0] == '1') && c.ncuts <= 4 * 32)
+    return launch_glm_chunked(c);
   return launch_glm_generic(c);
 }
 

@@ -41,6 +41,10 @@ struct FusedArgs {
   // the wake-up latency of a stream synchronise; NULL = not used
   unsigned long long* done_flag;
   unsigned long long done_val;
+  // column-chunked evaluation of a wide x (glm_generic.cu, launch_glm_chunked): this
+  // launch covers columns [out_beta_off, out_beta_off + K) of out_K_total and may
+  // have to leave the header of the packed result alone
+  int out_beta_off, out_K_total, out_skip_header;
   double c0;
   int tab_n;  // neg-binomial, scalar phi: rows with y < tab_n read lgamma / digamma
               // of (y + phi) from a per-CTA table instead of evaluating them

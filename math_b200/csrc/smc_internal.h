@@ -110,6 +110,9 @@ struct GlmCall {
   double* out = nullptr;  // packed result, device-accessible
   unsigned long long* done_flag = nullptr;  // see FusedArgs::done_flag
   unsigned long long done_val = 0;
+  // column chunk of a wider evaluation (see FusedArgs): 0 / 0 / false = the whole x
+  int out_beta_off = 0, out_K_total = 0;
+  bool out_skip_header = false;
   smc_matrix* d_alpha_vec = nullptr;
   smc_matrix* d_aux_vec = nullptr;
   smc_matrix* d_y_vec = nullptr;
@@ -123,6 +126,8 @@ int launch_glm(const GlmCall& c);
 int run_sync(GlmCall& c, int n_out, const double** out);
 // True when the single-pass TMA kernel can take this x.
 bool fused_supported(const smc_matrix* x);
+// The same without the bound on the number of columns (wide x: column chunks).
+bool fused_layout_ok(const smc_matrix* x);
 int launch_glm_fused(const GlmCall& c);
 int launch_glm_generic(const GlmCall& c);
 

@@ -225,6 +225,64 @@ def test_generic_path_matches(gpu, monkeypatch):
     assert_grad(r.d_alpha, o["d_alpha"][0])
 
 
+@pytest.mark.parametrize("N,K", [(3001, 257), (2050, 513), (1203, 1000)])
+def test_wide_x_column_chunks(gpu, monkeypatch, N, K):
+    """K > 256: column chunks through the fused kernel (forward theta chain, the
+    family on the last chunk, reverse x^T d), every family, against the oracle and
+    against the general two-pass kernels (SMC_FORCE_GENERIC)."""
+    mb = gpu
+    # bernoulli with a vector alpha as an autodiff variable and x var
+    d = make_inputs("bernoulli", N, K, seed=N + K, vec_alpha=True)
+    x, y = mb.to_matrix_cuda(d["x"]), mb.to_matrix_cuda(d["y"])
+    av = mb.to_matrix_cuda(d["alpha"])
+    r = mb.bernoulli_logit_glm_lpmf(y, x, av, d["beta"], var=("x", "alpha", "beta"))
+    o = po.bernoulli_logit_glm(d["y"], d["x"], d["alpha"], d["beta"],
+                               flags=_flags(False, ["x", "alpha", "beta"]))
+    assert_logp(r.logp, o["logp"])
+    assert_grad(r.d_beta, o["d_beta"], "d_beta")
+    assert_grad(r.d_alpha.to_host().ravel(), o["d_alpha"], "d_alpha")
+    assert_grad(r.d_x.to_host(), o["d_x"], "d_x")
+    monkeypatch.setenv("SMC_FORCE_GENERIC", "1")
+    rg = mb.bernoulli_logit_glm_lpmf(y, x, av, d["beta"], var=("x", "alpha", "beta"))
+    monkeypatch.delenv("SMC_FORCE_GENERIC")
+    assert_logp(r.logp, rg.logp)
+    assert_grad(r.d_beta, rg.d_beta, "d_beta vs two-pass")
+    # normal: scalar alpha / sigma, beta only
+    d = make_inputs("normal", N, K, seed=N)
+    x, y = mb.to_matrix_cuda(d["x"]), mb.to_matrix_cuda(d["y"])
+    r = mb.normal_id_glm_lpdf(y, x, d["alpha"], d["beta"], d["sigma"])
+    o = po.normal_id_glm(d["y"], d["x"], d["alpha"], d["beta"], d["sigma"])
+    assert_logp(r.logp, o["logp"])
+    assert_grad(r.d_beta, o["d_beta"], "d_beta")
+    assert_grad(r.d_alpha, o["d_alpha"][0], "d_alpha", scale=np.abs(o["d_beta"]).max())
+    assert_grad(r.d_aux, o["d_sigma"][0], "d_sigma", scale=np.abs(o["d_beta"]).max())
+    # neg-binomial with phi var, value only under propto
+    d = make_inputs("neg_binomial", N, K, seed=K)
+    x, y = mb.to_matrix_cuda(d["x"]), mb.to_matrix_cuda(d["y"])
+    for propto in (False, True):
+        r = mb.neg_binomial_2_log_glm_lpmf(y, x, d["alpha"], d["beta"], d["phi"],
+                                           propto=propto)
+        o = po.neg_binomial_2_log_glm(d["y"], d["x"], d["alpha"], d["beta"], d["phi"],
+                                      flags=_flags(propto, ["alpha", "beta", "aux"]))
+        assert_logp(r.logp, o["logp"])
+        assert_grad(r.d_beta, o["d_beta"], "d_beta")
+        assert_grad(r.d_aux, np.asarray(o["d_phi"]).ravel()[0], "d_phi",
+                    scale=np.abs(o["d_beta"]).max())
+    # ordered: the cut points ride with the last chunk
+    d = make_inputs("ordered", N, K, seed=7, C=6)
+    x, y = mb.to_matrix_cuda(d["x"]), mb.to_matrix_cuda(d["y"])
+    r = mb.ordered_logistic_glm_lpmf(y, x, d["beta"], d["cuts"], var=("x", "beta", "cuts"))
+    o = po.ordered_logistic_glm(d["y"], d["x"], d["beta"], d["cuts"],
+                                flags=_flags(False, ["x", "beta", "aux"]))
+    assert_logp(r.logp, o["logp"])
+    assert_grad(r.d_beta, o["d_beta"], "d_beta")
+    assert_grad(r.d_aux, o["d_cuts"], "d_cuts", scale=np.abs(o["d_beta"]).max() * 1e-2)
+    assert_grad(r.d_x.to_host(), o["d_x"], "d_x")
+    # value only (no reverse launches): the family call finishes the evaluation
+    r = mb.ordered_logistic_glm_lpmf(y, x, d["beta"], d["cuts"], var=())
+    assert_logp(r.logp, o["logp"])
+
+
 def test_synthetic_fill_matches_host(gpu):
     m = gpu.MatrixCuda(1000, 7)
     m.fill_synthetic(12345, row0=17, kind=0, scale=1.0)
