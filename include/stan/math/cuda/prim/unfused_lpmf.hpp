@@ -2,12 +2,13 @@
 #define STAN_MATH_CUDA_PRIM_UNFUSED_LPMF_HPP
 // The un-fused densities on a device-resident linear predictor (SURVEY.md
 // 8(f)3): bernoulli_logit_lpmf, poisson_log_lpmf, neg_binomial_2_log_lpmf,
-// ordered_logistic_lpmf and normal_lpdf for a theta that is a matrix_cuda<double>
+// ordered_logistic_lpmf, categorical_logit_lpmf and normal_lpdf for a theta that is a matrix_cuda<double>
 // or a var_value<matrix_cuda<double>> -- the B200 overloads of
 //   prim/prob/bernoulli_logit_lpmf.hpp L33-98      (opencl/prim/bernoulli_logit_lpmf.hpp)
 //   prim/prob/poisson_log_lpmf.hpp L27-100         (opencl/prim/poisson_log_lpmf.hpp)
 //   prim/prob/neg_binomial_2_log_lpmf.hpp L24-134  (opencl/prim/neg_binomial_2_log_lpmf.hpp)
 //   prim/prob/ordered_logistic_lpmf.hpp L72-214    (opencl/prim/ordered_logistic_lpmf.hpp)
+//   prim/prob/categorical_logit_lpmf.hpp L16-32    (no OpenCL twin; row-wise form)
 //   prim/prob/normal_lpdf.hpp L41-104              (opencl/prim/normal_lpdf.hpp)
 // for models that add terms to x * beta before the likelihood.  Same names,
 // template order and <propto>; value and d/dtheta come from one kernel over the
@@ -208,7 +209,42 @@ return_type_t<T_y, T_loc, T_scale> normal_lpdf(T_y&& y, T_loc&& mu, T_scale&& si
   return ops_partials.build(logp);
 }
 
-// The propto = false forwarding overloads are the reference's own (last lines of
+/** categorical_logit_lpmf with one row of log odds per outcome: `lin` is an N x C
+ * device matrix (data or autodiff) and the result is
+ * sum_i categorical_logit_lpmf(ns[i] | lin.row(i)^T) of
+ * prim/prob/categorical_logit_lpmf.hpp L16-32 -- what a model that adds terms to
+ * x * beta writes as a loop over the rows.  (The reference's own signatures take ONE
+ * column vector of log odds for every outcome; a C-vector is not worth a device.)
+ * d/dlin = one-hot(ns) - softmax(lin) is written straight into the device edge. */
+template <bool propto, typename T_n, typename T_prob,
+          require_t<is_cuda_operand<T_prob>>* = nullptr>
+return_type_t<T_prob> categorical_logit_lpmf(const T_n& ns, const T_prob& lin) {
+  using namespace cuda_internal;  // NOLINT
+  static constexpr const char* function = "categorical_logit_lpmf(CUDA)";
+  if (!is_stan_scalar<T_n>::value) {
+    check_size_match(function, "Size of ", "Random variable", operand_size(ns),
+                     "rows of ", "log odds parameter", lin.rows());
+  }
+  row_operand<int, T_n> n_op(ns);
+  auto ops_partials = make_partials_propagator(lin);
+  double logp = 0;
+  const unsigned flags = (propto ? SMC_PROPTO : 0u) | var_flag<T_prob>(SMC_VAR_ALPHA);
+  check_cuda_status(function,
+                    smc_categorical_logit_lpmf(n_op.handle(), n_op.scalar(), x_handle(lin),
+                                               flags, &logp,
+                                               dvec_handle<T_prob>(partials<0>(ops_partials))));
+  if (!include_summand<propto, T_prob>::value || lin.rows() == 0) {
+    return 0.0;
+  }
+  return ops_partials.build(logp);
+}
+
+template <typename T_n, typename T_prob, require_t<is_cuda_operand<T_prob>>* = nullptr>
+inline return_type_t<T_prob> categorical_logit_lpmf(const T_n& ns, const T_prob& lin) {
+  return categorical_logit_lpmf<false>(ns, lin);
+}
+
+// The other propto = false forwarding overloads are the reference's own (last lines of
 // each prim/prob/*_lpmf.hpp): their <false> calls resolve to the overloads above.
 
 }  // namespace math

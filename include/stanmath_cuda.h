@@ -289,6 +289,16 @@ int smc_ordered_logistic_lpmf(const smc_matrix* y, int y_scalar,
                               const smc_matrix* lambda, const double* cuts,
                               int64_t ncuts, unsigned flags, double* logp,
                               smc_matrix* d_lambda, double* d_cuts);
+/* prim/prob/categorical_logit_lpmf.hpp L16-32, one row of log odds per outcome:
+ * `lin` is an N x C f64 device matrix and the result is
+ * sum_i categorical_logit_lpmf(y_i, lin.row(i)^T) -- what a model that adds terms
+ * to x * beta writes as a loop over the rows.  SMC_VAR_ALPHA marks lin as an
+ * autodiff variable; its partial (one-hot(y_i) - softmax(lin_i)) is written to the
+ * N x C device matrix `d_lin`.  y outside [1, C] and non-finite log odds are
+ * SMC_ERR_DOMAIN (check_bounded L19, check_finite L22). */
+int smc_categorical_logit_lpmf(const smc_matrix* y, int y_scalar,
+                               const smc_matrix* lin, unsigned flags, double* logp,
+                               smc_matrix* d_lin);
 
 #ifdef __cplusplus
 }

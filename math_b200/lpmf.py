@@ -4,7 +4,8 @@
 reverse sweep (opencl/prim/multiply.hpp, opencl/rev/multiply.hpp); the
 ``*_lpmf`` functions are the un-fused densities on a device N-vector parameter
 (prim/prob/bernoulli_logit_lpmf.hpp, poisson_log_lpmf.hpp,
-neg_binomial_2_log_lpmf.hpp, ordered_logistic_lpmf.hpp) for models that add
+neg_binomial_2_log_lpmf.hpp, ordered_logistic_lpmf.hpp, categorical_logit_lpmf.hpp)
+for models that add
 terms to ``x * beta`` before the likelihood.  Values and partials come back in
 an ``LpmfResult`` (the C++ drop-in feeds them into the tape:
 include/stan/math/cuda/prim/unfused_lpmf.hpp, rev/multiply.hpp).
@@ -113,6 +114,19 @@ def ordered_logistic_lpmf(y, lam, cuts, propto=False, theta_var=True, cuts_var=T
     check(lib().smc_ordered_logistic_lpmf(_h(yv), ys, lam.handle, _dp(c), c.size,
                                           flags, C.byref(logp), _h(d), _dp(d_cuts)))
     return LpmfResult(logp.value, d, d_cuts if cuts_var else None)
+
+
+def categorical_logit_lpmf(y, lin, propto=False, lin_var=True):
+    """sum_i categorical_logit_lpmf(y_i | lin[i, :]) for an N x C device matrix of log
+    odds (prim/prob/categorical_logit_lpmf.hpp L16-32, one row per outcome);
+    ``d_theta`` is the N x C partial one-hot(y) - softmax(lin)."""
+    yv, ys = _split(y, int, "y")
+    flags = _flags(propto, lin_var)
+    d = MatrixCuda(lin.rows, lin.cols, np.float64) if lin_var else None
+    logp = C.c_double()
+    check(lib().smc_categorical_logit_lpmf(_h(yv), ys, lin.handle, flags, C.byref(logp),
+                                           _h(d)))
+    return LpmfResult(logp.value, d)
 
 
 def normal_lpdf(y, mu, sigma, propto=False, var=("mu", "sigma")):

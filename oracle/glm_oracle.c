@@ -628,6 +628,43 @@ int oracle_categorical_logit_glm(long N, long K, long C, const int* y, long ny,
   return 0;
 }
 
+/* ----- categorical_logit_lpmf, one row of log odds per outcome ----------------------
+ * reference: prim/prob/categorical_logit_lpmf.hpp L16-32 applied to every row of
+ * the column-major N x C matrix lin (what a model writes as a loop):
+ *   check_bounded(n, 1, C) L19; check_finite(beta) L22; propto exit L24-26;
+ *   value beta[n-1] - log_sum_exp(beta) L30-31, log_sum_exp = max + log(sum(exp(v -
+ *   max))) (prim/fun/log_sum_exp.hpp L81-93); its reverse sweep adds
+ *   exp(v - log_sum_exp(v)) = softmax(v) (rev/fun/log_sum_exp.hpp), so
+ *   d lin[i, c] = [c == y_i - 1] - softmax(lin[i, :])[c].
+ * flags: bit0 propto, bit2 lin var. */
+int oracle_categorical_logit_lpmf(long N, long C, const int* y, long ny,
+                                  const double* lin, long ld, unsigned flags,
+                                  double* logp, double* d_lin) {
+  if (bad_len(ny, N)) return 1;
+  if (logp) *logp = 0;
+  if (N == 0) return 0;
+  for (long i = 0; i < (ny == 1 ? 1 : N); ++i)
+    if (y[i] < 1 || y[i] > C) return 2;
+  for (long c = 0; c < C; ++c)
+    for (long i = 0; i < N; ++i)
+      if (!isfinite(lin[c * ld + i])) return 2;
+  if ((flags & F_PROPTO) && !(flags & F_VAR_ALPHA)) return 0;
+  acc_t lp = {0, 0};
+  for (long i = 0; i < N; ++i) {
+    const long yi = (ny == 1 ? y[0] : y[i]) - 1;
+    double m = -INFINITY, s = 0;
+    for (long c = 0; c < C; ++c) m = fmax(m, lin[c * ld + i]);
+    for (long c = 0; c < C; ++c) s += exp(lin[c * ld + i] - m);
+    const double lse = m + log(s);
+    acc_add(&lp, lin[yi * ld + i] - lse);
+    if (d_lin && (flags & F_VAR_ALPHA))
+      for (long c = 0; c < C; ++c)
+        d_lin[c * N + i] = (c == yi ? 1.0 : 0.0) - exp(lin[c * ld + i] - lse);
+  }
+  if (logp) *logp = acc_get(&lp);
+  return 0;
+}
+
 /* ----- binomial_logit_glm_lpmf ---------------------------------------------------
  * (the seventh GLM)
  * reference: prim/prob/binomial_logit_glm_lpmf.hpp L54-160 and the scalar

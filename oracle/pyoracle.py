@@ -287,6 +287,25 @@ def categorical_logit_glm(y, x, alpha, beta, flags=VAR_ALPHA | VAR_BETA,
     return _finish(rc, logp, d_alpha=d_alpha, d_beta=d_beta, d_x=d_x)
 
 
+def categorical_logit_lpmf(y, lin, flags=VAR_ALPHA, impl="oracle"):
+    """sum_i categorical_logit_lpmf(y_i | lin[i, :]) for an N x C matrix of log odds
+    (prim/prob/categorical_logit_lpmf.hpp L16-32 per row); d_lin is N x C."""
+    lin = _prep_x(lin)
+    N, Cc = lin.shape
+    y = _vec(y, np.int32)
+    logp = np.zeros(1)
+    d_lin = np.zeros((N, Cc), order="F")
+    if impl == "oracle":
+        rc = oracle_lib().oracle_categorical_logit_lpmf(
+            _L(N), _L(Cc), _i(y), _L(y.size), _d(lin), _L(max(N, 1)), C.c_uint(flags),
+            _d(logp), _d(d_lin))
+    else:
+        rc = ref_lib().ref_categorical_logit_lpmf(
+            _L(N), _L(Cc), _i(y), _L(y.size), _d(lin), int(bool(flags & PROPTO)),
+            _d(logp), _d(d_lin))
+    return _finish(rc, logp, d_lin=d_lin)
+
+
 FAMILY_ID = {"normal": 0, "bernoulli": 1, "poisson": 2, "neg_binomial": 3}
 
 

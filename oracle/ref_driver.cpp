@@ -414,6 +414,28 @@ int ref_categorical_logit_glm(long N, long K, long C, const int* y, long ny,
   });
 }
 
+// ------------------------------------------ categorical_logit_lpmf, row-wise
+// reference: stan/math/prim/prob/categorical_logit_lpmf.hpp L16-32, called once
+// per row of the column-major N x C matrix of log odds (the loop a model writes).
+int ref_categorical_logit_lpmf(long N, long C, const int* y, long ny,
+                               const double* lin, int propto, double* logp,
+                               double* d_lin) {
+  return guarded([&] {
+    with_bool(propto, [&](auto P) {
+      MatV l = make_mat<var>(lin, N, C);
+      var lp = 0.0;
+      for (long i = 0; i < N; ++i) {
+        VecV row = l.row(i).transpose();
+        lp += stan::math::categorical_logit_lpmf<decltype(P)::value>(
+            ny == 1 ? y[0] : y[i], row);
+      }
+      lp.grad();
+      if (logp) *logp = lp.val();
+      put_mat(d_lin, l);
+    });
+  });
+}
+
 // ----------------------------------------------------------------- binomial
 // reference: stan/math/prim/prob/binomial_logit_glm_lpmf.hpp L54-160
 // n: successes (nn = 1 or N), Nt: trials (nNt = 1 or N).

@@ -2,7 +2,8 @@
 // 8(f)3): the device matrix-vector product + add, and the un-fused densities on
 // a device linear predictor.  The oracle is the reference's own prim
 // implementation (bernoulli_logit_lpmf, poisson_log_lpmf,
-// neg_binomial_2_log_lpmf, ordered_logistic_lpmf) compiled into this binary;
+// neg_binomial_2_log_lpmf, ordered_logistic_lpmf, categorical_logit_lpmf) compiled
+// into this binary;
 // the protocol is the one of test/unit/math/opencl/util.hpp L129-191.
 #include "cuda_test_util.hpp"
 
@@ -41,6 +42,32 @@ auto ordl = [](const auto& y, const auto& lambda, const auto& c) {
 };
 auto ordl_propto = [](const auto& y, const auto& lambda, const auto& c) {
   return stan::math::ordered_logistic_lpmf<true>(y, lambda, c);
+};
+
+// categorical_logit_lpmf with one row of log odds per outcome: on the device one
+// call, on the host the loop over the rows a Stan model writes with the
+// reference's own (n, column vector) signature.
+template <bool propto>
+struct cat_rows {
+  template <typename T_n, typename T_lin>
+  auto operator()(const T_n& ns, const T_lin& lin) const {
+    if constexpr (stan::is_cuda_operand<T_lin>::value) {
+      return stan::math::categorical_logit_lpmf<propto>(ns, lin);
+    } else {
+      stan::return_type_t<T_lin> lp = 0.0;
+      for (Eigen::Index i = 0; i < lin.rows(); ++i) {
+        int n_i;
+        if constexpr (std::is_same<T_n, int>::value) {
+          n_i = ns;
+        } else {
+          n_i = ns[i];
+        }
+        Matrix<stan::value_type_t<T_lin>, Dynamic, 1> row = lin.row(i).transpose();
+        lp += stan::math::categorical_logit_lpmf<propto>(n_i, row);
+      }
+      return lp;
+    }
+  }
 };
 
 VectorXd random_theta(int N, double scale, unsigned seed) {
@@ -154,6 +181,46 @@ TEST(CudaUnfused, ordered_logistic_lpmf) {
   EXPECT_THROW(stan::math::ordered_logistic_lpmf(y_bad_d, l_d, c), std::domain_error);
   EXPECT_THROW(stan::math::ordered_logistic_lpmf(y_d, l_inf_d, c), std::domain_error);
   EXPECT_THROW(stan::math::ordered_logistic_lpmf(y_d, l_d, c_unordered), std::domain_error);
+}
+
+TEST(CudaUnfused, categorical_logit_lpmf_row_per_outcome) {
+  vector<int> y{1, 3, 1, 2, 2};
+  MatrixXd lin(5, 3);
+  lin << 0.5, -2, 4, 1.3, 0.2, -0.7, -30, 2, 55, 0, 0, 0, 700, -700, 1e-3;
+  compare_cpu_cuda_prim_rev(cat_rows<false>{}, std::make_tuple(DEV, DEV), y, lin);
+  compare_cpu_cuda_prim_rev(cat_rows<true>{}, std::make_tuple(DEV, DEV), y, lin);
+  compare_cpu_cuda_prim_rev(cat_rows<false>{}, std::make_tuple(HOST, DEV), y, lin);
+  compare_cpu_cuda_prim_rev(cat_rows<false>{}, std::make_tuple(HOST, DEV), 2, lin);
+  // register-resident rows (C <= 8, C <= 32) and the re-reading kernel (C = 43,
+  // the class count of the reference's OpenCL categorical test)
+  for (int C : {1, 2, 8, 9, 32, 43}) {
+    const int N = C == 43 ? 1153 : 4099;
+    srand(100 + C);
+    MatrixXd big = MatrixXd::Random(N, C) * 4.0;
+    vector<int> yb(N);
+    for (int i = 0; i < N; ++i) yb[i] = 1 + (i * 7) % C;
+    compare_cpu_cuda_prim_rev(cat_rows<false>{}, std::make_tuple(DEV, DEV), yb, big);
+  }
+  // the same call on a device matrix that came out of a device computation
+  matrix_cuda<int> y_d(y);
+  vector<int> y_bad{1, 3, 1, 4, 2}, y_short{1, 2, 3};
+  matrix_cuda<int> y_bad_d(y_bad), y_short_d(y_short);
+  matrix_cuda<double> lin_d(lin);
+  MatrixXd lin_inf = lin, lin_nan = lin;
+  lin_inf(2, 1) = INFINITY;
+  lin_nan(4, 2) = NAN;
+  matrix_cuda<double> lin_inf_d(lin_inf), lin_nan_d(lin_nan);
+  EXPECT_THROW(stan::math::categorical_logit_lpmf(y_bad_d, lin_d), std::domain_error);
+  EXPECT_THROW(stan::math::categorical_logit_lpmf(0, lin_d), std::domain_error);
+  EXPECT_THROW(stan::math::categorical_logit_lpmf(y_d, lin_inf_d), std::domain_error);
+  EXPECT_THROW(stan::math::categorical_logit_lpmf(y_d, lin_nan_d), std::domain_error);
+  EXPECT_THROW(stan::math::categorical_logit_lpmf<true>(y_d, lin_nan_d), std::domain_error);
+  EXPECT_THROW(stan::math::categorical_logit_lpmf(y_short_d, lin_d), std::invalid_argument);
+  EXPECT_EQ(stan::math::categorical_logit_lpmf<true>(y_d, lin_d), 0.0);
+  vector<int> e{};
+  matrix_cuda<int> e_d(e);
+  matrix_cuda<double> lin0_d(MatrixXd(0, 3));
+  EXPECT_EQ(stan::math::categorical_logit_lpmf(e_d, lin0_d), 0.0);
 }
 
 TEST(CudaUnfused, normal_lpdf) {
