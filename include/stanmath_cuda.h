@@ -244,6 +244,21 @@ int smc_linear_predictor(const smc_matrix* x, const double* beta,
  * be NULL) and *sum_v = sum_i v[i] (may be NULL).  One sweep over x. */
 int smc_linear_predictor_adjoint(const smc_matrix* x, const smc_matrix* v,
                                  double* xt_v, double* sum_v);
+/* The matrix form, for a K x C weight matrix (the product in front of an un-fused
+ * categorical_logit_lpmf; opencl/prim/multiply.hpp): lin_out[i,c] = sum_k x[i,k]
+ * beta[k,c] + alpha[c].  beta host column-major K x C, alpha host C doubles or NULL
+ * (no intercept), lin_out an N x C f64 device matrix.  One sweep over x per block of
+ * 64 classes through the categorical GLM's FP64 tensor-core (DMMA) kernel.
+ * Asynchronous on the thread's stream. */
+int smc_linear_predictor_matrix(const smc_matrix* x, const double* beta,
+                                int64_t n_classes, const double* alpha,
+                                smc_matrix* lin_out);
+/* Reverse sweep of the matrix form (opencl/rev/multiply.hpp L25-60): xt_adj[k,c] =
+ * sum_i x[i,k] adj[i,c] (host column-major K x C, may be NULL) and colsum[c] =
+ * sum_i adj[i,c] (host C doubles, may be NULL) for an N x C f64 device matrix adj.
+ * Fixed-order sums: bit-reproducible. */
+int smc_linear_predictor_matrix_adjoint(const smc_matrix* x, const smc_matrix* adj,
+                                        double* xt_adj, double* colsum);
 /* *sum = sum_i v[i] of an f64 device vector (fixed-order, deterministic). */
 int smc_vector_sum(const smc_matrix* v, double* sum);
 

@@ -82,6 +82,8 @@ SIGNATURES = {
     "smc_matrix_add_scalar": (_I, [_P, _D]),
     "smc_linear_predictor": (_I, [_P, _DP, _P, _D, _P]),
     "smc_linear_predictor_adjoint": (_I, [_P, _P, _DP, _DP]),
+    "smc_linear_predictor_matrix": (_I, [_P, _DP, _I64, _DP, _P]),
+    "smc_linear_predictor_matrix_adjoint": (_I, [_P, _P, _DP, _DP]),
     "smc_vector_sum": (_I, [_P, _DP]),
     "smc_indexing": (_I, [_DP, _I64, _P, _P]),
     "smc_indexing_rev": (_I, [_P, _P, _I64, _DP]),

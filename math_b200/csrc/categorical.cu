@@ -55,6 +55,9 @@ struct CatArgs {
   int rows_per_cta;  // pass 2 row slice (multiple of 4)
   int lin_stages;    // pass 1 (TMA): depth of the x / beta^T ring
   const double* beta_t;  // pass 1 (TMA): beta^T, [K][C8 + 4], zero padded
+  // pass 1 as a plain matrix product (smc_linear_predictor_matrix): the epilogue
+  // stores lin = x beta + alpha^T into T (classes < C only) and stops
+  int lin_only;
 };
 
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
@@ -150,6 +153,18 @@ __global__ void __launch_bounds__(kCatThreads, 1)
     for (int mt = 0; mt < 4; ++mt) {
       const int64_t row = r0 + 8 * mt + grp;
       const bool valid = row < a.N;
+      if (a.lin_only) {
+        if (valid) {
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int c = 8 * nt + 2 * tig + j;
+              if (c < a.C) a.T[(size_t)c * a.ldT + row] = acc[mt][nt][j] + alpha_s[c];
+            }
+        }
+        continue;
+      }
       const int yc = valid ? (a.y ? a.y[row] : a.y_scalar) - 1 : 0;
       double m = -INFINITY;
       double lin_y = 0.0;
@@ -504,6 +519,26 @@ __global__ void __launch_bounds__(kLinThreads, 1)
     }
     if (r0 >= a.N) continue;
 
+    if (a.lin_only) {
+      // rows 2 grp, 2 grp + 1 of a class are adjacent: one 16-byte store
+      const int64_t row = r0 + 2 * grp;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int c = lin_class<NT>(nt, 2 * tig + j);
+          if (c < a.C) {
+            double* tp = a.T + (size_t)c * a.ldT + row;
+            const double v0 = acc[0][nt][j] + alpha_s[c], v1 = acc[1][nt][j] + alpha_s[c];
+            if (row + 1 < a.N)
+              *reinterpret_cast<double2*>(tp) = make_double2(v0, v1);
+            else if (row < a.N)
+              *tp = v0;
+          }
+        }
+      continue;
+    }
+
     // ---- epilogue: softmax over the C classes of each row (held by a quad)
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
@@ -787,10 +822,21 @@ static bool cat_tma_ok(const smc_matrix* x) {
   return x->rows < 0x7fffff00ll && x->cols >= 1;
 }
 
-int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
-                       const double* alpha_host, const double* beta_host,
-                       int64_t C, unsigned flags, double* logp, double* d_alpha,
-                       double* d_beta, smc_matrix* d_x) {
+// The two sweeps are also the matrix products either side of an un-fused
+// categorical density (smc_linear_predictor_matrix[_adjoint] below):
+//   kCatLin  pass 1 alone, epilogue = store lin = x beta + alpha^T into `io` (N x C)
+//   kCatAdj  pass 2 alone with T = `io` (N x C adjoints): d_beta = x^T io
+enum CatMode { kCatGlm = 0, kCatLin = 1, kCatAdj = 2 };
+
+static bool vec16_ok(const smc_matrix* m) {
+  return (reinterpret_cast<uintptr_t>(m->data) & 15) == 0 && (m->ld & 1) == 0;
+}
+
+static int launch_cat_impl(CatMode mode, const smc_matrix* y, int y_scalar,
+                           const smc_matrix* x, const double* alpha_host,
+                           const double* beta_host, int64_t C, unsigned flags,
+                           double* logp, double* d_alpha, double* d_beta,
+                           smc_matrix* d_x, const smc_matrix* io) {
   Context& cx = ctx();
   CatArgs a;
   memset(&a, 0, sizeof(a));
@@ -801,6 +847,7 @@ int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
   if (a.C8 > 64)
     return fail(SMC_ERR_UNSUPPORTED,
                 "categorical_logit_glm_lpmf: more than 64 classes not supported yet");
+  a.lin_only = mode == kCatLin;
   a.x = static_cast<const double*>(x->data);
   a.ldx = x->ld;
   a.y = y ? static_cast<const int*>(y->data) : nullptr;
@@ -812,11 +859,15 @@ int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
   const size_t nparam = (size_t)a.K * a.C + a.C;
   const size_t off_bt = (nparam + 15) & ~(size_t)15;  // 128-byte aligned
   if (int rc = ensure_params(sizeof(double) * (off_bt + (size_t)a.K * C8p + 16))) return rc;
-  if (a.K)
+  if (a.K && mode != kCatAdj)
     SMC_CUDA(cudaMemcpyAsync(cx.params_dev, beta_host, sizeof(double) * a.K * a.C,
                              cudaMemcpyHostToDevice, cx.stream));
-  SMC_CUDA(cudaMemcpyAsync(cx.params_dev + (size_t)a.K * a.C, alpha_host,
-                           sizeof(double) * a.C, cudaMemcpyHostToDevice, cx.stream));
+  if (alpha_host)
+    SMC_CUDA(cudaMemcpyAsync(cx.params_dev + (size_t)a.K * a.C, alpha_host,
+                             sizeof(double) * a.C, cudaMemcpyHostToDevice, cx.stream));
+  else
+    SMC_CUDA(cudaMemsetAsync(cx.params_dev + (size_t)a.K * a.C, 0, sizeof(double) * a.C,
+                             cx.stream));
   a.beta = cx.params_dev;
   a.alpha = cx.params_dev + (size_t)a.K * a.C;
   a.beta_t = cx.params_dev + off_bt;
@@ -851,8 +902,8 @@ int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
   const bool lin_tma = tma && a.K >= 1;
   if (lin_tma) smem1 = (size_t)a.lin_stages * (lin_stage + 16) + lin_fixed;
 
-  const bool need_beta = flags & SMC_VAR_BETA;
-  const bool need_dx = (flags & SMC_VAR_X) && d_x;
+  const bool need_beta = mode == kCatAdj || (mode == kCatGlm && (flags & SMC_VAR_BETA));
+  const bool need_dx = mode == kCatGlm && (flags & SMC_VAR_X) && d_x;
   // pass-2 geometry
   const int MT = NT <= 4 ? 8 : 4;
   const int kchunk2 = kCatWarps * MT * 8;
@@ -869,7 +920,7 @@ int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
   int grid1 = (int)((ntiles + kCatWarps - 1) / kCatWarps);
   if (grid1 > cx.sm_count) grid1 = cx.sm_count;
   CUtensorMap tm_lin, tm_beta, tm_dbx, tm_dbt;
-  if (lin_tma) {
+  if (lin_tma && mode != kCatAdj) {
     if (encode_tmap_f64(&tm_lin, x->data, x->rows, x->cols, x->ld, kLinBox, ks_lin)
             != CUDA_SUCCESS
         || encode_tmap_f64(&tm_beta, a.beta_t, C8p, a.K, C8p, C8p, ks_lin)
@@ -883,17 +934,32 @@ int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
   }
   const int rs = 2 + a.C8;
 
-  // scratch: T (ldT x C8), out (rs), d_beta_dev (K*C), partials
-  a.ldT = (a.N + 3) & ~3ll;
-  const size_t nT = (size_t)a.ldT * a.C8;
+  // scratch: T (ldT x C8), out (rs), d_beta_dev (K*C), partials.  The products
+  // work in place on the caller's matrix when its layout allows: the TMA pass 1
+  // stores row pairs as 16 bytes; pass 2 reads T through a tensor map whose
+  // columns >= C are zero-filled (the plain kernel reads C8 columns, so a matrix
+  // with C < C8 is copied into the padded scratch first)
+  const bool direct = mode == kCatLin   ? (!lin_tma || vec16_ok(io))
+                      : mode == kCatAdj ? (tma ? vec16_ok(io) : a.C == a.C8)
+                                        : false;
+  a.ldT = direct ? io->ld : (a.N + 3) & ~3ll;
+  const size_t nT = direct ? 0 : (size_t)a.ldT * a.C8;
   const size_t npart1 = (size_t)grid1 * rs;
   const size_t npart2 = need_beta ? (size_t)nby * nbx * kchunk2 * a.C8 : 0;
   const size_t npart = npart1 > npart2 ? npart1 : npart2;
   const size_t ndb = (size_t)a.K * a.C;
   if (int rc = ensure_scratch(sizeof(double) * (nT + rs + ndb + 8))) return rc;
   if (int rc = ensure_partials(sizeof(double) * (npart + 8))) return rc;
-  a.T = cx.scratch;
+  a.T = direct ? static_cast<double*>(io->data) : cx.scratch;
   double* out_dev = cx.scratch + nT;
+  if (mode == kCatAdj && !direct) {
+    SMC_CUDA(cudaMemcpy2DAsync(a.T, sizeof(double) * a.ldT, io->data,
+                               sizeof(double) * io->ld, sizeof(double) * a.N, a.C,
+                               cudaMemcpyDeviceToDevice, cx.stream));
+    if (a.C8 > a.C)
+      SMC_CUDA(cudaMemsetAsync(a.T + (size_t)a.C * a.ldT, 0,
+                               sizeof(double) * a.ldT * (a.C8 - a.C), cx.stream));
+  }
   double* d_beta_dev = out_dev + rs;
   a.partials = cx.partials;
   a.out = out_dev;
@@ -902,7 +968,9 @@ int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
   a.ld_dx = need_dx ? d_x->ld : 0;
 
   int rc = SMC_OK;
-  if (lin_tma) {
+  if (mode == kCatAdj) {
+    // no pass 1
+  } else if (lin_tma) {
 #define SMC_LIN_CASE(NTV)                                                         \
   case NTV:                                                                       \
     rc = ks_lin == 32   ? run_lin_tma<NTV, 32>(tm_lin, tm_beta, a, grid1, smem1)  \
@@ -936,11 +1004,20 @@ int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
     default: rc = run_lin<8>(a, grid1, smem1); break;
   }
   if (rc) return rc;
-  cx.launches += 1;
-  cat_lin_finalize_kernel<<<1, 128, 0, cx.stream>>>(cx.partials, grid1, rs, a.C,
-                                                    out_dev);
-  SMC_CUDA(cudaGetLastError());
-  cx.launches += 1;
+  if (mode != kCatAdj) cx.launches += 1;
+  if (mode == kCatLin) {
+    if (!direct)
+      SMC_CUDA(cudaMemcpy2DAsync(io->data, sizeof(double) * io->ld, a.T,
+                                 sizeof(double) * a.ldT, sizeof(double) * a.N, a.C,
+                                 cudaMemcpyDeviceToDevice, cx.stream));
+    return SMC_OK;  // stream-ordered: the consumer runs on the same stream
+  }
+  if (mode == kCatGlm) {
+    cat_lin_finalize_kernel<<<1, 128, 0, cx.stream>>>(cx.partials, grid1, rs, a.C,
+                                                      out_dev);
+    SMC_CUDA(cudaGetLastError());
+    cx.launches += 1;
+  }
 
   if (need_beta && a.K > 0) {
     dim3 g2(nbx, nby);
@@ -950,7 +1027,8 @@ int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
       const int xbox = kchunk2 > 256 ? 256 : kchunk2;
       if (encode_tmap_f64(&tm_dbx, x->data, x->rows, x->cols, x->ld, kDbRows, xbox)
               != CUDA_SUCCESS
-          || encode_tmap_f64(&tm_dbt, a.T, a.N, a.C8, a.ldT, kDbRows, a.C8)
+          || encode_tmap_f64(&tm_dbt, a.T, a.N, direct ? a.C : a.C8, a.ldT, kDbRows,
+                             a.C8)
                  != CUDA_SUCCESS)
         return fail(SMC_ERR_CUDA, "cuTensorMapEncodeTiled failed (categorical pass 2)");
       switch (NT) {
@@ -999,15 +1077,18 @@ int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
 
   // results -> host
   if (int rc2 = ensure_out(sizeof(double) * (rs + ndb + 8))) return rc2;
-  SMC_CUDA(cudaMemcpyAsync(cx.out_host, out_dev, sizeof(double) * rs,
-                           cudaMemcpyDeviceToHost, cx.stream));
+  if (mode == kCatGlm)
+    SMC_CUDA(cudaMemcpyAsync(cx.out_host, out_dev, sizeof(double) * rs,
+                             cudaMemcpyDeviceToHost, cx.stream));
   if (need_beta && a.K > 0)
     SMC_CUDA(cudaMemcpyAsync(cx.out_host + rs, d_beta_dev, sizeof(double) * ndb,
                              cudaMemcpyDeviceToHost, cx.stream));
   SMC_CUDA(cudaStreamSynchronize(cx.stream));
-  *logp = cx.out_host[0];
-  if (d_alpha && (flags & SMC_VAR_ALPHA))
-    memcpy(d_alpha, cx.out_host + 2, sizeof(double) * a.C);
+  if (mode == kCatGlm) {
+    *logp = cx.out_host[0];
+    if (d_alpha && (flags & SMC_VAR_ALPHA))
+      memcpy(d_alpha, cx.out_host + 2, sizeof(double) * a.C);
+  }
   if (d_beta && need_beta) {
     if (a.K > 0)
       memcpy(d_beta, cx.out_host + rs, sizeof(double) * ndb);
@@ -1015,9 +1096,130 @@ int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
   return SMC_OK;
 }
 
+int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
+                       const double* alpha_host, const double* beta_host,
+                       int64_t C, unsigned flags, double* logp, double* d_alpha,
+                       double* d_beta, smc_matrix* d_x) {
+  return launch_cat_impl(kCatGlm, y, y_scalar, x, alpha_host, beta_host, C, flags, logp,
+                         d_alpha, d_beta, d_x, nullptr);
+}
+
+// Column sums of an N x C matrix, fixed order: [chunk][c] partials, then one sum
+// over the chunks per column.
+constexpr int kColsumChunks = 64;
+__global__ void colsum_partial_kernel(const double* __restrict__ m, int64_t ld, int64_t N,
+                                      double* __restrict__ partials) {
+  __shared__ double s_w[8];
+  const int c = blockIdx.y;
+  const int64_t per = (N + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = blockIdx.x * per, hi = min(N, lo + per);
+  const double* col = m + (size_t)c * ld;
+  double v = 0.0;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) v += col[i];
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) v += s_w[w];
+    partials[(size_t)c * gridDim.x + blockIdx.x] = v;
+  }
+}
+__global__ void colsum_final_kernel(const double* __restrict__ partials, int nchunks, int C,
+                                    double* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double v = 0.0;
+  for (int j = 0; j < nchunks; ++j) v += partials[(size_t)c * nchunks + j];
+  out[c] = v;
+}
+
 }  // namespace smc
 
 using namespace smc;
+
+namespace {
+// A view of `ncols` columns of m starting at column c0 (same buffer, not owned).
+smc_matrix column_block(const smc_matrix* m, int64_t c0, int64_t ncols) {
+  smc_matrix v;
+  v.data = static_cast<char*>(m->data) + sizeof(double) * (size_t)c0 * m->ld;
+  v.rows = m->rows;
+  v.cols = ncols;
+  v.ld = m->ld;
+  v.dtype = SMC_F64;
+  v.device = m->device;
+  return v;
+}
+constexpr int64_t kCatBlock = 64;  // classes one launch of the DMMA kernels takes
+}  // namespace
+
+extern "C" int smc_linear_predictor_matrix(const smc_matrix* x, const double* beta,
+                                           int64_t n_classes, const double* alpha,
+                                           smc_matrix* lin_out) {
+  static const char* fn = "linear_predictor_matrix";
+  if (int rc = ensure_ctx()) return rc;
+  if (!x || x->dtype != SMC_F64)
+    return fail(SMC_ERR_INVALID_ARGUMENT, "%s: x must be an f64 device matrix", fn);
+  const int64_t N = x->rows, K = x->cols, C = n_classes;
+  if (C < 0 || (K > 0 && C > 0 && !beta))
+    return fail(SMC_ERR_INVALID_ARGUMENT, "%s: NULL beta", fn);
+  if (!lin_out || lin_out->dtype != SMC_F64 || lin_out->rows != N || lin_out->cols != C)
+    return fail(SMC_ERR_INVALID_ARGUMENT,
+                "%s: lin_out must be an f64 %lld x %lld device matrix", fn, (long long)N,
+                (long long)C);
+  if (N == 0 || C == 0) return SMC_OK;
+  lin_out->version++;
+  for (int64_t c0 = 0; c0 < C; c0 += kCatBlock) {
+    const int64_t nc = C - c0 < kCatBlock ? C - c0 : kCatBlock;
+    smc_matrix blk = column_block(lin_out, c0, nc);
+    if (int rc = launch_cat_impl(kCatLin, nullptr, 1, x, alpha ? alpha + c0 : nullptr,
+                                 beta + (size_t)c0 * K, nc, 0, nullptr, nullptr, nullptr,
+                                 nullptr, &blk))
+      return rc;
+  }
+  return SMC_OK;
+}
+
+extern "C" int smc_linear_predictor_matrix_adjoint(const smc_matrix* x,
+                                                   const smc_matrix* adj, double* xt_adj,
+                                                   double* colsum) {
+  static const char* fn = "linear_predictor_matrix_adjoint";
+  if (int rc = ensure_ctx()) return rc;
+  if (!x || x->dtype != SMC_F64)
+    return fail(SMC_ERR_INVALID_ARGUMENT, "%s: x must be an f64 device matrix", fn);
+  const int64_t N = x->rows, K = x->cols;
+  if (!adj || adj->dtype != SMC_F64 || adj->rows != N)
+    return fail(SMC_ERR_INVALID_ARGUMENT, "%s: adj must be an f64 matrix with rows(x) rows",
+                fn);
+  const int64_t C = adj->cols;
+  if (xt_adj) memset(xt_adj, 0, sizeof(double) * (size_t)K * C);
+  if (colsum) memset(colsum, 0, sizeof(double) * (size_t)C);
+  if (N == 0 || C == 0) return SMC_OK;
+  Context& cx = ctx();
+  if (xt_adj && K > 0) {
+    for (int64_t c0 = 0; c0 < C; c0 += kCatBlock) {
+      const int64_t nc = C - c0 < kCatBlock ? C - c0 : kCatBlock;
+      smc_matrix blk = column_block(adj, c0, nc);
+      if (int rc = launch_cat_impl(kCatAdj, nullptr, 1, x, nullptr, nullptr, nc, 0, nullptr,
+                                   nullptr, xt_adj + (size_t)c0 * K, nullptr, &blk))
+        return rc;
+    }
+  }
+  if (colsum) {
+    const int chunks = N < 65536 ? 1 : kColsumChunks;
+    if (int rc = ensure_partials(sizeof(double) * (size_t)C * chunks)) return rc;
+    if (int rc = ensure_out(sizeof(double) * (size_t)C)) return rc;
+    colsum_partial_kernel<<<dim3(chunks, (unsigned)C), 256, 0, cx.stream>>>(
+        static_cast<const double*>(adj->data), adj->ld, N, cx.partials);
+    SMC_CUDA(cudaGetLastError());
+    colsum_final_kernel<<<(int)((C + 127) / 128), 128, 0, cx.stream>>>(cx.partials, chunks,
+                                                                      (int)C, cx.out_host);
+    SMC_CUDA(cudaGetLastError());
+    cx.launches += 2;
+    SMC_CUDA(cudaStreamSynchronize(cx.stream));
+    memcpy(colsum, cx.out_host, sizeof(double) * (size_t)C);
+  }
+  return SMC_OK;
+}
 
 extern "C" int smc_categorical_logit_glm(const smc_matrix* y, int y_scalar,
                                          const smc_matrix* x, const double* alpha,

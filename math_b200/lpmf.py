@@ -45,6 +45,32 @@ def multiply_adjoint(x, v):
     return g, s.value
 
 
+def multiply_matrix(x, beta, alpha=None):
+    """lin = x @ beta + alpha^T on the device for a K x C weight matrix (alpha: C
+    values or None): the product in front of an un-fused categorical_logit_lpmf."""
+    b = np.asfortranarray(np.asarray(beta, dtype=np.float64))
+    if b.ndim != 2 or b.shape[0] != x.cols:
+        raise ValueError(f"beta must be {x.cols} x C, got {b.shape}")
+    a = None
+    if alpha is not None:
+        a = np.ascontiguousarray(np.asarray(alpha, dtype=np.float64).ravel())
+        if a.size != b.shape[1]:
+            raise ValueError("alpha must have one entry per column of beta")
+    lin = MatrixCuda(x.rows, b.shape[1], np.float64)
+    check(lib().smc_linear_predictor_matrix(x.handle, _dp(b), b.shape[1],
+                                            _dp(a) if a is not None else None, lin.handle))
+    return lin
+
+
+def multiply_matrix_adjoint(x, adj):
+    """(x.T @ adj, adj.sum(axis=0)) for an N x C device matrix adj: the reverse sweep
+    of multiply_matrix (d_beta and d_alpha)."""
+    g = np.zeros((x.cols, adj.cols), order="F")
+    cs = np.zeros(adj.cols)
+    check(lib().smc_linear_predictor_matrix_adjoint(x.handle, adj.handle, _dp(g), _dp(cs)))
+    return g, cs
+
+
 def indexing(z, idx):
     """out[i] = z[idx[i]] (0-based) on the device: opencl/kernel_generator/indexing.hpp."""
     zz = np.ascontiguousarray(np.atleast_1d(np.asarray(z, dtype=np.float64)).ravel())

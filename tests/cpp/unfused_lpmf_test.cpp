@@ -9,6 +9,8 @@
 
 #include <boost/random/mersenne_twister.hpp>
 
+#include <array>
+
 using Eigen::Dynamic;
 using Eigen::Matrix;
 using Eigen::MatrixXd;
@@ -314,6 +316,83 @@ TEST(CudaUnfused, multiply_add_then_density_matches_the_fused_glm) {
     stan::math::recover_memory();
   }
   EXPECT_THROW(stan::math::multiply(x_d, VectorXd(VectorXd::Zero(K + 1))),
+               std::invalid_argument);
+}
+
+TEST(CudaUnfused, matrix_product_then_categorical_matches_the_fused_glm) {
+  // lin = x beta + alpha^T on the device (FP64 tensor-core sweep), the un-fused
+  // categorical density on it, and the reverse sweep x^T adj / column sums:
+  // against prim's categorical_logit_glm_lpmf on the host and the fused device GLM
+  for (auto shape : {std::array<int, 3>{1531, 37, 5}, std::array<int, 3>{4099, 128, 32},
+                     std::array<int, 3>{777, 21, 70}, std::array<int, 3>{5, 2, 3}}) {
+    const int N = shape[0], K = shape[1], C = shape[2];
+    srand(11 + C);
+    MatrixXd x = MatrixXd::Random(N, K);
+    MatrixXd beta = MatrixXd::Random(K, C) / std::sqrt(double(K));
+    VectorXd alpha = VectorXd::Random(C);
+    vector<int> y(N);
+    for (int i = 0; i < N; ++i) y[i] = 1 + (i * 7) % C;
+    matrix_cuda<double> x_d(x);
+    matrix_cuda<int> y_d(y);
+    // all data: the product itself, then the density
+    {
+      MatrixXd lin_dev = stan::math::from_matrix_cuda(stan::math::multiply(x_d, beta));
+      MatrixXd lin_cpu = x * beta;
+      ASSERT_EQ(lin_dev.rows(), N);
+      ASSERT_EQ(lin_dev.cols(), C);
+      const double scale = lin_cpu.cwiseAbs().maxCoeff();
+      for (int c = 0; c < C; ++c)
+        for (int i = 0; i < N; i += 13)
+          expect_close("x * beta", lin_dev(i, c), lin_cpu(i, c), kRelGrad, scale);
+      double dev = stan::math::categorical_logit_lpmf(
+          y_d, stan::math::linear_predictor(x_d, beta, alpha));
+      double cpu = stan::math::categorical_logit_glm_lpmf(y, x, alpha, beta);
+      expect_close("value", dev, cpu, kRelLogp, 0);
+    }
+    // alpha, beta autodiff (Eigen matrices of var)
+    {
+      Matrix<var, Dynamic, Dynamic> b1 = beta, b2 = beta, b3 = beta;
+      Matrix<var, Dynamic, 1> a1 = alpha, a2 = alpha, a3 = alpha;
+      var lp_dev = stan::math::categorical_logit_lpmf(
+          y_d, stan::math::linear_predictor(x_d, b1, a1));
+      var lp_cpu = stan::math::categorical_logit_glm_lpmf(y, x, a2, b2);
+      var lp_glm = C <= 64 ? stan::math::categorical_logit_glm_lpmf(y_d, x_d, a3, b3)
+                           : var(lp_cpu.val());
+      (lp_dev + lp_cpu + lp_glm).grad();
+      expect_close("value vs host", lp_dev.val(), lp_cpu.val(), kRelLogp, 0);
+      expect_close("value vs fused", lp_dev.val(), lp_glm.val(), kRelLogp, 0);
+      const double sa = a2.adj().cwiseAbs().maxCoeff(), sb = b2.adj().cwiseAbs().maxCoeff();
+      for (int c = 0; c < C; ++c) {
+        expect_close("d_alpha", a1[c].adj(), a2[c].adj(), kRelGrad, sa);
+        if (C <= 64) expect_close("d_alpha vs fused", a1[c].adj(), a3[c].adj(), kRelGrad, sa);
+        for (int k = 0; k < K; ++k) {
+          expect_close("d_beta", b1(k, c).adj(), b2(k, c).adj(), kRelGrad, sb);
+          if (C <= 64)
+            expect_close("d_beta vs fused", b1(k, c).adj(), b3(k, c).adj(), kRelGrad, sb);
+        }
+      }
+      stan::math::recover_memory();
+    }
+    // var_value<MatrixXd> beta through multiply (no intercept), data alpha dropped
+    {
+      stan::math::var_value<MatrixXd> b1(beta);
+      Matrix<var, Dynamic, Dynamic> b2 = beta;
+      var lp_dev = stan::math::categorical_logit_lpmf(y_d, stan::math::multiply(x_d, b1));
+      var lp_cpu = stan::math::categorical_logit_glm_lpmf(y, x, VectorXd(VectorXd::Zero(C)), b2);
+      (lp_dev + lp_cpu).grad();
+      expect_close("multiply value", lp_dev.val(), lp_cpu.val(), kRelLogp, 0);
+      const double sb = b2.adj().cwiseAbs().maxCoeff();
+      for (int c = 0; c < C; ++c)
+        for (int k = 0; k < K; ++k)
+          expect_close("multiply d_beta", b1.adj()(k, c), b2(k, c).adj(), kRelGrad, sb);
+      stan::math::recover_memory();
+    }
+  }
+  matrix_cuda<double> x_d(MatrixXd(MatrixXd::Zero(4, 3)));
+  EXPECT_THROW(stan::math::multiply(x_d, MatrixXd(MatrixXd::Zero(4, 2))),
+               std::invalid_argument);
+  EXPECT_THROW(stan::math::linear_predictor(x_d, MatrixXd(MatrixXd::Zero(3, 2)),
+                                            VectorXd(VectorXd::Zero(3))),
                std::invalid_argument);
 }
 

@@ -174,3 +174,57 @@ def test_gpu_full_size_properties(gpu):
     a, b = 999_000, 1_001_000
     o = po.categorical_logit_lpmf(y[a:b], lin[a:b])
     assert_grad(d[a:b].ravel(), o["d_lin"].ravel(), "d_lin block")
+
+
+# ------------------------------------------- GPU: the matrix products either side of it
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,K,C", [(1, 1, 1), (5, 2, 3), (1531, 37, 5), (4099, 128, 32),
+                                   (3001, 300, 8), (777, 21, 70), (2050, 64, 64),
+                                   (1025, 513, 130)])
+def test_gpu_matrix_product_and_adjoint(gpu, N, K, C):
+    """lin = x beta + alpha^T and its reverse sweep (x^T adj, column sums) against
+    numpy; the DMMA sweeps are fixed-order, so repeats are bit-identical."""
+    mb = gpu
+    rng = np.random.default_rng(N + K + C)
+    x = np.asfortranarray(rng.standard_normal((N, K)))
+    beta = rng.standard_normal((K, C)) / np.sqrt(K)
+    alpha = rng.standard_normal(C)
+    x_d = mb.to_matrix_cuda(x)
+    lin = mb.from_matrix_cuda(mb.lpmf.multiply_matrix(x_d, beta, alpha))
+    want = x @ beta + alpha
+    assert lin.shape == (N, C)
+    assert_grad(lin.ravel(), want.ravel(), "x beta + alpha",
+                scale=(np.abs(x) @ np.abs(beta)).max())
+    lin0 = mb.from_matrix_cuda(mb.lpmf.multiply_matrix(x_d, beta))
+    assert_grad(lin0.ravel(), (x @ beta).ravel(), "x beta",
+                scale=(np.abs(x) @ np.abs(beta)).max())
+    adj = np.asfortranarray(rng.standard_normal((N, C)))
+    adj_d = mb.to_matrix_cuda(adj)
+    g, cs = mb.lpmf.multiply_matrix_adjoint(x_d, adj_d)
+    assert_grad(g.ravel(), (x.T @ adj).ravel(), "x^T adj", scale=(np.abs(x).T @ np.abs(adj)).max())
+    assert_grad(cs, adj.sum(axis=0), "column sums", scale=np.abs(adj).sum(axis=0).max())
+    g2, cs2 = mb.lpmf.multiply_matrix_adjoint(x_d, adj_d)
+    assert np.array_equal(g, g2) and np.array_equal(cs, cs2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,K,C", [(30011, 128, 32), (5003, 40, 7)])
+def test_gpu_unfused_categorical_pipeline_equals_fused_glm(gpu, N, K, C):
+    """multiply_matrix -> categorical_logit_lpmf -> multiply_matrix_adjoint gives the
+    fused categorical GLM's value, d_alpha and d_beta, and the oracle's."""
+    mb = gpu
+    rng = np.random.default_rng(N + C)
+    x = np.asfortranarray(rng.standard_normal((N, K)))
+    beta = np.asfortranarray(rng.standard_normal((K, C)) / np.sqrt(K))
+    alpha = rng.standard_normal(C) * 0.3
+    y = rng.integers(1, C + 1, N).astype(np.int32)
+    x_d, y_d = mb.to_matrix_cuda(x), mb.to_matrix_cuda(y)
+    fused = mb.categorical_logit_glm_lpmf(y_d, x_d, alpha, beta)
+    un = mb.lpmf.categorical_logit_lpmf(y_d, mb.lpmf.multiply_matrix(x_d, beta, alpha))
+    g, cs = mb.lpmf.multiply_matrix_adjoint(x_d, un.d_theta)
+    o = po.categorical_logit_glm(y, x, alpha, beta)
+    for ref_logp, ref_da, ref_db, tag in ((fused.logp, fused.d_alpha, fused.d_beta, "fused"),
+                                          (o["logp"], o["d_alpha"], o["d_beta"], "oracle")):
+        assert_logp(un.logp, ref_logp)
+        assert_grad(cs, np.asarray(ref_da).ravel(), "d_alpha vs " + tag)
+        assert_grad(g.ravel(order="F"), np.asarray(ref_db).ravel(order="F"), "d_beta vs " + tag)
