@@ -228,6 +228,16 @@ int smc_glm_eval_device(int family, const smc_matrix* y, double y_scalar,
                         smc_matrix* d_aux_vec, smc_matrix* d_y_vec,
                         smc_matrix* d_x);
 
+/* The categorical GLM in the same asynchronous form: `params_dev` holds beta
+ * (column-major K x C) followed by alpha (C) on the device; `out_dev` receives
+ * [logp, #rows with a non-finite term, d_alpha[C], d_beta[K x C]] (2 + C + K*C
+ * doubles) for the all-reduce.  No y-range / value checks (the caller checks y
+ * once at upload and inspects out[1]). */
+int smc_categorical_logit_glm_device(const smc_matrix* y, int y_scalar,
+                                     const smc_matrix* x, const double* params_dev,
+                                     int64_t n_classes, unsigned flags,
+                                     double* out_dev, smc_matrix* d_x);
+
 /* ---- the step either side of the GLMs ------------------ */
 /* Models that add terms to the linear predictor before the likelihood form
  * theta on the device and call the un-fused density on it.  These replace what

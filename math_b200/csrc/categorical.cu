@@ -836,7 +836,13 @@ static int launch_cat_impl(CatMode mode, const smc_matrix* y, int y_scalar,
                            const smc_matrix* x, const double* alpha_host,
                            const double* beta_host, int64_t C, unsigned flags,
                            double* logp, double* d_alpha, double* d_beta,
-                           smc_matrix* d_x, const smc_matrix* io) {
+                           smc_matrix* d_x, const smc_matrix* io,
+                           const double* params_user = nullptr,
+                           double* out_user = nullptr) {
+  // params_user / out_user (kCatGlm only): parameters already on the device
+  // (beta K x C, then alpha C) and the packed result [logp, #non-finite,
+  // d_alpha[C], d_beta[K x C]] left on the device, no host synchronisation --
+  // the form the row-sharded multi-GPU driver all-reduces
   Context& cx = ctx();
   CatArgs a;
   memset(&a, 0, sizeof(a));
@@ -859,10 +865,15 @@ static int launch_cat_impl(CatMode mode, const smc_matrix* y, int y_scalar,
   const size_t nparam = (size_t)a.K * a.C + a.C;
   const size_t off_bt = (nparam + 15) & ~(size_t)15;  // 128-byte aligned
   if (int rc = ensure_params(sizeof(double) * (off_bt + (size_t)a.K * C8p + 16))) return rc;
-  if (a.K && mode != kCatAdj)
+  if (params_user) {
+    // (a D2D copy keeps every alignment assumption of the kernels on cx.params_dev)
+    SMC_CUDA(cudaMemcpyAsync(cx.params_dev, params_user, sizeof(double) * nparam,
+                             cudaMemcpyDeviceToDevice, cx.stream));
+  } else if (a.K && mode != kCatAdj)
     SMC_CUDA(cudaMemcpyAsync(cx.params_dev, beta_host, sizeof(double) * a.K * a.C,
                              cudaMemcpyHostToDevice, cx.stream));
-  if (alpha_host)
+  if (params_user) {
+  } else if (alpha_host)
     SMC_CUDA(cudaMemcpyAsync(cx.params_dev + (size_t)a.K * a.C, alpha_host,
                              sizeof(double) * a.C, cudaMemcpyHostToDevice, cx.stream));
   else
@@ -1075,6 +1086,16 @@ static int launch_cat_impl(CatMode mode, const smc_matrix* y, int y_scalar,
     cx.launches += 1;
   }
 
+  if (out_user) {
+    SMC_CUDA(cudaMemcpyAsync(out_user, out_dev, sizeof(double) * (2 + a.C),
+                             cudaMemcpyDeviceToDevice, cx.stream));
+    if (need_beta && a.K > 0)
+      SMC_CUDA(cudaMemcpyAsync(out_user + 2 + a.C, d_beta_dev, sizeof(double) * ndb,
+                               cudaMemcpyDeviceToDevice, cx.stream));
+    else if (ndb)
+      SMC_CUDA(cudaMemsetAsync(out_user + 2 + a.C, 0, sizeof(double) * ndb, cx.stream));
+    return SMC_OK;
+  }
   // results -> host
   if (int rc2 = ensure_out(sizeof(double) * (rs + ndb + 8))) return rc2;
   if (mode == kCatGlm)
@@ -1219,6 +1240,32 @@ extern "C" int smc_linear_predictor_matrix_adjoint(const smc_matrix* x,
     memcpy(colsum, cx.out_host, sizeof(double) * (size_t)C);
   }
   return SMC_OK;
+}
+
+extern "C" int smc_categorical_logit_glm_device(const smc_matrix* y, int y_scalar,
+                                                const smc_matrix* x,
+                                                const double* params_dev,
+                                                int64_t n_classes, unsigned flags,
+                                                double* out_dev, smc_matrix* d_x) {
+  static const char* fn = "categorical_logit_glm_device";
+  if (int rc = ensure_ctx()) return rc;
+  if (!x || x->dtype != SMC_F64)
+    return fail(SMC_ERR_INVALID_ARGUMENT, "%s: x must be an f64 device matrix", fn);
+  const int64_t N = x->rows, K = x->cols, C = n_classes;
+  if (y && (y->dtype != SMC_I32 || y->rows * y->cols != N))
+    return fail(SMC_ERR_INVALID_ARGUMENT, "%s: size of y does not match rows of x", fn);
+  if (C < 1 || !params_dev || !out_dev)
+    return fail(SMC_ERR_INVALID_ARGUMENT, "%s: NULL or empty params_dev / out_dev", fn);
+  if ((flags & SMC_VAR_X)
+      && (!d_x || d_x->dtype != SMC_F64 || d_x->rows != N || d_x->cols != K))
+    return fail(SMC_ERR_INVALID_ARGUMENT, "%s: SMC_VAR_X needs d_x shaped like x", fn);
+  if (N == 0 || C == 1) {  // L73-75: this rank contributes nothing
+    SMC_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double) * (size_t)(2 + C + K * C),
+                             ctx().stream));
+    return SMC_OK;
+  }
+  return launch_cat_impl(kCatGlm, y, y_scalar, x, nullptr, nullptr, C, flags, nullptr,
+                         nullptr, nullptr, d_x, nullptr, params_dev, out_dev);
 }
 
 extern "C" int smc_categorical_logit_glm(const smc_matrix* y, int y_scalar,

@@ -103,3 +103,54 @@ class ShardedGlm:
         if self.ncuts:
             res["d_cuts"] = o[OUT_HEADER + self.K:OUT_HEADER + self.K + self.ncuts].copy()
         return res
+
+
+def cuda_local_eval_categorical(y, x, params_t, n_classes, flags, out_t, d_x=None):
+    """This rank's shard of categorical_logit_glm_lpmf, asynchronous on the current
+    torch stream: params_t = [beta (K x C, column-major), alpha (C)] on the device,
+    out_t = [logp, nonfinite, d_alpha (C), d_beta (K x C)] left on the device."""
+    from .matrix_cuda import MatrixCuda
+    yh, ys = (y.handle, 0) if isinstance(y, MatrixCuda) else (None, int(y))
+    check(lib().smc_categorical_logit_glm_device(
+        yh, ys, x.handle, C.c_void_p(params_t.data_ptr()), int(n_classes), int(flags),
+        C.c_void_p(out_t.data_ptr()), d_x.handle if d_x is not None else None))
+
+
+class ShardedCategoricalGlm(ShardedGlm):
+    """Row-sharded categorical_logit_glm_lpmf (K*C + C parameters
+    broadcast, 2 + C + K*C doubles all-reduced -- 16,418 at K=512, C=32).  Same
+    protocol as ShardedGlm; ``evaluate`` takes [beta.ravel(order="F"), alpha]."""
+
+    def __init__(self, y, x, K, n_classes, flags=0, device="cuda",
+                 local_eval=cuda_local_eval_categorical, dist=None):
+        super().__init__("categorical_logit", y, x, K, flags=flags, device=device,
+                         local_eval=local_eval, dist=dist)
+        t = self.torch
+        self.n_classes = n_classes
+        self.params = t.zeros(K * n_classes + n_classes, dtype=t.float64, device=device)
+        self.out = t.zeros(2 + n_classes + K * n_classes, dtype=t.float64, device=device)
+
+    @staticmethod
+    def pack_params(alpha, beta):
+        return np.concatenate([np.asarray(beta, dtype=np.float64).ravel(order="F"),
+                               np.asarray(alpha, dtype=np.float64).ravel()])
+
+    def evaluate(self, params_host=None, **row_outputs):
+        t = self.torch
+        if self.rank == 0 and params_host is not None:
+            p = t.as_tensor(np.ascontiguousarray(params_host, dtype=np.float64))
+            self.params.copy_(p, non_blocking=True)
+        if self.world > 1:
+            self.dist.broadcast(self.params, src=0)
+        self.local_eval(self.y, self.x, self.params, self.n_classes, self.flags, self.out,
+                        **row_outputs)
+        if self.world > 1:
+            self.dist.all_reduce(self.out, op=self.dist.ReduceOp.SUM)
+        return self.out
+
+    def unpack(self, out_host):
+        o = np.asarray(out_host, dtype=np.float64)
+        Cc, K = self.n_classes, self.K
+        return {"logp": float(o[0]), "nonfinite": float(o[1]),
+                "d_alpha": o[2:2 + Cc].copy(),
+                "d_beta": o[2 + Cc:2 + Cc + K * Cc].reshape((K, Cc), order="F").copy()}

@@ -24,7 +24,7 @@ def main():
     import torch.distributed as dist
     import math_b200 as mb
     from math_b200 import _lib
-    from math_b200.sharded import ShardedGlm, shard_rows
+    from math_b200.sharded import ShardedCategoricalGlm, ShardedGlm, shard_rows
     from oracle import pyoracle as po
     from tests.util import assert_grad, assert_logp, make_inputs
 
@@ -79,6 +79,33 @@ def main():
             assert_logp(res["logp"], o["logp"])
             assert_grad(res["d_beta"], o["d_beta"], "d_beta")
             report[family] = {"rel_logp_vs_single": rel, "rel_dbeta_vs_single": grel}
+    # the GEMM-shaped family: K*C + C parameters broadcast, 2 + C + K*C doubles reduced
+    for K, Cc in ((96, 32), (37, 5)):
+        d = make_inputs("categorical", N, K, seed=12, C=Cc)
+        lo, hi = shard_rows(N, world, rank)
+        x = mb.to_matrix_cuda(np.asfortranarray(d["x"][lo:hi]))
+        y = mb.to_matrix_cuda(np.ascontiguousarray(d["y"][lo:hi]))
+        flags = _lib.VAR_ALPHA | _lib.VAR_BETA
+        glm = ShardedCategoricalGlm(y, x, K, Cc, flags=flags, device=f"cuda:{local}")
+        params = ShardedCategoricalGlm.pack_params(d["alpha"], d["beta"])
+        out = glm.evaluate(params if rank == 0 else None)
+        torch.cuda.synchronize()
+        res = glm.unpack(out.cpu().numpy())
+        if rank == 0:
+            s = mb.categorical_logit_glm_lpmf(mb.to_matrix_cuda(np.ascontiguousarray(d["y"])),
+                                              mb.to_matrix_cuda(np.asfortranarray(d["x"])),
+                                              d["alpha"], d["beta"])
+            rel = abs(res["logp"] - s.logp) / abs(s.logp)
+            grel = np.abs(res["d_beta"] - s.d_beta).max() / np.abs(s.d_beta).max()
+            arel = np.abs(res["d_alpha"] - s.d_alpha).max() / np.abs(s.d_alpha).max()
+            assert rel < 1e-12 and grel < 1e-12 and arel < 1e-12, (K, Cc, rel, grel, arel)
+            assert res["nonfinite"] == 0.0
+            o = po.categorical_logit_glm(d["y"], d["x"], d["alpha"], d["beta"])
+            assert_logp(res["logp"], o["logp"])
+            assert_grad(res["d_alpha"], o["d_alpha"], "d_alpha")
+            assert_grad(res["d_beta"].ravel(order="F"), o["d_beta"].ravel(order="F"), "d_beta")
+            report[f"categorical_logit_K{K}_C{Cc}"] = {"rel_logp_vs_single": rel,
+                                                       "rel_dbeta_vs_single": grel}
     dist.barrier()
     if rank == 0:
         print("MULTI_GPU_OK " + json.dumps({"world": world, "cases": report}), flush=True)

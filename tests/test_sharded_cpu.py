@@ -12,7 +12,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from math_b200 import _lib
-from math_b200.sharded import ShardedGlm, packed_size, shard_rows
+from math_b200.sharded import ShardedCategoricalGlm, ShardedGlm, packed_size, shard_rows
 from oracle import pyoracle as po
 from tests.util import assert_grad, assert_logp, make_inputs
 
@@ -47,11 +47,31 @@ def _oracle_local_eval(family, y, x, alpha, aux, params_t, ncuts, flags, out_t, 
     out_t.copy_(torch.from_numpy(out))
 
 
+def _oracle_local_eval_categorical(y, x, params_t, n_classes, flags, out_t, **_):
+    K, Cc = x.shape[1], n_classes
+    p = params_t.numpy()
+    beta = p[:K * Cc].reshape((K, Cc), order="F")
+    alpha = p[K * Cc:]
+    r = po.categorical_logit_glm(y, x, alpha, beta, flags)
+    out = np.concatenate([[r["logp"], 0.0], r["d_alpha"], r["d_beta"].ravel(order="F")])
+    out_t.copy_(torch.from_numpy(out))
+
+
 def _worker(rank, world, port, family, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         N, K = 1001, 13
+        if family == "categorical_logit":
+            d = make_inputs("categorical", N, K, seed=5, C=6)
+            lo, hi = shard_rows(N, world, rank)
+            glm = ShardedCategoricalGlm(d["y"][lo:hi], d["x"][lo:hi], K, 6,
+                                        flags=po.VAR_ALPHA | po.VAR_BETA, device="cpu",
+                                        local_eval=_oracle_local_eval_categorical)
+            params = ShardedCategoricalGlm.pack_params(d["alpha"], d["beta"])
+            res = glm.unpack(glm.evaluate(params if rank == 0 else None).numpy())
+            q.put(res if rank == 0 else {"logp": res["logp"]})
+            return
         if family == "poisson_log":
             d = make_inputs("poisson", N, K, seed=3)
             params, ncuts = d["beta"], 0
@@ -83,7 +103,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("family", ["poisson_log", "ordered_logistic"])
+@pytest.mark.parametrize("family", ["poisson_log", "ordered_logistic", "categorical_logit"])
 def test_two_ranks_match_single(family):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -99,7 +119,12 @@ def test_two_ranks_match_single(family):
     other = next(g for g in got if "d_beta" not in g)
     assert full["logp"] == other["logp"]  # every rank holds the reduced result
     N, K = 1001, 13
-    if family == "poisson_log":
+    if family == "categorical_logit":
+        d = make_inputs("categorical", N, K, seed=5, C=6)
+        ref = po.categorical_logit_glm(d["y"], d["x"], d["alpha"], d["beta"])
+        assert_grad(full["d_alpha"], ref["d_alpha"], "d_alpha")
+        assert full["d_beta"].shape == (K, 6)
+    elif family == "poisson_log":
         d = make_inputs("poisson", N, K, seed=3)
         ref = po.poisson_log_glm(d["y"], d["x"], 0.1, d["beta"])
     else:
@@ -107,5 +132,6 @@ def test_two_ranks_match_single(family):
         ref = po.ordered_logistic_glm(d["y"], d["x"], d["beta"], d["cuts"])
         assert_grad(full["d_cuts"], ref["d_cuts"], "d_cuts")
     assert_logp(full["logp"], ref["logp"])
-    assert_grad(full["d_beta"], ref["d_beta"], "d_beta")
+    assert_grad(np.ravel(full["d_beta"], order="F"), np.ravel(ref["d_beta"], order="F"),
+                "d_beta")
     assert packed_size(K, 5) == _lib.OUT_HEADER + K + 5
