@@ -25,6 +25,8 @@
 #include <cstring>
 #include <vector>
 
+#include <limits>
+
 #include "smc_internal.h"
 #include "tma_utils.cuh"
 
@@ -58,6 +60,7 @@ struct CatArgs {
   // pass 1 as a plain matrix product (smc_linear_predictor_matrix): the epilogue
   // stores lin = x beta + alpha^T into T (classes < C only) and stops
   int lin_only;
+  int dx_acc;  // cat_dx_kernel adds to d_x (class blocks after the first of a wide C)
 };
 
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
@@ -755,7 +758,8 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int c = 0; c < CMAX; ++c)
       if (c < a.C) v = fma(t[c], __ldg(a.beta + (size_t)c * a.K + k), v);
-    a.d_x[(size_t)k * a.ld_dx + row] = v;
+    double* dst = a.d_x + (size_t)k * a.ld_dx + row;
+    *dst = a.dx_acc ? *dst + v : v;
   }
 }
 
@@ -1242,6 +1246,78 @@ extern "C" int smc_linear_predictor_matrix_adjoint(const smc_matrix* x,
   return SMC_OK;
 }
 
+// More classes than one launch of the DMMA kernels holds (C8 > 64): the same
+// evaluation composed from the stand-alone pieces -- lin = x beta + alpha^T in
+// class blocks of 64, the row-wise categorical density on lin (value and
+// T = one-hot - softmax), d_beta = x^T T and d_alpha = column sums of T in class
+// blocks, d_x = T beta^T accumulated over the blocks.  Two sweeps over x per block.
+static int categorical_wide(const char* fn, const smc_matrix* y, int y_scalar,
+                            const smc_matrix* x, const double* alpha, const double* beta,
+                            int64_t C, unsigned flags, double* logp, double* d_alpha,
+                            double* d_beta, smc_matrix* d_x) {
+  Context& cx = ctx();
+  const int64_t N = x->rows, K = x->cols;
+  const int64_t ld = (N + 15) & ~(int64_t)15;
+  const size_t bytes = sizeof(double) * (size_t)ld * C;
+  void *lin_p = nullptr, *t_p = nullptr;
+  if (int rc = cache_alloc(&lin_p, bytes)) return rc;
+  if (int rc = cache_alloc(&t_p, bytes)) {
+    cache_free(lin_p, bytes);
+    return rc;
+  }
+  smc_matrix lin, T;
+  lin.data = lin_p;
+  lin.rows = N;
+  lin.cols = C;
+  lin.ld = ld;
+  lin.dtype = SMC_F64;
+  lin.device = cx.device;
+  T = lin;
+  T.data = t_p;
+  int rc = smc_linear_predictor_matrix(x, beta, C, alpha, &lin);
+  if (!rc) rc = smc_categorical_logit_lpmf(y, y_scalar, &lin, SMC_VAR_ALPHA, logp, &T);
+  if (rc == SMC_ERR_DOMAIN) {
+    // a non-finite linear predictor: the caller's lazy checks name the operand
+    *logp = std::numeric_limits<double>::quiet_NaN();
+    rc = SMC_OK;
+  } else if (!rc) {
+    const bool need_alpha = (flags & SMC_VAR_ALPHA) && d_alpha;
+    const bool need_beta = (flags & SMC_VAR_BETA) && d_beta;
+    if (need_alpha || need_beta)
+      rc = smc_linear_predictor_matrix_adjoint(x, &T, need_beta ? d_beta : nullptr,
+                                               need_alpha ? d_alpha : nullptr);
+    if (!rc && (flags & SMC_VAR_X) && d_x && K > 0) {
+      rc = ensure_params(sizeof(double) * (size_t)K * C);
+      if (!rc && cudaMemcpyAsync(cx.params_dev, beta, sizeof(double) * (size_t)K * C,
+                                 cudaMemcpyHostToDevice, cx.stream) != cudaSuccess)
+        rc = fail(SMC_ERR_CUDA, "%s: uploading beta failed", fn);
+      d_x->version++;
+      for (int64_t c0 = 0; !rc && c0 < C; c0 += kCatBlock) {
+        CatArgs a;
+        memset(&a, 0, sizeof(a));
+        a.N = N;
+        a.K = (int)K;
+        a.C = (int)(C - c0 < kCatBlock ? C - c0 : kCatBlock);
+        a.T = static_cast<double*>(T.data) + (size_t)c0 * ld;
+        a.ldT = ld;
+        a.beta = cx.params_dev + (size_t)c0 * K;
+        a.d_x = static_cast<double*>(d_x->data);
+        a.ld_dx = d_x->ld;
+        a.dx_acc = c0 > 0;
+        cat_dx_kernel<64><<<(int)((N + 255) / 256), 256, 0, cx.stream>>>(a);
+        if (cudaGetLastError() != cudaSuccess)
+          rc = fail(SMC_ERR_CUDA, "%s: d_x launch failed", fn);
+        cx.launches += 1;
+      }
+      if (!rc && cudaStreamSynchronize(cx.stream) != cudaSuccess)
+        rc = fail(SMC_ERR_CUDA, "%s: stream synchronise failed", fn);
+    }
+  }
+  cache_free(lin_p, bytes);
+  cache_free(t_p, bytes);
+  return rc;
+}
+
 extern "C" int smc_categorical_logit_glm_device(const smc_matrix* y, int y_scalar,
                                                 const smc_matrix* x,
                                                 const double* params_dev,
@@ -1259,6 +1335,10 @@ extern "C" int smc_categorical_logit_glm_device(const smc_matrix* y, int y_scala
   if ((flags & SMC_VAR_X)
       && (!d_x || d_x->dtype != SMC_F64 || d_x->rows != N || d_x->cols != K))
     return fail(SMC_ERR_INVALID_ARGUMENT, "%s: SMC_VAR_X needs d_x shaped like x", fn);
+  if (((C + 7) & ~(int64_t)7) > kCatBlock)
+    return fail(SMC_ERR_UNSUPPORTED,
+                "%s: more than 64 classes take the synchronous smc_categorical_logit_glm",
+                fn);
   if (N == 0 || C == 1) {  // L73-75: this rank contributes nothing
     SMC_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double) * (size_t)(2 + C + K * C),
                              ctx().stream));
@@ -1302,8 +1382,12 @@ extern "C" int smc_categorical_logit_glm(const smc_matrix* y, int y_scalar,
   if ((flags & SMC_PROPTO) && !(flags & (SMC_VAR_X | SMC_VAR_ALPHA | SMC_VAR_BETA)))
     return SMC_OK;  // L80-82
   double lp = 0.0;
-  if (int rc = launch_categorical(y, y_scalar, x, alpha, beta, C, flags, &lp, d_alpha,
+  if (((C + 7) & ~(int64_t)7) > kCatBlock) {
+    if (int rc = categorical_wide(fn, y, y_scalar, x, alpha, beta, C, flags, &lp, d_alpha,
                                   d_beta, d_x))
+      return rc;
+  } else if (int rc = launch_categorical(y, y_scalar, x, alpha, beta, C, flags, &lp,
+                                         d_alpha, d_beta, d_x))
     return rc;
   if (!std::isfinite(lp)) {  // lazy checks, L122-126
     for (int64_t i = 0; i < K * C; ++i)

@@ -151,6 +151,19 @@ TEST(CudaCategoricalLogitGLM, big) {
   compare_cpu_cuda_prim_rev(f_propto, std::make_tuple(DEV, DEV, HOST, HOST), y, x, alpha, beta);
 }
 
+TEST(CudaCategoricalLogitGLM, more_than_64_classes) {
+  // beyond one launch of the DMMA kernels: composed from class blocks of 64
+  int N = 307, M = 23, C = 97;
+  srand(12);
+  vector<int> y(N);
+  for (int i = 0; i < N; i++) y[i] = (i * 11) % C + 1;
+  MatrixXd x = MatrixXd::Random(N, M);
+  MatrixXd beta = MatrixXd::Random(M, C);
+  VectorXd alpha = VectorXd::Random(C);
+  compare_cpu_cuda_prim_rev(f, std::make_tuple(DEV, DEV, HOST, HOST), y, x, alpha, beta);
+  compare_cpu_cuda_prim_rev(f_propto, std::make_tuple(DEV, DEV, HOST, HOST), y, x, alpha, beta);
+}
+
 TEST(CudaCategoricalLogitGLM, config5a_shape) {
   // BASELINE.json configs[4] (categorical part) at reduced N: K = 512, C = 32
   int N = 4099, M = 512, C = 32;

@@ -304,7 +304,8 @@ def test_determinism(gpu):
 
 @pytest.mark.parametrize("N,K,C", [(5, 2, 3), (153, 71, 43), (1000, 1, 2), (4099, 64, 8),
                                    (3000, 512, 32), (2000, 100, 64), (50, 600, 5),
-                                   (700, 40, 17)])
+                                   (700, 40, 17), (1531, 37, 65), (777, 21, 130),
+                                   (300, 5, 200)])
 def test_categorical(gpu, N, K, C):
     d = make_inputs("categorical", N, K, seed=N + 5 * C, C=C)
     x = gpu.to_matrix_cuda(d["x"])
