@@ -763,6 +763,152 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// d_x = T beta^T on the FP64 tensor pipe, computed transposed so that a lane ends
+// up with two consecutive ROWS of one attribute (one 16-byte store):
+//   D'[attribute][row] = sum_c beta[attribute][c] T[row][c]
+//   A (8 x 4) = beta^T tile from shared memory ([attribute][C8 + 4], conflict-free),
+//   B (4 x 8) = T^T tile, held in registers for the warp's 32 rows across every
+//   attribute tile of the CTA's chunk.
+// CTA (bx, by): row blocks bx, bx + gridDim.x, ... x attribute chunk by.  Written
+// once, coalesced in 64-byte runs per attribute; N*K*8 bytes of stores against
+// 2 N K C flops: store-bound for C <= ~40, DMMA-bound above.
+constexpr int kDxRowsPerWarp = 32;
+template <int NT>
+__global__ void __launch_bounds__(kCatThreads, 1)
+    cat_dx_dmma_kernel(const __grid_constant__ CatArgs a, int kch) {
+  extern __shared__ __align__(16) double dx_bs[];  // [kch][C8 + 4]
+  constexpr int KS = 2 * NT;                       // k-steps of 4 classes
+  const int C8p = a.C8 + 4;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = lane >> 2, tig = lane & 3;
+  const int kbase = blockIdx.y * kch;
+  for (int idx = tid; idx < kch * C8p; idx += kCatThreads) {
+    const int k = idx / C8p;
+    dx_bs[idx] = kbase + k < a.K ? a.beta_t[(size_t)kbase * C8p + idx] : 0.0;
+  }
+  __syncthreads();
+  int ktiles = (min(kch, a.K - kbase) + 7) >> 3;
+  const int64_t rows_per_cta = (int64_t)kCatWarps * kDxRowsPerWarp;
+  for (int64_t rb = blockIdx.x; rb * rows_per_cta < a.N; rb += gridDim.x) {
+    const int64_t i0 = rb * rows_per_cta + (int64_t)warp * kDxRowsPerWarp;
+    if (i0 >= a.N) continue;
+    double tf[4][KS];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      const int64_t r = i0 + 8 * mt + grp;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const int c = 4 * ks + tig;
+        tf[mt][ks] = (r < a.N && c < a.C) ? __ldg(a.T + (size_t)c * a.ldT + r) : 0.0;
+      }
+    }
+    for (int kt = 0; kt < ktiles; ++kt) {
+      const double* bp = dx_bs + (size_t)(8 * kt + grp) * C8p + tig;
+      double af[KS];
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) af[ks] = bp[4 * ks];
+      double acc[4][2];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) acc[mt][0] = acc[mt][1] = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) dmma(acc[mt][0], acc[mt][1], af[ks], tf[mt][ks]);
+      const int k = kbase + 8 * kt + grp;
+      if (k < a.K) {
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+          const int64_t r = i0 + 8 * mt + 2 * tig;
+          double* dst = a.d_x + (size_t)k * a.ld_dx + r;
+          if (r + 1 < a.N) {
+            double2 v = make_double2(acc[mt][0], acc[mt][1]);
+            if (a.dx_acc) {
+              const double2 o = *reinterpret_cast<const double2*>(dst);
+              v.x += o.x;
+              v.y += o.y;
+            }
+            *reinterpret_cast<double2*>(dst) = v;
+          } else if (r < a.N) {
+            *dst = a.dx_acc ? *dst + acc[mt][0] : acc[mt][0];
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int NT>
+static int run_dx_dmma(const CatArgs& a, dim3 grid, int kch, size_t smem) {
+  static size_t attr[16] = {};
+  Context& c = ctx();
+  if (attr[c.device & 15] < smem) {
+    SMC_CUDA(cudaFuncSetAttribute(cat_dx_dmma_kernel<NT>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr[c.device & 15] = smem;
+  }
+  cat_dx_dmma_kernel<NT><<<grid, kCatThreads, smem, c.stream>>>(a, kch);
+  SMC_CUDA(cudaGetLastError());
+  return SMC_OK;
+}
+
+// d_x = T beta^T (+= when a.dx_acc).  a.beta_t must point at K x (C8 + 4) doubles of
+// device scratch; it is filled here unless `beta_t_ready`.
+static int run_cat_dx(const CatArgs& a, bool beta_t_ready) {
+  Context& cx = ctx();
+  const char* force = getenv("SMC_CAT_DX_FMA");
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(a.d_x) & 15) == 0 && (a.ld_dx & 1) == 0;
+  // (8 classes or fewer: two DMMA k-steps per attribute tile do not pay for the
+  // fragment loads -- the plain-FMA kernel is faster there, 1.18 vs 1.72 ms at
+  // N=4e6, K=128, C=8; from 9 classes on it falls off a cliff, 26.3 vs 2.06 ms at
+  // N=2e6, K=512, C=32)
+  if (!vec_ok || a.C <= 8 || (force && force[0] == '1')) {
+    const int g3 = (int)((a.N + 255) / 256);
+    if (a.C <= 8)
+      cat_dx_kernel<8><<<g3, 256, 0, cx.stream>>>(a);
+    else if (a.C <= 16)
+      cat_dx_kernel<16><<<g3, 256, 0, cx.stream>>>(a);
+    else if (a.C <= 32)
+      cat_dx_kernel<32><<<g3, 256, 0, cx.stream>>>(a);
+    else
+      cat_dx_kernel<64><<<g3, 256, 0, cx.stream>>>(a);
+    SMC_CUDA(cudaGetLastError());
+    cx.launches += 1;
+    return SMC_OK;
+  }
+  const int C8p = a.C8 + 4;
+  if (!beta_t_ready) {
+    const int64_t nbt = (int64_t)a.K * C8p;
+    cat_beta_transpose_kernel<<<(int)((nbt + 255) / 256), 256, 0, cx.stream>>>(
+        a.beta, a.K, a.C, C8p, const_cast<double*>(a.beta_t));
+    SMC_CUDA(cudaGetLastError());
+    cx.launches += 1;
+  }
+  int kch = (int)((160 * 1024) / ((size_t)C8p * 8)) & ~7;
+  const int k8 = (a.K + 7) & ~7;
+  if (kch > k8) kch = k8;
+  const int nby = (a.K + kch - 1) / kch;
+  const int64_t nrb = (a.N + kCatWarps * kDxRowsPerWarp - 1) / (kCatWarps * kDxRowsPerWarp);
+  int nbx = cx.sm_count / nby;
+  if (nbx < 1) nbx = 1;
+  if (nbx > nrb) nbx = (int)nrb;
+  const size_t smem = (size_t)kch * C8p * 8;
+  const dim3 grid(nbx, nby);
+  int rc;
+  switch (a.C8 / 8) {
+    case 1: rc = run_dx_dmma<1>(a, grid, kch, smem); break;
+    case 2: rc = run_dx_dmma<2>(a, grid, kch, smem); break;
+    case 3: rc = run_dx_dmma<3>(a, grid, kch, smem); break;
+    case 4: rc = run_dx_dmma<4>(a, grid, kch, smem); break;
+    case 5: rc = run_dx_dmma<5>(a, grid, kch, smem); break;
+    case 6: rc = run_dx_dmma<6>(a, grid, kch, smem); break;
+    case 7: rc = run_dx_dmma<7>(a, grid, kch, smem); break;
+    default: rc = run_dx_dmma<8>(a, grid, kch, smem); break;
+  }
+  if (rc) return rc;
+  cx.launches += 1;
+  return SMC_OK;
+}
+
 template <int NT>
 static int run_lin(const CatArgs& a, int grid, size_t smem) {
   static size_t attr[16] = {};
@@ -1077,17 +1223,7 @@ static int launch_cat_impl(CatMode mode, const smc_matrix* y, int y_scalar,
     cx.launches += 1;
   }
   if (need_dx && a.K > 0) {
-    const int g3 = (int)((a.N + 255) / 256);
-    if (a.C <= 8)
-      cat_dx_kernel<8><<<g3, 256, 0, cx.stream>>>(a);
-    else if (a.C <= 16)
-      cat_dx_kernel<16><<<g3, 256, 0, cx.stream>>>(a);
-    else if (a.C <= 32)
-      cat_dx_kernel<32><<<g3, 256, 0, cx.stream>>>(a);
-    else
-      cat_dx_kernel<64><<<g3, 256, 0, cx.stream>>>(a);
-    SMC_CUDA(cudaGetLastError());
-    cx.launches += 1;
+    if (int rc2 = run_cat_dx(a, lin_tma)) return rc2;
   }
 
   if (out_user) {
@@ -1287,7 +1423,8 @@ static int categorical_wide(const char* fn, const smc_matrix* y, int y_scalar,
       rc = smc_linear_predictor_matrix_adjoint(x, &T, need_beta ? d_beta : nullptr,
                                                need_alpha ? d_alpha : nullptr);
     if (!rc && (flags & SMC_VAR_X) && d_x && K > 0) {
-      rc = ensure_params(sizeof(double) * (size_t)K * C);
+      const size_t off_bt = ((size_t)K * C + 15) & ~(size_t)15;
+      rc = ensure_params(sizeof(double) * (off_bt + (size_t)K * (kCatBlock + 4) + 16));
       if (!rc && cudaMemcpyAsync(cx.params_dev, beta, sizeof(double) * (size_t)K * C,
                                  cudaMemcpyHostToDevice, cx.stream) != cudaSuccess)
         rc = fail(SMC_ERR_CUDA, "%s: uploading beta failed", fn);
@@ -1298,16 +1435,15 @@ static int categorical_wide(const char* fn, const smc_matrix* y, int y_scalar,
         a.N = N;
         a.K = (int)K;
         a.C = (int)(C - c0 < kCatBlock ? C - c0 : kCatBlock);
+        a.C8 = (a.C + 7) & ~7;
+        a.beta_t = cx.params_dev + off_bt;
         a.T = static_cast<double*>(T.data) + (size_t)c0 * ld;
         a.ldT = ld;
         a.beta = cx.params_dev + (size_t)c0 * K;
         a.d_x = static_cast<double*>(d_x->data);
         a.ld_dx = d_x->ld;
         a.dx_acc = c0 > 0;
-        cat_dx_kernel<64><<<(int)((N + 255) / 256), 256, 0, cx.stream>>>(a);
-        if (cudaGetLastError() != cudaSuccess)
-          rc = fail(SMC_ERR_CUDA, "%s: d_x launch failed", fn);
-        cx.launches += 1;
+        rc = run_cat_dx(a, false);
       }
       if (!rc && cudaStreamSynchronize(cx.stream) != cudaSuccess)
         rc = fail(SMC_ERR_CUDA, "%s: stream synchronise failed", fn);
