@@ -168,6 +168,11 @@ int ensure_scratch(size_t bytes) {
 }
 
 // ---------------------------------------------------------------- kernels
+// Element-wise sweeps over a column-major matrix with a leading dimension.  The
+// read-modify-write ones use a flat index: its 64-bit division hides under three
+// memory accesses per element (the N x K reverse sweep x.adj += lp.adj * d_x of an
+// autodiff design matrix: 4.9 ms = 6.3 TB/s at N=1e7, K=128; a 2-D grid measured
+// 5 % slower).
 __global__ void axpy_kernel(double* __restrict__ y, int64_t ldy,
                             const double* __restrict__ x, int64_t ldx,
                             int64_t rows, int64_t cols, double a) {
@@ -189,14 +194,17 @@ __global__ void add_scalar_kernel(double* __restrict__ y, int64_t ldy, int64_t r
   }
 }
 
+// The read-only scan is instruction-bound with a flat index (2.57 ms at N=1e7,
+// K=128): blockIdx.y strides the columns, the threads of blockIdx.x the rows
+// (1.42 ms = 7.2 TB/s).
 __global__ void all_finite_kernel(const double* __restrict__ x, int64_t ld,
                                   int64_t rows, int64_t cols, int* bad) {
-  const int64_t total = rows * cols;
   int local = 0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t c = i / rows, r = i - c * rows;
-    if (!isfinite(x[c * ld + r])) local = 1;
+  for (int64_t c = blockIdx.y; c < cols; c += gridDim.y) {
+    const double* xc = x + c * ld;
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows;
+         r += (int64_t)gridDim.x * blockDim.x)
+      if (!isfinite(xc[r])) local = 1;
   }
   if (__any_sync(0xffffffffu, local) && (threadIdx.x & 31) == 0) *bad = 1;
 }
@@ -239,6 +247,19 @@ static inline int grid_for(int64_t total, int threads) {
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;
+}
+
+// Grid of the 2-D element-wise kernels: row chunks x columns, at most 16 CTAs per SM.
+static inline dim3 grid2d_for(int64_t rows, int64_t cols, int threads) {
+  const int64_t cap = (int64_t)t_ctx.sm_count * 16;
+  int64_t gx = (rows + threads - 1) / threads;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  int64_t gy = cap / gx;
+  if (gy > cols) gy = cols;
+  if (gy > 65535) gy = 65535;
+  if (gy < 1) gy = 1;
+  return dim3((unsigned)gx, (unsigned)gy);
 }
 
 static inline size_t elem_size(int dtype) { return dtype == SMC_F64 ? 8 : 4; }
@@ -492,7 +513,7 @@ int smc_matrix_all_finite(const smc_matrix* m, int* all_finite) {
   if (int rc = ensure_out(4096)) return rc;
   int* flag = reinterpret_cast<int*>(ctx().out_host);
   *flag = 0;
-  all_finite_kernel<<<grid_for(total, 256), 256, 0, ctx().stream>>>(
+  all_finite_kernel<<<grid2d_for(m->rows, m->cols, 256), 256, 0, ctx().stream>>>(
       static_cast<const double*>(m->data), m->ld, m->rows, m->cols, flag);
   SMC_CUDA(cudaGetLastError());
   SMC_CUDA(cudaStreamSynchronize(ctx().stream));
