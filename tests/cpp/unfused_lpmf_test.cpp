@@ -388,6 +388,41 @@ TEST(CudaUnfused, matrix_product_then_categorical_matches_the_fused_glm) {
       stan::math::recover_memory();
     }
   }
+  // the other host containers: var_value<MatrixXd> weights, a row vector of var and a
+  // var_value<VectorXd> as intercepts, data weights with autodiff intercepts
+  {
+    const int N = 257, K = 9, C = 4;
+    srand(21);
+    MatrixXd x = MatrixXd::Random(N, K), beta = MatrixXd::Random(K, C);
+    VectorXd alpha = VectorXd::Random(C);
+    vector<int> y(N);
+    for (int i = 0; i < N; ++i) y[i] = 1 + (i * 3) % C;
+    matrix_cuda<double> x_d(x);
+    matrix_cuda<int> y_d(y);
+    stan::math::var_value<MatrixXd> b1(beta);
+    Matrix<var, 1, Dynamic> a1 = alpha.transpose();
+    stan::math::var_value<VectorXd> a2(alpha);
+    Matrix<var, Dynamic, 1> a3 = alpha, a_ref = alpha;
+    Matrix<var, Dynamic, Dynamic> b_ref = beta;
+    var lp1 = stan::math::categorical_logit_lpmf(y_d, stan::math::linear_predictor(x_d, b1, a1));
+    var lp2 = stan::math::categorical_logit_lpmf(y_d, stan::math::linear_predictor(x_d, beta, a2));
+    var lp3 = stan::math::categorical_logit_lpmf<true>(
+        y_d, stan::math::linear_predictor(x_d, beta, a3));
+    var lp_ref = stan::math::categorical_logit_glm_lpmf(y, x, a_ref, b_ref);
+    (lp1 + lp2 + lp3 + lp_ref).grad();
+    expect_close("value 1", lp1.val(), lp_ref.val(), kRelLogp, 0);
+    expect_close("value 2", lp2.val(), lp_ref.val(), kRelLogp, 0);
+    expect_close("value 3", lp3.val(), lp_ref.val(), kRelLogp, 0);
+    const double sa = a_ref.adj().cwiseAbs().maxCoeff(), sb = b_ref.adj().cwiseAbs().maxCoeff();
+    for (int c = 0; c < C; ++c) {
+      expect_close("row-vector d_alpha", a1[c].adj(), a_ref[c].adj(), kRelGrad, sa);
+      expect_close("var_value d_alpha", a2.adj()[c], a_ref[c].adj(), kRelGrad, sa);
+      expect_close("propto d_alpha", a3[c].adj(), a_ref[c].adj(), kRelGrad, sa);
+      for (int k = 0; k < K; ++k)
+        expect_close("var_value d_beta", b1.adj()(k, c), b_ref(k, c).adj(), kRelGrad, sb);
+    }
+    stan::math::recover_memory();
+  }
   matrix_cuda<double> x_d(MatrixXd(MatrixXd::Zero(4, 3)));
   EXPECT_THROW(stan::math::multiply(x_d, MatrixXd(MatrixXd::Zero(4, 2))),
                std::invalid_argument);
