@@ -41,7 +41,7 @@ constexpr int kCutsPerThread = 4;
 constexpr int kFastCuts = 16;  // up to this many cut points: lane-private d_cuts slots
 
 __host__ __device__ inline int link_tab_doubles(int fam, int ncuts, int tab_n) {
-  if (fam == kOrdered) return 4 * (ncuts + 1);
+  if (fam == kOrdered) return 6 * (ncuts + 1);
   if (fam == kNegBinomial) return 2 * tab_n;
   return 0;
 }
@@ -151,8 +151,10 @@ __global__ void __launch_bounds__(256, 1)
   tab.cuts = cuts_s;
   if constexpr (FAM == kOrdered) {
     tab.cls = tab_s;
-    for (int c = 1 + tid; c <= a.ncuts + 1; c += blockDim.x)
+    for (int c = 1 + tid; c <= a.ncuts + 1; c += blockDim.x) {
       ordered_class_entry(params + a.K, a.ncuts, c, tab_s + 4 * (c - 1));
+      ordered_class_l1m(tab_s + 4 * (c - 1), tab_s + 4 * (a.ncuts + 1) + 2 * (c - 1));
+    }
   }
   if constexpr (FAM == kNegBinomial) {
     if (a.tab_n > 0) {

@@ -53,10 +53,20 @@ struct FusedArgs {
 
 // Per-CTA lookup tables that take row-independent transcendentals out of the
 // per-row link (values are produced by the very same expressions, so results
-// are bit-identical to evaluating them per row):
+// are bit-identical to evaluating them per row -- except l1m, see below):
 //   ordered   cls[4 c' .. 4 c' + 3], c' = class - 1:  c1, c2 (the two cut points
 //             of the class, +-inf at the ends), ed / (ed - 1), 1 / (1 - ed) with
 //             ed = exp(c2 - c1)          (ordered_logistic_glm_lpmf.hpp L108-121, L165-174)
+//             cls[4 C + 2 c' .. + 1]:  l1m = log1m_exp(c2 - c1) and the bound `lim`
+//             on |cut1| under which a row may use it.  prim evaluates
+//             log1m_exp(cut1 - cut2) per row (L160) with cut1 - cut2 =
+//             (loc - c1) - (loc - c2): mathematically c2 - c1 for every row of the
+//             class, numerically off by up to 2 ulp(loc).  The table value is the
+//             exact-argument one; a row takes it only while that rounding cannot
+//             move the term by more than 5e-13 (|loc| <= 1e3 (c1 - c2), enforced
+//             through |cut1| <= lim = 1e3 (c1 - c2) - |c1|), else it evaluates the
+//             term per row as prim does.  Saves two of the six transcendentals of
+//             an interior-class row.
 //   neg-binomial (scalar phi)  lg[y] = lgamma(y + phi), dg[y] = digamma(y + phi)
 //             for integer y < tab_n     (neg_binomial_2_log_glm_lpmf.hpp L189-195, L235-244)
 // Null pointers mean "evaluate per row" (the general two-pass path).
@@ -80,6 +90,15 @@ __device__ __forceinline__ void ordered_class_entry(const double* cuts, int ncut
   e[1] = c2;
   e[2] = ed / (ed - 1.0);
   e[3] = 1.0 / (1.0 - ed);
+}
+
+// l1m entry of one class (see LinkTab): e = the class's c1, c2 from
+// ordered_class_entry; out[0] = log1m_exp(c2 - c1), out[1] = lim.
+__device__ __forceinline__ void ordered_class_l1m(const double* e, double* out) {
+  const double c1 = e[0], c2 = e[1];
+  const bool interior = isfinite(c1) && isfinite(c2);
+  out[0] = interior ? log1m_exp(c2 - c1) : 0.0;
+  out[1] = interior ? 1e3 * (c1 - c2) - fabs(c1) : -1.0;  // end classes: term unused
 }
 
 // The first and last class of the ordered link carry +-inf cut points
@@ -320,8 +339,17 @@ __device__ __forceinline__ void link_lp(const FusedArgs& a, const LinkStash<FAM>
       acc.lp += A;
     else if (st.c == C)
       acc.lp += B;
-    else
-      acc.lp += B + log1m_exp(cut1 - cut2) + A;  // L141-161
+    else {
+      double l1m;  // L160: a class constant up to the rounding of cut1 - cut2
+      bool per_row = true;
+      if (tab.cls) {
+        const double2 w = *reinterpret_cast<const double2*>(tab.cls + 4 * C + 2 * (st.c - 1));
+        per_row = !(fabs(cut1) <= w.y);
+        l1m = w.x;
+      }
+      if (per_row) l1m = log1m_exp(cut1 - cut2);
+      acc.lp += B + l1m + A;  // L141-161
+    }
   }
 }
 

@@ -155,6 +155,30 @@ def test_ordered(gpu, N, K, C):
         assert_grad(r.d_x.to_host(), o["d_x"], "d_x")
 
 
+@pytest.mark.parametrize("cuts,scale", [
+    ([-1.0, -1.0 + 1e-9, 0.5, 0.5 + 1e-6], 1.0),   # gaps far below the table's limit
+    ([-0.8, -0.79, 0.3, 0.31, 1.0], 8.0),           # gap 1e-2: |loc| up to ~30 crosses it
+    ([-2.0, -0.5, 0.4, 1.7], 40.0),                 # wide gaps, saturated predictors
+])
+def test_ordered_interior_class_term(gpu, cuts, scale):
+    """log1m_exp(cut1 - cut2) of an interior class (L160) comes from a per-class table
+    only while the rounding of (loc - c1) - (loc - c2) cannot matter; rows beyond the
+    table's limit (close cut points, large |loc|) evaluate it per row as prim does.
+    Both routes against the oracle, which follows prim per row."""
+    N, K = 20011, 64
+    cuts = np.asarray(cuts)
+    d = make_inputs("ordered", N, K, seed=7, C=len(cuts) + 1)
+    beta = d["beta"] * scale
+    x = gpu.to_matrix_cuda(d["x"])
+    y = gpu.to_matrix_cuda(d["y"])
+    r = gpu.ordered_logistic_glm_lpmf(y, x, beta, cuts, var=("beta", "cuts"))
+    o = po.ordered_logistic_glm(d["y"], d["x"], beta, cuts, flags=_flags(False, ["beta", "aux"]))
+    assert o["rc"] == 0 and np.isfinite(o["logp"])
+    assert_logp(r.logp, o["logp"])
+    assert_grad(r.d_beta, o["d_beta"], "d_beta")
+    assert_grad(r.d_aux, o["d_cuts"], "d_cuts", scale=np.abs(o["d_beta"]).max() * 1e-2)
+
+
 def test_zero_instances_and_errors(gpu):
     """zero_instances + error_checking cases of the reference's device tests."""
     x0 = gpu.MatrixCuda(0, 2)
