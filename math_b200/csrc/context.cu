@@ -375,6 +375,11 @@ int smc_matrix_wrap(void* device_ptr, int64_t rows, int64_t cols, int64_t ld,
 
 int smc_matrix_free(smc_matrix* m) {
   if (!m) return SMC_OK;
+  if (m->grp_perm || m->grp_off) {
+    if (int rc = ensure_ctx()) return rc;
+    if (m->grp_perm) cache_free(m->grp_perm, m->grp_perm_bytes);
+    if (m->grp_off) cache_free(m->grp_off, m->grp_off_bytes);
+  }
   if (m->owned && m->data) {
     if (int rc = ensure_ctx()) return rc;
     if (m->device == ctx().device) {

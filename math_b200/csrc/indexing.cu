@@ -12,6 +12,7 @@
 // order.
 #include <atomic>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "smc_internal.h"
@@ -79,6 +80,70 @@ __global__ void indexing_rev_final_kernel(const double* __restrict__ partials, i
   out[g] = s;
 }
 
+// More groups than the per-warp accumulators hold: the rows of every group are
+// summed from a cached, stably sorted row list (idx is data, so the list is built
+// once per upload): one warp per group, lanes stride the group's rows, fixed-order
+// combine -- deterministic, and nothing but G doubles crosses PCIe per evaluation.
+__global__ void __launch_bounds__(kIdxThreads)
+    indexing_rev_sorted_kernel(const int* __restrict__ perm, const int* __restrict__ off,
+                               const double* __restrict__ v, int G, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t g = (int64_t)blockIdx.x * kIdxWarps + (threadIdx.x >> 5); g < G;
+       g += (int64_t)gridDim.x * kIdxWarps) {
+    const int lo = off[g], hi = off[g + 1];
+    double s = 0.0;
+    for (int j = lo + lane; j < hi; j += 32) s += v[perm[j]];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[g] = s;
+  }
+}
+
+// Builds (or finds) the sorted row list of idx for G groups.
+int group_index(const char* fn, const smc_matrix* idxc, int64_t G) {
+  smc_matrix* idx = const_cast<smc_matrix*>(idxc);
+  std::lock_guard<std::mutex> lock(cache_mutex());
+  if (idx->grp_perm && idx->grp_version == idx->version && idx->grp_G == G) return SMC_OK;
+  const int64_t n = idx->rows * idx->cols;
+  if (n > 0x7fffffff || G > 0x7ffffffe)
+    return fail(SMC_ERR_UNSUPPORTED, "%s: more than 2^31 rows or groups", fn);
+  std::vector<int> id((size_t)n), perm((size_t)n), off((size_t)G + 1, 0);
+  if (int rc = smc_matrix_download(idx, id.data(), idx->rows)) return rc;
+  for (int64_t i = 0; i < n; ++i) off[(size_t)id[(size_t)i] + 1]++;
+  for (int64_t g = 0; g < G; ++g) off[(size_t)g + 1] += off[(size_t)g];
+  {
+    std::vector<int> next(off.begin(), off.end() - 1);
+    for (int64_t i = 0; i < n; ++i) perm[(size_t)next[(size_t)id[(size_t)i]]++] = (int)i;
+  }
+  const size_t pb = sizeof(int) * (size_t)n, ob = sizeof(int) * ((size_t)G + 1);
+  if (idx->grp_perm && idx->grp_perm_bytes != pb) {
+    cache_free(idx->grp_perm, idx->grp_perm_bytes);
+    idx->grp_perm = nullptr;
+  }
+  if (idx->grp_off && idx->grp_off_bytes != ob) {
+    cache_free(idx->grp_off, idx->grp_off_bytes);
+    idx->grp_off = nullptr;
+  }
+  if (!idx->grp_perm) {
+    void* p = nullptr;
+    if (int rc = cache_alloc(&p, pb)) return rc;
+    idx->grp_perm = static_cast<int*>(p);
+    idx->grp_perm_bytes = pb;
+  }
+  if (!idx->grp_off) {
+    void* p = nullptr;
+    if (int rc = cache_alloc(&p, ob)) return rc;
+    idx->grp_off = static_cast<int*>(p);
+    idx->grp_off_bytes = ob;
+  }
+  Context& c = ctx();
+  SMC_CUDA(cudaMemcpyAsync(idx->grp_perm, perm.data(), pb, cudaMemcpyHostToDevice, c.stream));
+  SMC_CUDA(cudaMemcpyAsync(idx->grp_off, off.data(), ob, cudaMemcpyHostToDevice, c.stream));
+  SMC_CUDA(cudaStreamSynchronize(c.stream));  // the host vectors go out of scope
+  idx->grp_version = idx->version;
+  idx->grp_G = G;
+  return SMC_OK;
+}
+
 int check_index(const char* fn, const smc_matrix* idx, int64_t G) {
   if (!idx || idx->dtype != SMC_I32 || (idx->cols != 1 && idx->rows != 1 && idx->rows * idx->cols))
     return fail(SMC_ERR_INVALID_ARGUMENT, "%s: idx must be an i32 device vector", fn);
@@ -130,13 +195,17 @@ int smc_indexing_rev(const smc_matrix* idx, const smc_matrix* res_adj, int64_t G
   if (!adj_z) return fail(SMC_ERR_INVALID_ARGUMENT, "%s: NULL adj_z", fn);
   Context& c = ctx();
   if (G > kMaxGroupsFast) {
-    // more groups than the per-warp shared-memory accumulators hold: sequential
-    // host accumulation in row order (deterministic; N * 12 bytes over PCIe)
-    std::vector<double> v((size_t)n);
-    std::vector<int> id((size_t)n);
-    if (int rc = smc_matrix_download(res_adj, v.data(), res_adj->rows)) return rc;
-    if (int rc = smc_matrix_download(idx, id.data(), idx->rows)) return rc;
-    for (int64_t i = 0; i < n; ++i) adj_z[id[(size_t)i]] += v[(size_t)i];
+    if (int rc = group_index(fn, idx, G)) return rc;
+    if (int rc = ensure_out(sizeof(double) * (size_t)G)) return rc;
+    int64_t blocks = (G + kIdxWarps - 1) / kIdxWarps;
+    if (blocks > c.sm_count * 16) blocks = c.sm_count * 16;
+    indexing_rev_sorted_kernel<<<(int)blocks, kIdxThreads, 0, c.stream>>>(
+        idx->grp_perm, idx->grp_off, static_cast<const double*>(res_adj->data), (int)G,
+        c.out_host);
+    SMC_CUDA(cudaGetLastError());
+    c.launches += 1;
+    SMC_CUDA(cudaStreamSynchronize(c.stream));
+    for (int64_t g = 0; g < G; ++g) adj_z[g] += c.out_host[g];
     return SMC_OK;
   }
   int grid = c.sm_count;

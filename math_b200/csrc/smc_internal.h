@@ -177,4 +177,13 @@ struct smc_matrix {
   int binom_partner_scalar = 0;
   bool binom_in_support = false;
   double binom_coef_sum = 0;
+  // cached group index of an i32 index vector (indexing.cu, reverse sweep with more
+  // groups than the shared-memory accumulators hold): the rows stably sorted by
+  // group and the start of every group, on the device; valid while grp_version ==
+  // version and grp_G is the caller's group count.  Owned by the matrix.
+  int* grp_perm = nullptr;
+  int* grp_off = nullptr;
+  size_t grp_perm_bytes = 0, grp_off_bytes = 0;
+  int64_t grp_G = 0;
+  uint64_t grp_version = 0;
 };

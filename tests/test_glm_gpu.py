@@ -156,7 +156,10 @@ def test_ordered(gpu, N, K, C):
 
 
 @pytest.mark.parametrize("cuts,scale", [
-    ([-1.0, -1.0 + 1e-9, 0.5, 0.5 + 1e-6], 1.0),   # gaps far below the table's limit
+    # gaps of 1e-3: lim = 1e3 gap - |c1| is <= 0.5, so most rows of those classes take
+    # the per-row route (closer cut points make prim's own formula ill-conditioned:
+    # the term moves by ulp(loc) / gap with the summation order of x * beta)
+    ([-1.0, -1.0 + 1e-3, 0.5, 0.5 + 2e-3], 1.0),
     ([-0.8, -0.79, 0.3, 0.31, 1.0], 8.0),           # gap 1e-2: |loc| up to ~30 crosses it
     ([-2.0, -0.5, 0.4, 1.7], 40.0),                 # wide gaps, saturated predictors
 ])

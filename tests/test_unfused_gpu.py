@@ -125,6 +125,31 @@ def test_indexing_and_reverse(gpu, N, G):
         mb.lpmf.indexing(z, mb.to_matrix_cuda(np.array([0, G], dtype=np.int32)))
 
 
+def test_indexing_rev_many_groups_follows_reupload(gpu):
+    """More groups than the shared-memory accumulators hold: the reverse sweep runs
+    from a sorted row list cached on the index vector; a new upload into the same
+    device vector must invalidate it."""
+    mb = gpu
+    N, G = 400_003, 50_000
+    rng = np.random.default_rng(17)
+    v = rng.standard_normal(N)
+    v_d = mb.to_matrix_cuda(v)
+    idx = rng.integers(0, G, N).astype(np.int32)
+    idx_d = mb.to_matrix_cuda(idx)
+    for _ in range(2):
+        g1 = mb.lpmf.indexing_rev(idx_d, v_d, G)
+        g2 = mb.lpmf.indexing_rev(idx_d, v_d, G)
+        assert np.array_equal(g1, g2)
+        want = np.zeros(G)
+        np.add.at(want, idx, v)
+        assert_grad(g1, want, "indexing_rev", scale=np.abs(v).sum() / G)
+        idx = rng.permutation(idx).astype(np.int32)  # second round: new contents
+        idx_d.upload_rows(0, idx)
+    # a different group count on the same vector (some groups empty)
+    g3 = mb.lpmf.indexing_rev(idx_d, v_d, G + 1000)
+    assert g3.shape == (G + 1000,) and np.all(g3[G:] == 0.0)
+
+
 def test_unfused_pipeline_equals_fused_glm(gpu):
     """multiply -> density -> multiply_adjoint gives the fused GLM's value and
     gradient (three sweeps instead of one: what the fusion buys is in DESIGN.md)."""
