@@ -11,5 +11,5 @@ python profiles/time_configs.py > gpurun_out/configs.jsonl 2> gpurun_out/configs
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv \
     --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline \
     > gpurun_out/bench_under_ncu.log 2>&1
-CFGS="5a" bash profiles/run_ncu_all.sh > /dev/null 2>&1
+CFGS="5b" bash profiles/run_ncu_all.sh > /dev/null 2>&1
 ls gpurun_out | wc -l
