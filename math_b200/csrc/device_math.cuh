@@ -9,9 +9,23 @@
 
 namespace smc {
 
+// log1p(e) for e >= 0 on ONE code path: log(u) + (e - (u - 1)) / u with u = 1 + e
+// (the second term restores what rounding u lost; it is below ulp(1), so a single-
+// precision reciprocal is enough).  libdevice's log1p switches between two
+// evaluation schemes on the size of its argument and calls the out-of-line FP64
+// division: in a warp whose lanes fall on both sides -- the rule for
+// e = exp(-|theta|) in (0, 1] -- both schemes run back to back.  Worst error over
+// [0, 1] incl. tiny arguments: 1.5 ulp with a 0.5-ulp log (glibc's log1p: 0.83);
+// exact 0 at e = 0.
+__device__ __forceinline__ double log1p_nonneg(double e) {
+  const double u = 1.0 + e;
+  const double c = e - (u - 1.0);
+  return log(u) + c * (double)__frcp_rn((float)u);
+}
+
 __device__ __forceinline__ double log1p_exp(double a) {
-  if (a > 0.0) return a + log1p(exp(-a));
-  return log1p(exp(a));
+  if (a > 0.0) return a + log1p_nonneg(exp(-a));
+  return log1p_nonneg(exp(a));
 }
 
 __device__ __forceinline__ double log1m_exp(double a) {

@@ -120,9 +120,7 @@ __device__ __forceinline__ double div_or_zero(double num, double den) {
   return z ? 0.0 : q;
 }
 __device__ __forceinline__ double log1p_or_zero(double e) {
-  const bool z = e == 0.0;
-  const double l = log1p(opaque(z ? 1.0 : e));
-  return z ? 0.0 : l;
+  return log1p_nonneg(e);  // no division inside, exact 0 at e == 0
 }
 
 // Fills everything in `a` that does not depend on the kernel variant: shapes,
@@ -185,7 +183,7 @@ __device__ __forceinline__ double link_d(const FusedArgs& a, double xb,
     // log_inv_logit (log_inv_logit.hpp L52-58) and log1m_inv_logit
     // (log1m_inv_logit.hpp L44-50): their log1p_exp arguments are -|theta|
     const double th = xb + in.alpha;
-    const double l = log1p(exp(-fabs(th)));
+    const double l = log1p_nonneg(exp(-fabs(th)));
     const double lil = th < 0.0 ? th - l : -l;
     d = in.y - in.aux * exp(lil);
     bad = !isfinite(th);
@@ -291,7 +289,7 @@ __device__ __forceinline__ void link_lp(const FusedArgs& a, const LinkStash<FAM>
   if (!st.valid) return;
   if constexpr (FAM == kBernoulli) {
     const double t = st.v0, e = st.v1;
-    acc.lp += t > 20.0 ? -e : (t < -20.0 ? t : -log1p(e));  // L120-126
+    acc.lp += t > 20.0 ? -e : (t < -20.0 ? t : -log1p_nonneg(e));  // L120-126
   } else if constexpr (FAM == kBinomial) {
     const double th = st.v0, l = st.v1, n = st.v2, nt = st.v3;
     const double lil = th < 0.0 ? th - l : -l;
