@@ -249,7 +249,7 @@ __device__ __forceinline__ double link_d(const FusedArgs& a, double xb,
     // exp(-|cut|) serves both the stable log1p_exp forms (L135-138) and the
     // stable inv_logit selects (L168-174): for cut > 0 it IS exp(-cut), for
     // cut <= 0 it IS exp(cut) -- same argument, same bits
-    const double e1 = exp(-fabs(cut1)), e2 = exp(-fabs(cut2));
+    const double e1 = exp_nonpos(-fabs(cut1)), e2 = exp_nonpos(-fabs(cut2));
     // (one division per select: the numerator is chosen, the quotient is the same)
     const double d1 = div_or_zero(cut2 > 0.0 ? e2 : 1.0, 1.0 + e2) - ce[2];
     const double d2 = ce[3] - div_or_zero(cut1 > 0.0 ? e1 : 1.0, 1.0 + e1);
