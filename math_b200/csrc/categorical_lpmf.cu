@@ -10,7 +10,8 @@
 // model that adds terms to x * beta writes as a loop over the rows.  One sweep:
 // lane = row, the C log odds of a row are staged in shared memory (C <= 32)
 // between the max, the sum and the derivative, so lin is read once and d_lin
-// written once (2 * N * C * 8 bytes); wider rows re-read through L1/L2.  Deterministic:
+// written once (2 * N * C * 8 bytes); wider rows use two lanes per row or re-read
+// through L1/L2 (see the launch logic).  Deterministic:
 // static row -> thread schedule, fixed-order block and grid sums, no atomics.
 #include <atomic>
 #include <cmath>
@@ -113,6 +114,94 @@ __global__ void __launch_bounds__(kCatThreads)
   }
 }
 
+// 32 < C <= 64 (instantiated for L = 2): L lanes share a row (lane part q owns the classes
+// q, q + L, q + 2 L, ...: at most 32 per lane, staged in shared memory as above), the
+// row max / sum / picked log odds are combined with shuffles.  A warp covers 32 / L
+// consecutive rows, so a load instruction still touches L full 128- or 64-byte runs.
+// Same arithmetic per element as the single-lane kernel; the row sum is associated
+// per lane part first (fixed order: deterministic).
+template <int L>
+__global__ void __launch_bounds__(kCatThreads)
+    cat_lpmf_multilane_kernel(const double* __restrict__ lin, int64_t ld, int64_t N, int C,
+                              const int* __restrict__ y, int y_scalar,
+                              double* __restrict__ d_lin, int64_t d_ld,
+                              double* __restrict__ partials) {
+  extern __shared__ double cat_stage[];  // [ceil(C / L)][kCatThreads]
+  __shared__ double s_lp[kCatWarps], s_bad[kCatWarps];
+  constexpr int RW = 32 / L;  // rows per warp
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = lane / RW, rl = lane - q * RW;
+  const int64_t rows_per_cta = (int64_t)kCatWarps * RW;
+  const int64_t stride = (int64_t)gridDim.x * rows_per_cta;
+  double* mine = cat_stage + threadIdx.x;
+  double lp = 0.0, bad = 0.0;
+  for (int64_t base = blockIdx.x * rows_per_cta + (int64_t)warp * RW; base < N;
+       base += stride) {  // uniform per warp: every lane takes part in the shuffles
+    const int64_t i = base + rl;
+    const bool live = i < N;
+    const double* row = lin + (live ? i : N - 1);
+    const int yi = live ? (y ? y[i] : y_scalar) - 1 : 0;
+    double m = -INFINITY, vy = 0.0, s = 0.0;
+    bool finite = true;
+    int j = 0;
+#pragma unroll 8
+    for (int c = q; c < C; c += L, ++j) {
+      const double v = row[(int64_t)c * ld];
+      mine[j * kCatThreads] = v;
+      finite = finite && isfinite(v);
+      m = fmax(m, v);
+      vy = c == yi ? v : vy;
+    }
+    if (rl == 0 && base + stride < N) {  // one lane per run of the next row block
+      for (int c = q; c < C; c += L) prefetch_l2(row + stride + (int64_t)c * ld);
+    }
+#pragma unroll
+    for (int o = RW; o < 32; o <<= 1) {
+      m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+      vy += __shfl_xor_sync(0xffffffffu, vy, o);
+      finite = __shfl_xor_sync(0xffffffffu, (int)finite, o) && finite;
+    }
+    j = 0;
+#pragma unroll 4
+    for (int c = q; c < C; c += L, ++j) {
+      const double e = exp(mine[j * kCatThreads] - m);
+      mine[j * kCatThreads] = e;
+      s += e;
+    }
+#pragma unroll
+    for (int o = RW; o < 32; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (d_lin && live) {
+      const double inv = 1.0 / s;
+      double* drow = d_lin + i;
+      j = 0;
+#pragma unroll 4
+      for (int c = q; c < C; c += L, ++j)
+        drow[(int64_t)c * d_ld] = (c == yi ? 1.0 : 0.0) - mine[j * kCatThreads] * inv;
+    }
+    if (live && q == 0) {
+      if (finite) lp += vy - (m + log(s));
+      else bad += 1.0;
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    lp += __shfl_xor_sync(0xffffffffu, lp, o);
+    bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if (lane == 0) {
+    s_lp[warp] = lp;
+    s_bad[warp] = bad;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kCatWarps; ++w) {  // fixed order
+      lp += s_lp[w];
+      bad += s_bad[w];
+    }
+    partials[2 * (size_t)blockIdx.x] = lp;
+    partials[2 * (size_t)blockIdx.x + 1] = bad;
+  }
+}
+
 // out[0] = sum of the per-CTA log densities, out[1] = number of rows with a
 // non-finite entry; one warp, lane-strided partial sums combined in lane order.
 __global__ void cat_lpmf_final_kernel(const double* __restrict__ partials, int nblocks,
@@ -165,12 +254,18 @@ extern "C" int smc_categorical_logit_lpmf(const smc_matrix* y, int y_scalar,
                   (long long)C);
   }
   Context& c = ctx();
-  // C doubles of shared memory per thread: 64 KB per CTA at C = 32 (three CTAs per
-  // SM); wider rows than 32 classes take the re-reading kernel
-  const bool staged = C <= 32;
+  // C <= 32: lane = row, C doubles of shared memory per thread (64 KB per CTA at
+  // C = 32, three CTAs per SM).  C <= 64 with the derivative wanted: two lanes per
+  // row, at most 32 doubles per thread again (N=4e6, C=64: 1.44 -> 1.12 ms).
+  // Everything else re-reads through L1/L2: without a derivative pass (data log
+  // odds) exp is evaluated once per entry anyway and staging is pure overhead
+  // (N=1e7, C=32: 0.80 vs 0.93 ms; N=4e6, C=64: 0.65 vs 0.81 ms), and four lanes per
+  // row (C <= 128) lose to it either way (1.76 vs 2.03 ms).
+  const int lanes = !lin_var ? 0 : C <= 32 ? 1 : C <= 64 ? 2 : 0;
   const int threads = kCatThreads;
-  const size_t smem = staged ? sizeof(double) * (size_t)C * threads : 0;
-  int grid = (int)((N + threads - 1) / threads);
+  const int64_t rows_per_cta = lanes ? threads / lanes : threads;
+  const size_t smem = lanes ? sizeof(double) * (size_t)((C + lanes - 1) / lanes) * threads : 0;
+  int grid = (int)((N + rows_per_cta - 1) / rows_per_cta);
   const int cap = c.sm_count * 8;  // grid-stride rows: more CTAs than fit just queue
   if (grid > cap) grid = cap;
   if (int rc = ensure_partials(sizeof(double) * 2 * (size_t)grid)) return rc;
@@ -181,15 +276,21 @@ extern "C" int smc_categorical_logit_lpmf(const smc_matrix* y, int y_scalar,
   if (d) d_lin->version++;
   const double* l = static_cast<const double*>(lin->data);
   const int* yp = y ? static_cast<const int*>(y->data) : nullptr;
-  if (staged) {
+  if (lanes) {
     static std::atomic<bool> attr_set[16];
     if (!attr_set[c.device & 15]) {
       SMC_CUDA(cudaFuncSetAttribute(cat_lpmf_kernel<true>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      SMC_CUDA(cudaFuncSetAttribute(cat_lpmf_multilane_kernel<2>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
       attr_set[c.device & 15] = true;
     }
-    cat_lpmf_kernel<true><<<grid, threads, smem, c.stream>>>(l, lin->ld, N, (int)C, yp,
-                                                            y_scalar, d, d_ld, c.partials);
+    if (lanes == 1)
+      cat_lpmf_kernel<true><<<grid, threads, smem, c.stream>>>(l, lin->ld, N, (int)C, yp,
+                                                              y_scalar, d, d_ld, c.partials);
+    else
+      cat_lpmf_multilane_kernel<2><<<grid, threads, smem, c.stream>>>(
+          l, lin->ld, N, (int)C, yp, y_scalar, d, d_ld, c.partials);
   } else {
     cat_lpmf_kernel<false><<<grid, threads, 0, c.stream>>>(l, lin->ld, N, (int)C, yp,
                                                           y_scalar, d, d_ld, c.partials);

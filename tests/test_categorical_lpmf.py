@@ -108,7 +108,8 @@ def test_gpu_matches_golden(gpu, case):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("N,C", [(1, 1), (1, 5), (257, 2), (4099, 8), (4099, 9), (50021, 32),
-                                 (3001, 33), (1153, 43), (777, 200)])
+                                 (3001, 33), (1153, 43), (2049, 64), (1025, 65), (513, 128),
+                                 (777, 200)])
 def test_gpu_matches_oracle(gpu, N, C):
     mb = gpu
     rng = np.random.default_rng(N + C)
