@@ -10,6 +10,8 @@
 // range and a private accumulator per group in shared memory, collisions inside
 // a 32-row step are resolved in lane order, warps / CTAs are combined in index
 // order.
+#include <cub/device/device_radix_sort.cuh>
+
 #include <atomic>
 #include <cstring>
 #include <mutex>
@@ -82,7 +84,7 @@ __global__ void indexing_rev_final_kernel(const double* __restrict__ partials, i
 
 // More groups than the per-warp accumulators hold: the rows of every group are
 // summed from a cached, stably sorted row list (idx is data, so the list is built
-// once per upload): one warp per group, lanes stride the group's rows, fixed-order
+// once per upload, on the device): one warp per group, lanes stride the group's rows, fixed-order
 // combine -- deterministic, and nothing but G doubles crosses PCIe per evaluation.
 __global__ void __launch_bounds__(kIdxThreads)
     indexing_rev_sorted_kernel(const int* __restrict__ perm, const int* __restrict__ off,
@@ -98,22 +100,35 @@ __global__ void __launch_bounds__(kIdxThreads)
   }
 }
 
-// Builds (or finds) the sorted row list of idx for G groups.
+__global__ void iota_kernel(int* __restrict__ v, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    v[i] = i;
+}
+
+// off[g] = first position of group g in the sorted keys (n for groups past the
+// last one; an empty group gets the position of the next non-empty one).
+__global__ void group_offsets_kernel(const int* __restrict__ keys, int n, int G,
+                                     int* __restrict__ off) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const int cur = keys[j], prev = j ? keys[j - 1] : -1;
+    for (int g = prev + 1; g <= cur; ++g) off[g] = j;
+    if (j == n - 1)
+      for (int g = cur + 1; g <= G; ++g) off[g] = n;
+  }
+}
+
+// Builds (or finds) the sorted row list of idx for G groups: a stable radix sort of
+// (group, row) pairs on the device (cub), then the start of every group.  idx is
+// data, so this runs once per upload.
 int group_index(const char* fn, const smc_matrix* idxc, int64_t G) {
   smc_matrix* idx = const_cast<smc_matrix*>(idxc);
   std::lock_guard<std::mutex> lock(cache_mutex());
   if (idx->grp_perm && idx->grp_version == idx->version && idx->grp_G == G) return SMC_OK;
-  const int64_t n = idx->rows * idx->cols;
-  if (n > 0x7fffffff || G > 0x7ffffffe)
+  const int64_t n64 = idx->rows * idx->cols;
+  if (n64 > 0x7fffffff || G > 0x7ffffffe)
     return fail(SMC_ERR_UNSUPPORTED, "%s: more than 2^31 rows or groups", fn);
-  std::vector<int> id((size_t)n), perm((size_t)n), off((size_t)G + 1, 0);
-  if (int rc = smc_matrix_download(idx, id.data(), idx->rows)) return rc;
-  for (int64_t i = 0; i < n; ++i) off[(size_t)id[(size_t)i] + 1]++;
-  for (int64_t g = 0; g < G; ++g) off[(size_t)g + 1] += off[(size_t)g];
-  {
-    std::vector<int> next(off.begin(), off.end() - 1);
-    for (int64_t i = 0; i < n; ++i) perm[(size_t)next[(size_t)id[(size_t)i]]++] = (int)i;
-  }
+  const int n = (int)n64;
+  Context& c = ctx();
   const size_t pb = sizeof(int) * (size_t)n, ob = sizeof(int) * ((size_t)G + 1);
   if (idx->grp_perm && idx->grp_perm_bytes != pb) {
     cache_free(idx->grp_perm, idx->grp_perm_bytes);
@@ -135,10 +150,31 @@ int group_index(const char* fn, const smc_matrix* idxc, int64_t G) {
     idx->grp_off = static_cast<int*>(p);
     idx->grp_off_bytes = ob;
   }
-  Context& c = ctx();
-  SMC_CUDA(cudaMemcpyAsync(idx->grp_perm, perm.data(), pb, cudaMemcpyHostToDevice, c.stream));
-  SMC_CUDA(cudaMemcpyAsync(idx->grp_off, off.data(), ob, cudaMemcpyHostToDevice, c.stream));
-  SMC_CUDA(cudaStreamSynchronize(c.stream));  // the host vectors go out of scope
+  int end_bit = 1;
+  while (end_bit < 31 && (1ll << end_bit) < G) ++end_bit;
+  size_t temp_bytes = 0;
+  const int* keys_in = static_cast<const int*>(idx->data);
+  SMC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys_in, (int*)nullptr,
+                                           (const int*)nullptr, idx->grp_perm, n, 0, end_bit,
+                                           c.stream));
+  // scratch: sorted keys, the row numbers 0..n-1, cub's workspace
+  const size_t off_iota = (pb + 255) & ~(size_t)255, off_tmp = 2 * off_iota;
+  if (int rc = ensure_scratch(off_tmp + temp_bytes)) return rc;
+  char* scratch = reinterpret_cast<char*>(c.scratch);
+  int* keys_sorted = reinterpret_cast<int*>(scratch);
+  int* rows_in = reinterpret_cast<int*>(scratch + off_iota);
+  int blocks = (n + 255) / 256;
+  if (blocks > c.sm_count * 16) blocks = c.sm_count * 16;
+  iota_kernel<<<blocks, 256, 0, c.stream>>>(rows_in, n);
+  SMC_CUDA(cudaGetLastError());
+  SMC_CUDA(cub::DeviceRadixSort::SortPairs(scratch + off_tmp, temp_bytes, keys_in, keys_sorted,
+                                           rows_in, idx->grp_perm, n, 0, end_bit, c.stream));
+  group_offsets_kernel<<<blocks, 256, 0, c.stream>>>(keys_sorted, n, (int)G, idx->grp_off);
+  SMC_CUDA(cudaGetLastError());
+  c.launches += 3;
+  // other host threads (their own streams) may pick the list up as soon as it is
+  // marked valid
+  SMC_CUDA(cudaStreamSynchronize(c.stream));
   idx->grp_version = idx->version;
   idx->grp_G = G;
   return SMC_OK;
