@@ -69,11 +69,43 @@ int int_bounds(const char* fn, const smc_matrix* y, int y_scalar, int lo, int hi
   return SMC_OK;
 }
 
-// Host copy of a device vector (rare paths only: the lazy value checks).
-int fetch(const smc_matrix* v, std::vector<double>* out) {
-  out->resize((size_t)(v->rows * v->cols));
-  if (out->empty()) return SMC_OK;
-  return smc_matrix_download(v, out->data(), v->rows);
+// The lazy value checks behind a non-finite result: which kind of non-finite value
+// does a device vector hold?  bit 0: a NaN; bit 1: +inf; bit 2: -inf in a row whose
+// count n_i is not 0 (poisson_log_lpmf.hpp L56-66).  One scan on the device; only
+// the three flags come back.
+constexpr int kHasNan = 1, kHasPosInf = 2, kHasNegInfNonzeroCount = 4;
+__global__ void classify_kernel(const double* __restrict__ v, const int* __restrict__ n,
+                                int n_scalar, int64_t N, int* __restrict__ out) {
+  int f = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const double t = v[i];
+    if (t != t) f |= kHasNan;
+    if (t == INFINITY) f |= kHasPosInf;
+    if (t == -INFINITY && (n ? n[i] : n_scalar) != 0) f |= kHasNegInfNonzeroCount;
+  }
+  f = __reduce_or_sync(0xffffffffu, f);
+  if ((threadIdx.x & 31) == 0 && f) atomicOr(out, f);
+}
+
+int classify(const smc_matrix* v, const smc_matrix* n, int n_scalar, int* flags_out) {
+  Context& c = ctx();
+  const int64_t N = v->rows * v->cols;
+  *flags_out = 0;
+  if (N == 0) return SMC_OK;
+  if (int rc = ensure_out(4096)) return rc;
+  int* flag = reinterpret_cast<int*>(c.out_host);
+  *flag = 0;
+  int64_t blocks = (N + 255) / 256;
+  if (blocks > c.sm_count * 16) blocks = c.sm_count * 16;
+  classify_kernel<<<(int)blocks, 256, 0, c.stream>>>(
+      static_cast<const double*>(v->data), n ? static_cast<const int*>(n->data) : nullptr,
+      n_scalar, N, flag);
+  SMC_CUDA(cudaGetLastError());
+  c.launches += 1;
+  SMC_CUDA(cudaStreamSynchronize(c.stream));
+  *flags_out = *flag;
+  return SMC_OK;
 }
 
 }  // namespace
@@ -172,12 +204,11 @@ int smc_bernoulli_logit_lpmf(const smc_matrix* n, int n_scalar,
   const double lp = o[SMC_OUT_LOGP];
   if (o[SMC_OUT_NONFINITE] > 0) {
     // check_not_nan(theta), L48-49: +-inf is a legal logit, NaN is not
-    std::vector<double> th;
-    if (int rc = fetch(theta, &th)) return rc;
-    for (double t : th)
-      if (std::isnan(t))
-        return fail(SMC_ERR_DOMAIN,
-                    "%s: Logit transformed probability parameter is nan", fn);
+    int kinds = 0;
+    if (int rc = classify(theta, nullptr, 0, &kinds)) return rc;
+    if (kinds & kHasNan)
+      return fail(SMC_ERR_DOMAIN, "%s: Logit transformed probability parameter is nan",
+                  fn);
   }
   *logp = lp;
   return SMC_OK;
@@ -210,23 +241,10 @@ int smc_poisson_log_lpmf(const smc_matrix* n, int n_scalar, const smc_matrix* al
   const double lp = o[SMC_OUT_LOGP];
   if (o[SMC_OUT_NONFINITE] > 0) {
     // check_not_nan(alpha) L47; then the two log(0) exits, L56-66
-    std::vector<double> th;
-    if (int rc = fetch(alpha, &th)) return rc;
-    std::vector<int> nv;
-    if (n) {
-      nv.resize((size_t)N);
-      if (int rc = smc_matrix_download(n, nv.data(), n->rows)) return rc;
-    }
-    for (double t : th)
-      if (std::isnan(t))
-        return fail(SMC_ERR_DOMAIN, "%s: Log rate parameter is nan", fn);
-    bool zero = false;
-    for (size_t i = 0; i < th.size(); ++i) {
-      if (th[i] == std::numeric_limits<double>::infinity()) zero = true;
-      if (th[i] == -std::numeric_limits<double>::infinity()
-          && (n ? nv[i] : n_scalar) != 0)
-        zero = true;
-    }
+    int kinds = 0;
+    if (int rc = classify(alpha, n, n_scalar, &kinds)) return rc;
+    if (kinds & kHasNan) return fail(SMC_ERR_DOMAIN, "%s: Log rate parameter is nan", fn);
+    const bool zero = kinds & (kHasPosInf | kHasNegInfNonzeroCount);
     if (zero && !skip) {
       // LOG_ZERO is returned as a constant: no partials
       if (c.d_alpha_vec) {
@@ -349,10 +367,9 @@ int smc_normal_lpdf(const smc_matrix* y, double y_scalar, const smc_matrix* mu,
       if (!ok) return fail(SMC_ERR_DOMAIN, "%s: Location parameter is not finite", fn);
     }
     if (y) {
-      std::vector<double> yv;
-      if (int rc = fetch(y, &yv)) return rc;
-      for (double t : yv)
-        if (std::isnan(t)) return fail(SMC_ERR_DOMAIN, "%s: Random variable is nan", fn);
+      int kinds = 0;
+      if (int rc = classify(y, nullptr, 0, &kinds)) return rc;
+      if (kinds & kHasNan) return fail(SMC_ERR_DOMAIN, "%s: Random variable is nan", fn);
     }
   }
   if (skip) return SMC_OK;  // L67-69
