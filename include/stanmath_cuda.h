@@ -116,6 +116,10 @@ int smc_matrix_zero(smc_matrix* m);
 /* Device-to-device copy of a same-shaped matrix (matrix_cl copy construction,
  * matrix_cl.hpp L198-210); asynchronous on the thread's stream. */
 int smc_matrix_copy(smc_matrix* dst, const smc_matrix* src);
+/* out[i, k] = beta[k] * d[i] for an N x 1 f64 device vector d and K host doubles
+ * (K <= 256): the N x K partial beta (x) d of an autodiff design matrix written as a
+ * pure store stream.  out: N x K f64, 16-byte aligned, even leading dimension. */
+int smc_matrix_outer(smc_matrix* out, const smc_matrix* d, const double* beta);
 /* y += a * x on the device: update_adjoints for a device-resident operand
  * (rev/functor/operands_and_partials.hpp L28-38). */
 int smc_matrix_axpy(smc_matrix* y, double a, const smc_matrix* x);

@@ -62,6 +62,7 @@ SIGNATURES = {
     "smc_matrix_zero": (_I, [_P]),
     "smc_matrix_copy": (_I, [_P, _P]),
     "smc_matrix_axpy": (_I, [_P, _D, _P]),
+    "smc_matrix_outer": (_I, [_P, _P, _DP]),
     "smc_matrix_all_finite": (_I, [_P, C.POINTER(_I)]),
     "smc_matrix_int_range": (_I, [_P, C.POINTER(_I), C.POINTER(_I)]),
     "smc_matrix_fill_synthetic": (_I, [_P, C.c_uint64, _I64, _I, _D, _I, _I]),

@@ -209,6 +209,37 @@ __global__ void all_finite_kernel(const double* __restrict__ x, int64_t ld,
   if (__any_sync(0xffffffffu, local) && (threadIdx.x & 31) == 0) *bad = 1;
 }
 
+// out[i, k] = beta[k] * d[i]: the N x K partial of an autodiff design matrix as a
+// pure write stream (two rows per thread: one 16-byte store per column).
+struct OuterArgs {
+  double* out;
+  int64_t ld;
+  const double* d;
+  int64_t N;
+  int K;
+  const double* beta_dev;  // NULL: beta[] below
+  double beta[kMaxParamDoubles];
+};
+__global__ void __launch_bounds__(256)
+    outer_kernel(const __grid_constant__ OuterArgs a) {
+  const int64_t npairs = (a.N + 1) / 2;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npairs;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = 2 * p;
+    const bool two = i + 1 < a.N;
+    const double d0 = a.d[i], d1 = two ? a.d[i + 1] : 0.0;
+    double* o = a.out + i;
+#pragma unroll 8
+    for (int k = 0; k < a.K; ++k) {
+      const double b = a.beta_dev ? __ldg(a.beta_dev + k) : a.beta[k];
+      if (two)
+        *reinterpret_cast<double2*>(o + (int64_t)k * a.ld) = make_double2(b * d0, b * d1);
+      else
+        o[(int64_t)k * a.ld] = b * d0;
+    }
+  }
+}
+
 __host__ __device__ inline uint64_t synth_hash(uint64_t seed, uint64_t row,
                                                uint64_t col) {
   uint64_t z = seed + row * 0x9E3779B97F4A7C15ull + col * 0xBF58476D1CE4E5B9ull;
@@ -260,6 +291,29 @@ static inline dim3 grid2d_for(int64_t rows, int64_t cols, int threads) {
   if (gy > 65535) gy = 65535;
   if (gy < 1) gy = 1;
   return dim3((unsigned)gx, (unsigned)gy);
+}
+
+// out (N x K, ld) = d beta^T on this thread's stream; beta from the host or, when
+// beta_dev is set, from device memory (the asynchronous multi-GPU path).
+int launch_outer(double* out, int64_t ld, const double* d, int64_t N, int K,
+                 const double* beta_host, const double* beta_dev) {
+  if (N == 0 || K == 0) return SMC_OK;
+  if (K > kMaxParamDoubles || (reinterpret_cast<uintptr_t>(out) & 15) || (K > 1 && (ld & 1)))
+    return fail(SMC_ERR_UNSUPPORTED,
+                "outer: needs K <= %d and a 16-byte aligned matrix with an even ld",
+                kMaxParamDoubles);
+  OuterArgs a;
+  a.out = out;
+  a.ld = ld;
+  a.d = d;
+  a.N = N;
+  a.K = K;
+  a.beta_dev = beta_dev;
+  if (!beta_dev) memcpy(a.beta, beta_host, sizeof(double) * K);
+  outer_kernel<<<grid_for((N + 1) / 2, 256), 256, 0, t_ctx.stream>>>(a);
+  SMC_CUDA(cudaGetLastError());
+  t_ctx.launches += 1;
+  return SMC_OK;
 }
 
 static inline size_t elem_size(int dtype) { return dtype == SMC_F64 ? 8 : 4; }
@@ -493,6 +547,17 @@ int smc_matrix_axpy(smc_matrix* y, double a, const smc_matrix* x) {
       x->ld, y->rows, y->cols, a);
   SMC_CUDA(cudaGetLastError());
   return SMC_OK;
+}
+
+int smc_matrix_outer(smc_matrix* out, const smc_matrix* d, const double* beta) {
+  if (!out || !d || !beta || out->dtype != SMC_F64 || d->dtype != SMC_F64
+      || d->rows * d->cols != out->rows)
+    return fail(SMC_ERR_INVALID_ARGUMENT, "outer: shape/dtype mismatch");
+  if (int rc = ensure_ctx()) return rc;
+  out->version++;
+  return launch_outer(static_cast<double*>(out->data), out->ld,
+                      static_cast<const double*>(d->data), out->rows, (int)out->cols, beta,
+                      nullptr);
 }
 
 int smc_matrix_add_scalar(smc_matrix* y, double a) {

@@ -129,6 +129,9 @@ bool fused_supported(const smc_matrix* x);
 // The same without the bound on the number of columns (wide x: column chunks).
 bool fused_layout_ok(const smc_matrix* x);
 int launch_glm_fused(const GlmCall& c);
+// out (N x K, leading dimension ld) = d beta^T as a pure store stream (context.cu)
+int launch_outer(double* out, int64_t ld, const double* d, int64_t N, int K,
+                 const double* beta_host, const double* beta_dev);
 int launch_glm_generic(const GlmCall& c);
 
 // sum_i lgamma(y_i + 1) over an i32 device vector (cached on the matrix).
