@@ -1016,19 +1016,21 @@ static int launch_cat_impl(CatMode mode, const smc_matrix* y, int y_scalar,
   const size_t off_bt = (nparam + 15) & ~(size_t)15;  // 128-byte aligned
   if (int rc = ensure_params(sizeof(double) * (off_bt + (size_t)a.K * C8p + 16))) return rc;
   if (params_user) {
-    // (a D2D copy keeps every alignment assumption of the kernels on cx.params_dev)
+    // beta and alpha in one piece (a D2D copy keeps every alignment assumption of
+    // the kernels on cx.params_dev)
     SMC_CUDA(cudaMemcpyAsync(cx.params_dev, params_user, sizeof(double) * nparam,
                              cudaMemcpyDeviceToDevice, cx.stream));
-  } else if (a.K && mode != kCatAdj)
-    SMC_CUDA(cudaMemcpyAsync(cx.params_dev, beta_host, sizeof(double) * a.K * a.C,
-                             cudaMemcpyHostToDevice, cx.stream));
-  if (params_user) {
-  } else if (alpha_host)
-    SMC_CUDA(cudaMemcpyAsync(cx.params_dev + (size_t)a.K * a.C, alpha_host,
-                             sizeof(double) * a.C, cudaMemcpyHostToDevice, cx.stream));
-  else
-    SMC_CUDA(cudaMemsetAsync(cx.params_dev + (size_t)a.K * a.C, 0, sizeof(double) * a.C,
-                             cx.stream));
+  } else {
+    if (a.K && mode != kCatAdj)
+      SMC_CUDA(cudaMemcpyAsync(cx.params_dev, beta_host, sizeof(double) * a.K * a.C,
+                               cudaMemcpyHostToDevice, cx.stream));
+    if (alpha_host)
+      SMC_CUDA(cudaMemcpyAsync(cx.params_dev + (size_t)a.K * a.C, alpha_host,
+                               sizeof(double) * a.C, cudaMemcpyHostToDevice, cx.stream));
+    else
+      SMC_CUDA(cudaMemsetAsync(cx.params_dev + (size_t)a.K * a.C, 0, sizeof(double) * a.C,
+                               cx.stream));
+  }
   a.beta = cx.params_dev;
   a.alpha = cx.params_dev + (size_t)a.K * a.C;
   a.beta_t = cx.params_dev + off_bt;
