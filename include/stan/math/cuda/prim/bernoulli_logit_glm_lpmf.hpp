@@ -55,7 +55,7 @@ return_type_t<T_x, T_alpha, T_beta> bernoulli_logit_glm_lpmf(
   auto ops_partials = make_partials_propagator(x, alpha, beta);
   row_partial<T_alpha> d_alpha_vec(partials<1>(ops_partials), N);
 
-  const unsigned flags = (propto ? SMC_PROPTO : 0u) | var_flag<T_x>(SMC_VAR_X)
+  const unsigned flags = (propto ? SMC_PROPTO : 0u) | dx_flags<T_x>()
                          | var_flag<T_alpha>(SMC_VAR_ALPHA)
                          | var_flag<T_beta>(SMC_VAR_BETA);
   double logp = 0, d_alpha = 0;
@@ -65,7 +65,7 @@ return_type_t<T_x, T_alpha, T_beta> bernoulli_logit_glm_lpmf(
       smc_bernoulli_logit_glm(y_op.handle(), y_op.scalar(), x_handle(x),
                               alpha_op.handle(), alpha_op.scalar(), beta_val.data(),
                               flags, &logp, &d_alpha, d_alpha_vec.handle(),
-                              d_beta.data(), dx_handle<T_x>(partials<0>(ops_partials))));
+                              d_beta.data(), dx_factor_handle<T_x>(partials<0>(ops_partials), beta_val.data())));
 
   // partials: d_x was written into the edge by the kernel (L158-159)
   if constexpr (!is_constant_all<T_alpha>::value) {  // L162-164

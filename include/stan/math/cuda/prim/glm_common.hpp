@@ -166,7 +166,8 @@ inline const smc_matrix* x_handle(const T_x& x) {
   }
 }
 
-/** Device handle the kernel writes d_x into: the x edge's own partial. */
+/** Device handle the kernel writes the full N x K d_x into: the x edge's own
+ * partial (the categorical GLM, whose d_x = T beta^T has rank C). */
 template <typename T_x, typename Edge>
 inline smc_matrix* dx_handle(Edge& edge_partials) {
   if constexpr (is_var_matrix_cuda<T_x>::value) {
@@ -174,6 +175,22 @@ inline smc_matrix* dx_handle(Edge& edge_partials) {
   } else {
     return nullptr;
   }
+}
+
+/** The rank-one families (d_x = d beta^T): the x edge keeps the factor d and beta,
+ * the product is applied by the reverse sweep (cuda_edge_partial::factored).
+ * Returns the N x 1 device vector to pass as d_x together with dx_flags<T_x>(). */
+template <typename T_x, typename Edge>
+inline smc_matrix* dx_factor_handle(Edge& edge_partials, const double* beta) {
+  if constexpr (is_var_matrix_cuda<T_x>::value) {
+    return edge_partials.factored(beta);
+  } else {
+    return nullptr;
+  }
+}
+template <typename T_x>
+constexpr unsigned dx_flags() {
+  return is_var_matrix_cuda<T_x>::value ? (SMC_VAR_X | SMC_DX_FACTORED) : 0u;
 }
 
 }  // namespace cuda_internal

@@ -67,7 +67,7 @@ return_type_t<T_x, T_alpha, T_beta, T_precision> neg_binomial_2_log_glm_lpmf(
   row_partial<T_precision> d_phi_vec(partials<3>(ops_partials), N);
 
   const unsigned flags
-      = (propto ? SMC_PROPTO : 0u) | var_flag<T_x>(SMC_VAR_X)
+      = (propto ? SMC_PROPTO : 0u) | dx_flags<T_x>()
         | var_flag<T_alpha>(SMC_VAR_ALPHA) | var_flag<T_beta>(SMC_VAR_BETA)
         | var_flag<T_precision>(SMC_VAR_AUX);
   double logp = 0, d_alpha = 0, d_phi = 0;
@@ -78,7 +78,7 @@ return_type_t<T_x, T_alpha, T_beta, T_precision> neg_binomial_2_log_glm_lpmf(
           y_op.handle(), y_op.scalar(), x_handle(x), alpha_op.handle(),
           alpha_op.scalar(), beta_val.data(), phi_op.handle(), phi_op.scalar(),
           flags, &logp, &d_alpha, d_alpha_vec.handle(), d_beta.data(), &d_phi,
-          d_phi_vec.handle(), dx_handle<T_x>(partials<0>(ops_partials))));
+          d_phi_vec.handle(), dx_factor_handle<T_x>(partials<0>(ops_partials), beta_val.data())));
 
   if constexpr (!is_constant_all<T_alpha>::value) {  // L225-231
     if constexpr (is_stan_scalar<T_alpha>::value) {

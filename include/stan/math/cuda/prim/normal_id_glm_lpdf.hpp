@@ -56,7 +56,7 @@ return_type_t<T_y, T_x, T_alpha, T_beta, T_scale> normal_id_glm_lpdf(
 
   const unsigned flags
       = (propto ? SMC_PROPTO : 0u) | var_flag<T_y>(SMC_VAR_Y)
-        | var_flag<T_x>(SMC_VAR_X) | var_flag<T_alpha>(SMC_VAR_ALPHA)
+        | dx_flags<T_x>() | var_flag<T_alpha>(SMC_VAR_ALPHA)
         | var_flag<T_beta>(SMC_VAR_BETA) | var_flag<T_scale>(SMC_VAR_AUX);
   double logp = 0, d_alpha = 0, d_sigma = 0, d_y = 0;
   Eigen::VectorXd d_beta(K);
@@ -67,7 +67,7 @@ return_type_t<T_y, T_x, T_alpha, T_beta, T_scale> normal_id_glm_lpdf(
                         sigma_op.scalar(), flags, &logp, &d_alpha,
                         d_alpha_vec.handle(), d_beta.data(), &d_sigma,
                         d_sigma_vec.handle(), &d_y, d_y_vec.handle(),
-                        dx_handle<T_x>(partials<1>(ops_partials))));
+                        dx_factor_handle<T_x>(partials<1>(ops_partials), beta_val.data())));
 
   if constexpr (!is_constant_all<T_y>::value) {  // L141-147
     if constexpr (is_stan_scalar<T_y>::value) {

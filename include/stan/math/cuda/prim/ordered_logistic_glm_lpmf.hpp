@@ -60,7 +60,7 @@ return_type_t<T_x, T_beta, T_cuts> ordered_logistic_glm_lpmf(
   const Eigen::VectorXd beta_val = host_values(beta);
   auto ops_partials = make_partials_propagator(x, beta, cuts);
 
-  const unsigned flags = (propto ? SMC_PROPTO : 0u) | var_flag<T_x>(SMC_VAR_X)
+  const unsigned flags = (propto ? SMC_PROPTO : 0u) | dx_flags<T_x>()
                          | var_flag<T_beta>(SMC_VAR_BETA)
                          | var_flag<T_cuts>(SMC_VAR_AUX);
   double logp = 0;
@@ -70,7 +70,7 @@ return_type_t<T_x, T_beta, T_cuts> ordered_logistic_glm_lpmf(
       smc_ordered_logistic_glm(y_op.handle(), y_op.scalar(), x_handle(x),
                                beta_val.data(), cuts_val.data(), n_cuts, flags,
                                &logp, d_beta.data(), d_cuts.data(),
-                               dx_handle<T_x>(partials<0>(ops_partials))));
+                               dx_factor_handle<T_x>(partials<0>(ops_partials), beta_val.data())));
 
   if constexpr (!is_constant_all<T_beta>::value) {  // L185-195
     store_host_partial<T_beta>(partials<1>(ops_partials), d_beta.data(), K);

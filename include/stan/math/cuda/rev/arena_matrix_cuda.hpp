@@ -36,10 +36,14 @@ class arena_matrix_cuda : public matrix_cuda_base {
   using Scalar = T;
   arena_matrix_cuda() = default;
 
-  /** rows x cols of zeros owned by the arena. */
+  /** rows x cols of zeros owned by the arena.  The zeros are declared, not written
+   * (smc_matrix_zero_lazy): the adjoint of a device var is usually produced whole by
+   * its one consumer, which then stores into it without a memset or a read. */
   arena_matrix_cuda(int64_t rows, int64_t cols) {
     matrix_cuda<T> m(rows, cols);
-    m.zero();
+    if (m.handle()) {
+      check_cuda_status("arena_matrix_cuda(zeros)", smc_matrix_zero_lazy(m.handle()));
+    }
     take(std::move(m));
   }
   /** rows x cols owned by the arena, contents unspecified (the producer

@@ -60,11 +60,15 @@ inline var_value<matrix_cuda<double>> indexing(const T_z& z, const matrix_cuda<i
   check_cuda_status("indexing(CUDA)",
                     smc_indexing(zv.data(), zv.size(), idx.handle(), out.handle()));
   var_value<matrix_cuda<double>> res(std::move(out));
-  arena_matrix_cuda<int> idx_arena = arena_matrix_cuda<int>::view(idx);
-  reverse_pass_callback([z_arena, idx_arena, res]() mutable {
+  // idx is data and outlives the sweep (like every data matrix a callback views): the
+  // callback keeps the caller's own handle, so what the library caches on it -- the
+  // index range and, for many groups, the sorted row list -- is built once per upload,
+  // not once per gradient evaluation on a throw-away view
+  const smc_matrix* idx_handle = idx.handle();
+  reverse_pass_callback([z_arena, idx_handle, res]() mutable {
     Eigen::VectorXd g = Eigen::VectorXd::Zero(z_arena.size());
     check_cuda_status("indexing(CUDA) reverse",
-                      smc_indexing_rev(idx_arena.handle(), res.adj().handle(), g.size(),
+                      smc_indexing_rev(idx_handle, res.adj().handle(), g.size(),
                                        g.data()));
     if constexpr (std::decay_t<decltype(z_arena.adj())>::ColsAtCompileTime == 1) {
       z_arena.adj() += g;

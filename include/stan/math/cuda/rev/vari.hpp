@@ -9,7 +9,10 @@
 //
 //   - the vari sits on var_nochain_stack_ (its chain() is empty: producers
 //     propagate into adj_ through update_adjoints),
-//   - set_zero_adjoint() re-zeros adj_ on the device (opencl/rev/vari.hpp L287),
+//   - set_zero_adjoint() re-zeros adj_ on the device (opencl/rev/vari.hpp L287);
+//     zeros are declared lazily (smc_matrix_zero_lazy): the first producer to
+//     propagate into the adjoint stores its contribution instead of adding to a
+//     freshly written block of zeros,
 //   - value and adjoint buffers are arena-owned (freed by recover_memory()).
 #include <stan/math/cuda/rev/arena_matrix_cuda.hpp>
 #include <stan/math/rev/core/var.hpp>
@@ -49,7 +52,7 @@ class vari_value<matrix_cuda<double>, void> : public vari_base {
   void set_zero_adjoint() override {
     if (adj_.handle()) {
       check_cuda_status("vari_value<matrix_cuda>::set_zero_adjoint",
-                        smc_matrix_zero(adj_.handle()));
+                        smc_matrix_zero_lazy(adj_.handle()));
     }
   }
 };

@@ -56,6 +56,12 @@ enum smc_dtype { SMC_F64 = 0, SMC_I32 = 1 };
 #define SMC_VAR_BETA 8u   /* beta is a var                                   */
 #define SMC_VAR_AUX 16u   /* sigma / phi / cuts is a var                     */
 #define SMC_VAR_Y 32u     /* y is a var (normal_id_glm only)                 */
+/* With SMC_VAR_X: d_x receives the N x 1 factor d of the rank-one partial
+ * d_x = d beta^T instead of the N x K product.  The caller keeps beta and runs its
+ * reverse sweep x.adj += lp.adj * d beta^T with smc_matrix_rank1_update, so the
+ * product is never materialised (memory-bound families; the categorical partial
+ * T beta^T has rank C and ignores this flag). */
+#define SMC_DX_FACTORED 64u
 
 /* Layout of the packed result vector written by the *_device entry points
  * (and all-reduced across GPUs by the row-sharded driver):
@@ -113,6 +119,17 @@ int smc_matrix_download(const smc_matrix* m, void* host, int64_t ld_host);
 int smc_matrix_download_rows(const smc_matrix* m, int64_t row0, int64_t nrows,
                              void* host, int64_t ld_host);
 int smc_matrix_zero(smc_matrix* m);
+/* Declares every element zero WITHOUT touching memory (the adjoint of a device var,
+ * opencl/rev/vari.hpp L287 `adj_ = constant(0, ...)`): the memset is deferred until a
+ * library call reads the matrix or writes part of it (including smc_matrix_data,
+ * which hands out the raw pointer), and never runs when the next writer overwrites
+ * or accumulates into the whole matrix (smc_matrix_rank1_update, smc_matrix_axpy,
+ * uploads, copies): those store their result directly. */
+int smc_matrix_zero_lazy(smc_matrix* m);
+/* For the owner of WRAPPED memory (smc_matrix_wrap) that changed the contents behind
+ * the library's back: drops what the handle caches about them (range and lgamma
+ * sums of an integer vector, binomial pair statistics). */
+int smc_matrix_invalidate(smc_matrix* m);
 /* Device-to-device copy of a same-shaped matrix (matrix_cl copy construction,
  * matrix_cl.hpp L198-210); asynchronous on the thread's stream. */
 int smc_matrix_copy(smc_matrix* dst, const smc_matrix* src);
@@ -123,6 +140,15 @@ int smc_matrix_outer(smc_matrix* out, const smc_matrix* d, const double* beta);
 /* y += a * x on the device: update_adjoints for a device-resident operand
  * (rev/functor/operands_and_partials.hpp L28-38). */
 int smc_matrix_axpy(smc_matrix* y, double a, const smc_matrix* x);
+/* y[i,k] += a * (d[i] * beta[k]) for an N x K f64 device matrix y, an N x 1 f64
+ * device vector d and K host doubles: the reverse sweep of an autodiff design
+ * matrix, x.adj() += lp.adj() * partial with partial = d beta^T
+ * (rev/functor/operands_and_partials.hpp L28-38;
+ * prim/prob/neg_binomial_2_log_glm_lpmf.hpp L221-222) as ONE read-modify-write of the
+ * adjoint -- or one pure store when y is lazily zero -- without ever forming the
+ * N x K partial.  y: 16-byte aligned, even leading dimension. */
+int smc_matrix_rank1_update(smc_matrix* y, double a, const smc_matrix* d,
+                            const double* beta);
 /* Lazy value checks (cf. check_cl in opencl/prim/ *_glm_*.hpp). */
 /* y += a (every element) */
 int smc_matrix_add_scalar(smc_matrix* y, double a);

@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("MATH_B200_LIB") or os.path.join(HERE, "lib",
 OK, ERR_INVALID_ARGUMENT, ERR_DOMAIN, ERR_CUDA, ERR_UNSUPPORTED = range(5)
 F64, I32 = 0, 1
 PROPTO, VAR_X, VAR_ALPHA, VAR_BETA, VAR_AUX, VAR_Y = 1, 2, 4, 8, 16, 32
+DX_FACTORED = 64
 OUT_HEADER, OUT_LOGP, OUT_SUM_D, OUT_AUX, OUT_NONFINITE, OUT_AUX2 = 8, 0, 1, 2, 3, 4
 
 
@@ -60,6 +61,9 @@ SIGNATURES = {
     "smc_matrix_download": (_I, [_P, _P, _I64]),
     "smc_matrix_download_rows": (_I, [_P, _I64, _I64, _P, _I64]),
     "smc_matrix_zero": (_I, [_P]),
+    "smc_matrix_zero_lazy": (_I, [_P]),
+    "smc_matrix_invalidate": (_I, [_P]),
+    "smc_matrix_rank1_update": (_I, [_P, _D, _P, _DP]),
     "smc_matrix_copy": (_I, [_P, _P]),
     "smc_matrix_axpy": (_I, [_P, _D, _P]),
     "smc_matrix_outer": (_I, [_P, _P, _DP]),

@@ -28,7 +28,7 @@ int check_shapes(const char* fn, const smc_matrix* x, const smc_matrix* y,
   if (y) {
     if (y->dtype != y_dtype)
       return fail(SMC_ERR_INVALID_ARGUMENT, "%s: y has the wrong dtype", fn);
-    if (y->rows * y->cols != N || (y->cols != 1 && y->rows != 1 && N != 0))
+    if (y->rows * y->cols != N || !vec_contiguous(y))
       return fail(SMC_ERR_INVALID_ARGUMENT,
                   "%s: size of y (%lld) does not match rows of x (%lld)", fn,
                   (long long)(y->rows * y->cols), (long long)N);
@@ -36,7 +36,7 @@ int check_shapes(const char* fn, const smc_matrix* x, const smc_matrix* y,
   const smc_matrix* vs[2] = {v1, v2};
   for (const smc_matrix* v : vs) {
     if (!v) continue;
-    if (v->dtype != SMC_F64 || v->rows * v->cols != N)
+    if (v->dtype != SMC_F64 || v->rows * v->cols != N || !vec_contiguous(v))
       return fail(SMC_ERR_INVALID_ARGUMENT,
                   "%s: size of a per-row vector (%lld) does not match rows of x "
                   "(%lld)",
@@ -46,7 +46,7 @@ int check_shapes(const char* fn, const smc_matrix* x, const smc_matrix* y,
 }
 
 int check_out_vec(const char* fn, const smc_matrix* m, int64_t N) {
-  if (m && (m->dtype != SMC_F64 || m->rows * m->cols != N))
+  if (m && (m->dtype != SMC_F64 || m->rows * m->cols != N || !vec_contiguous(m)))
     return fail(SMC_ERR_INVALID_ARGUMENT, "%s: per-row output has the wrong size",
                 fn);
   return SMC_OK;
@@ -55,6 +55,14 @@ int check_out_vec(const char* fn, const smc_matrix* m, int64_t N) {
 int check_dx(const char* fn, unsigned flags, const smc_matrix* x,
              const smc_matrix* d_x) {
   if (!(flags & SMC_VAR_X)) return SMC_OK;
+  if (flags & SMC_DX_FACTORED) {
+    if (!d_x || d_x->dtype != SMC_F64 || d_x->rows * d_x->cols != x->rows
+        || !vec_contiguous(d_x))
+      return fail(SMC_ERR_INVALID_ARGUMENT,
+                  "%s: SMC_DX_FACTORED needs d_x to be an f64 vector of rows(x) doubles",
+                  fn);
+    return SMC_OK;
+  }
   if (!d_x || d_x->dtype != SMC_F64 || d_x->rows != x->rows
       || d_x->cols != x->cols)
     return fail(SMC_ERR_INVALID_ARGUMENT,
@@ -194,7 +202,7 @@ int smc_binomial_logit_glm(const smc_matrix* n, int n_scalar,
   if (int rc = check_shapes(fn, x, n, SMC_I32, alpha_vec, nullptr)) return rc;  // L88-93
   if (trials
       && (trials->dtype != SMC_I32 || trials->rows * trials->cols != N
-          || (trials->cols != 1 && trials->rows != 1)))
+          || !vec_contiguous(trials)))
     return fail(SMC_ERR_INVALID_ARGUMENT,
                 "%s: size of the population size parameter (%lld) does not match "
                 "rows of x (%lld)",
@@ -508,7 +516,8 @@ int smc_glm_eval_device(int family, const smc_matrix* y, double y_scalar,
                             alpha_vec, family == kBinomial ? nullptr : aux_vec))
     return rc;
   if (family == kBinomial && aux_vec
-      && (aux_vec->dtype != SMC_I32 || aux_vec->rows * aux_vec->cols != x->rows))
+      && (aux_vec->dtype != SMC_I32 || aux_vec->rows * aux_vec->cols != x->rows
+          || !vec_contiguous(aux_vec)))
     return fail(SMC_ERR_INVALID_ARGUMENT,
                 "%s: binomial trials must be an i32 vector with one entry per row", fn);
   if (!params_dev || !out_dev)

@@ -855,13 +855,13 @@ static int run_dx_dmma(const CatArgs& a, dim3 grid, int kch, size_t smem) {
 // device scratch; it is filled here unless `beta_t_ready`.
 static int run_cat_dx(const CatArgs& a, bool beta_t_ready) {
   Context& cx = ctx();
-  const char* force = getenv("SMC_CAT_DX_FMA");
+  const bool force_fma = knobs().cat_dx_fma;  // A/B switch
   const bool vec_ok = (reinterpret_cast<uintptr_t>(a.d_x) & 15) == 0 && (a.ld_dx & 1) == 0;
   // (8 classes or fewer: two DMMA k-steps per attribute tile do not pay for the
   // fragment loads -- the plain-FMA kernel is faster there, 1.18 vs 1.72 ms at
   // N=4e6, K=128, C=8; from 9 classes on it falls off a cliff, 26.3 vs 2.06 ms at
   // N=2e6, K=512, C=32)
-  if (!vec_ok || a.C <= 8 || (force && force[0] == '1')) {
+  if (!vec_ok || a.C <= 8 || force_fma) {
     const int g3 = (int)((a.N + 255) / 256);
     if (a.C <= 8)
       cat_dx_kernel<8><<<g3, 256, 0, cx.stream>>>(a);
@@ -964,8 +964,7 @@ static int run_dbeta_tma(const CUtensorMap& tmx, const CUtensorMap& tmt,
 }
 
 static bool cat_tma_ok(const smc_matrix* x) {
-  const char* force = getenv("SMC_CAT_NO_TMA");
-  if (force && force[0] == '1') return false;
+  if (knobs().cat_no_tma) return false;  // A/B switch
   if (!get_encode()) return false;
   if ((reinterpret_cast<uintptr_t>(x->data) & 15) != 0) return false;
   if (x->cols > 1 && (x->ld & 1)) return false;
@@ -994,6 +993,9 @@ static int launch_cat_impl(CatMode mode, const smc_matrix* y, int y_scalar,
   // d_alpha[C], d_beta[K x C]] left on the device, no host synchronisation --
   // the form the row-sharded multi-GPU driver all-reduces
   Context& cx = ctx();
+  for (const smc_matrix* m : {x, y, io})
+    if (int rc = realize(m)) return rc;
+  if (d_x) d_x->zero_pending = false;  // overwritten
   CatArgs a;
   memset(&a, 0, sizeof(a));
   a.N = x->rows;
@@ -1055,8 +1057,7 @@ static int launch_cat_impl(CatMode mode, const smc_matrix* y, int y_scalar,
   while (ks_lin > 8
          && 4 * ((size_t)ks_lin * (2 * kLinBox + C8p) * 8 + 16) + lin_fixed > 216 * 1024)
     ks_lin /= 2;
-  if (const char* e = getenv("SMC_CAT_KS")) {  // tuning knob: attributes per stage
-    const int v = atoi(e);
+  if (const int v = knobs().cat_ks) {  // tuning knob: attributes per stage
     if (v == 8 || v == 16 || (v == 32 && ks_lin == 32)) ks_lin = v;
   }
   const size_t lin_stage = (size_t)ks_lin * (2 * kLinBox + C8p) * 8;
@@ -1356,7 +1357,7 @@ extern "C" int smc_linear_predictor_matrix_adjoint(const smc_matrix* x,
   const int64_t C = adj->cols;
   if (xt_adj) memset(xt_adj, 0, sizeof(double) * (size_t)K * C);
   if (colsum) memset(colsum, 0, sizeof(double) * (size_t)C);
-  if (N == 0 || C == 0) return SMC_OK;
+  if (N == 0 || C == 0 || adj->zero_pending) return SMC_OK;  // x^T 0
   Context& cx = ctx();
   if (xt_adj && K > 0) {
     for (int64_t c0 = 0; c0 < C; c0 += kCatBlock) {
@@ -1466,7 +1467,7 @@ extern "C" int smc_categorical_logit_glm_device(const smc_matrix* y, int y_scala
   if (!x || x->dtype != SMC_F64)
     return fail(SMC_ERR_INVALID_ARGUMENT, "%s: x must be an f64 device matrix", fn);
   const int64_t N = x->rows, K = x->cols, C = n_classes;
-  if (y && (y->dtype != SMC_I32 || y->rows * y->cols != N))
+  if (y && (y->dtype != SMC_I32 || y->rows * y->cols != N || !vec_contiguous(y)))
     return fail(SMC_ERR_INVALID_ARGUMENT, "%s: size of y does not match rows of x", fn);
   if (C < 1 || !params_dev || !out_dev)
     return fail(SMC_ERR_INVALID_ARGUMENT, "%s: NULL or empty params_dev / out_dev", fn);
@@ -1497,7 +1498,7 @@ extern "C" int smc_categorical_logit_glm(const smc_matrix* y, int y_scalar,
   if (!x || x->dtype != SMC_F64)
     return fail(SMC_ERR_INVALID_ARGUMENT, "%s: x must be an f64 device matrix", fn);
   const int64_t N = x->rows, K = x->cols, C = n_classes;
-  if (y && (y->dtype != SMC_I32 || y->rows * y->cols != N))
+  if (y && (y->dtype != SMC_I32 || y->rows * y->cols != N || !vec_contiguous(y)))
     return fail(SMC_ERR_INVALID_ARGUMENT,
                 "%s: size of y does not match rows of x", fn);  // L68-72
   if (C < 1 || !alpha || (K > 0 && !beta) || !logp)

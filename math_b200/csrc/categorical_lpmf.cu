@@ -232,7 +232,7 @@ extern "C" int smc_categorical_logit_lpmf(const smc_matrix* y, int y_scalar,
     return fail(SMC_ERR_INVALID_ARGUMENT, "%s: lin must be an f64 device matrix", fn);
   const int64_t N = lin->rows, C = lin->cols;
   if (y && (y->dtype != SMC_I32 || y->rows * y->cols != N
-            || (y->cols != 1 && y->rows != 1 && N != 0)))
+            || !vec_contiguous(y)))
     return fail(SMC_ERR_INVALID_ARGUMENT,
                 "%s: size of the random variable (%lld) does not match the rows of the "
                 "log odds (%lld)",
@@ -273,7 +273,12 @@ extern "C" int smc_categorical_logit_lpmf(const smc_matrix* y, int y_scalar,
   // when lin is data and propto drops the value, only check_finite is left: L22 / L41
   double* d = lin_var ? static_cast<double*>(d_lin->data) : nullptr;
   const int64_t d_ld = lin_var ? d_lin->ld : 0;
-  if (d) d_lin->version++;
+  if (d) {
+    d_lin->version++;
+    d_lin->zero_pending = false;  // overwritten
+  }
+  if (int rc = realize(lin)) return rc;
+  if (int rc = realize(y)) return rc;
   const double* l = static_cast<const double*>(lin->data);
   const int* yp = y ? static_cast<const int*>(y->data) : nullptr;
   if (lanes) {

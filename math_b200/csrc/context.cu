@@ -1,15 +1,26 @@
 // Per-thread runtime state and the device matrix type (matrix_cl analogue,
 // reference: stan/math/opencl/matrix_cl.hpp L46-55, opencl/copy.hpp).
+#include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "smc_internal.h"
 
 namespace smc {
 
+// t_ctx is the calling thread's own context; t_cur is the one launches go to: t_ctx,
+// or -- while a row-sharded call walks over the GPUs (sharded.cu) -- the context of
+// the shard's device.  Error text always lands in the thread's own context.
 static thread_local Context t_ctx;
+static thread_local Context* t_cur = &t_ctx;
 
-Context& ctx() { return t_ctx; }
+Context& ctx() { return *t_cur; }
+Context* swap_current_context(Context* c) {
+  Context* prev = t_cur;
+  t_cur = c ? c : &t_ctx;
+  return prev == &t_ctx ? nullptr : prev;
+}
 
 Context::~Context() {
   // Runs at thread exit; the CUDA runtime may already be gone at process exit,
@@ -32,6 +43,27 @@ std::mutex& cache_mutex() {
   return m;
 }
 
+static std::atomic<uint64_t> g_next_id{1};
+uint64_t next_matrix_id() { return g_next_id.fetch_add(1, std::memory_order_relaxed); }
+
+const Knobs& knobs() {
+  static const Knobs k = [] {
+    auto on = [](const char* name) {
+      const char* e = getenv(name);
+      return e && e[0] == '1';
+    };
+    Knobs v;
+    v.force_generic = on("SMC_FORCE_GENERIC");
+    v.dx_fused = on("SMC_DX_FUSED");
+    v.cat_dx_fma = on("SMC_CAT_DX_FMA");
+    v.cat_no_tma = on("SMC_CAT_NO_TMA");
+    const char* ks = getenv("SMC_CAT_KS");
+    v.cat_ks = ks ? atoi(ks) : 0;
+    return v;
+  }();
+  return k;
+}
+
 int fail(int status, const char* fmt, ...) {
   char buf[512];
   va_list ap;
@@ -42,8 +74,7 @@ int fail(int status, const char* fmt, ...) {
   return status;
 }
 
-static int bind_device(int device) {
-  Context& c = t_ctx;
+int init_context(Context& c, int device) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0)
@@ -59,7 +90,7 @@ static int bind_device(int device) {
     return SMC_OK;
   }
   if (c.inited) {
-    // moving the thread to another device: drop the old workspace
+    // moving the context to another device: drop the old workspace
     c.~Context();
     new (&c) Context();
   }
@@ -71,6 +102,7 @@ static int bind_device(int device) {
                 "device %d is sm_%d%d; this library is built for sm_100a only",
                 device, prop.major, prop.minor);
   c.device = device;
+  c.id = g_next_id.fetch_add(1, std::memory_order_relaxed);
   c.sm_count = prop.multiProcessorCount;
   SMC_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
   c.stream = c.own_stream;
@@ -80,9 +112,11 @@ static int bind_device(int device) {
   return SMC_OK;
 }
 
+static int bind_device(int device) { return init_context(t_ctx, device); }
+
 int ensure_ctx() {
-  if (t_ctx.inited) {
-    SMC_CUDA(cudaSetDevice(t_ctx.device));
+  if (t_cur->inited) {
+    SMC_CUDA(cudaSetDevice(t_cur->device));
     return SMC_OK;
   }
   return bind_device(0);
@@ -93,7 +127,7 @@ static int grow(void** p, size_t* have, size_t want, bool pinned) {
   size_t n = want < 4096 ? 4096 : want;
   if (*p) {
     // make sure nothing in flight still uses the old buffer
-    SMC_CUDA(cudaStreamSynchronize(t_ctx.stream));
+    SMC_CUDA(cudaStreamSynchronize(t_cur->stream));
     if (pinned)
       SMC_CUDA(cudaFreeHost(*p));
     else
@@ -110,7 +144,7 @@ static int grow(void** p, size_t* have, size_t want, bool pinned) {
 }
 
 int cache_alloc(void** p, size_t bytes) {
-  Context& c = t_ctx;
+  Context& c = *t_cur;
   auto it = c.block_cache.find(bytes);
   if (it != c.block_cache.end() && !it->second.empty()) {
     *p = it->second.back();
@@ -135,13 +169,13 @@ int cache_alloc(void** p, size_t bytes) {
 void cache_free(void* p, size_t bytes) {
   // work queued on this thread's stream may still touch the block; the next
   // owner is this thread again, on the same stream, so no synchronisation
-  Context& c = t_ctx;
+  Context& c = *t_cur;
   c.block_cache[bytes].push_back(p);
   c.cached_bytes += bytes;
 }
 
 void cache_trim() {
-  Context& c = t_ctx;
+  Context& c = *t_cur;
   if (c.cached_bytes == 0) return;
   cudaStreamSynchronize(c.stream);
   for (auto& kv : c.block_cache)
@@ -151,19 +185,19 @@ void cache_trim() {
 }
 
 int ensure_partials(size_t bytes) {
-  return grow(reinterpret_cast<void**>(&t_ctx.partials), &t_ctx.partials_bytes,
+  return grow(reinterpret_cast<void**>(&t_cur->partials), &t_cur->partials_bytes,
               bytes, false);
 }
 int ensure_params(size_t bytes) {
-  return grow(reinterpret_cast<void**>(&t_ctx.params_dev), &t_ctx.params_bytes,
+  return grow(reinterpret_cast<void**>(&t_cur->params_dev), &t_cur->params_bytes,
               bytes, false);
 }
 int ensure_out(size_t bytes) {
-  return grow(reinterpret_cast<void**>(&t_ctx.out_host), &t_ctx.out_bytes, bytes,
+  return grow(reinterpret_cast<void**>(&t_cur->out_host), &t_cur->out_bytes, bytes,
               true);
 }
 int ensure_scratch(size_t bytes) {
-  return grow(reinterpret_cast<void**>(&t_ctx.scratch), &t_ctx.scratch_bytes,
+  return grow(reinterpret_cast<void**>(&t_cur->scratch), &t_cur->scratch_bytes,
               bytes, false);
 }
 
@@ -181,6 +215,17 @@ __global__ void axpy_kernel(double* __restrict__ y, int64_t ldy,
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t c = i / rows, r = i - c * rows;
     y[c * ldy + r] += a * x[c * ldx + r];
+  }
+}
+
+__global__ void scale_copy_kernel(double* __restrict__ y, int64_t ldy,
+                                  const double* __restrict__ x, int64_t ldx,
+                                  int64_t rows, int64_t cols, double a) {
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = i / rows, r = i - c * rows;
+    y[c * ldy + r] = a * x[c * ldx + r];
   }
 }
 
@@ -209,17 +254,26 @@ __global__ void all_finite_kernel(const double* __restrict__ x, int64_t ld,
   if (__any_sync(0xffffffffu, local) && (threadIdx.x & 31) == 0) *bad = 1;
 }
 
-// out[i, k] = beta[k] * d[i]: the N x K partial of an autodiff design matrix as a
-// pure write stream (two rows per thread: one 16-byte store per column).
+// out[i, k] (+)= a * (beta[k] * d[i]).  RMW = false: the N x K partial beta (x) d of an
+// autodiff design matrix -- or its whole reverse sweep x.adj = lp.adj * beta (x) d when
+// the adjoint is known to be zero -- as a pure write stream (two rows per thread: one
+// 16-byte store per column).  RMW = true: x.adj += lp.adj * beta (x) d as one
+// read-modify-write of the adjoint; the product is never materialised
+// (rev/functor/operands_and_partials.hpp L28-38 with partial = beta (x) d,
+// prim/prob/neg_binomial_2_log_glm_lpmf.hpp L221-222).  SCALED = false skips the
+// multiplication by a (a = 1 would be exact anyway; it keeps the plain partial's
+// instruction stream as it was).
 struct OuterArgs {
   double* out;
   int64_t ld;
   const double* d;
   int64_t N;
   int K;
+  double a;
   const double* beta_dev;  // NULL: beta[] below
   double beta[kMaxParamDoubles];
 };
+template <bool RMW, bool SCALED>
 __global__ void __launch_bounds__(256)
     outer_kernel(const __grid_constant__ OuterArgs a) {
   const int64_t npairs = (a.N + 1) / 2;
@@ -232,10 +286,19 @@ __global__ void __launch_bounds__(256)
 #pragma unroll 8
     for (int k = 0; k < a.K; ++k) {
       const double b = a.beta_dev ? __ldg(a.beta_dev + k) : a.beta[k];
-      if (two)
-        *reinterpret_cast<double2*>(o + (int64_t)k * a.ld) = make_double2(b * d0, b * d1);
-      else
-        o[(int64_t)k * a.ld] = b * d0;
+      double v0 = b * d0, v1 = b * d1;
+      if (SCALED) {
+        v0 *= a.a;
+        v1 *= a.a;
+      }
+      double* ok = o + (int64_t)k * a.ld;
+      if (two) {
+        double2 cur = make_double2(0.0, 0.0);
+        if (RMW) cur = *reinterpret_cast<const double2*>(ok);
+        *reinterpret_cast<double2*>(ok) = make_double2(cur.x + v0, cur.y + v1);
+      } else {
+        ok[0] = (RMW ? ok[0] : 0.0) + v0;
+      }
     }
   }
 }
@@ -274,7 +337,7 @@ __global__ void fill_synth_kernel(void* data, int64_t ld, int64_t rows,
 
 static inline int grid_for(int64_t total, int threads) {
   int64_t b = (total + threads - 1) / threads;
-  const int64_t cap = (int64_t)t_ctx.sm_count * 16;
+  const int64_t cap = (int64_t)t_cur->sm_count * 16;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;
@@ -282,7 +345,7 @@ static inline int grid_for(int64_t total, int threads) {
 
 // Grid of the 2-D element-wise kernels: row chunks x columns, at most 16 CTAs per SM.
 static inline dim3 grid2d_for(int64_t rows, int64_t cols, int threads) {
-  const int64_t cap = (int64_t)t_ctx.sm_count * 16;
+  const int64_t cap = (int64_t)t_cur->sm_count * 16;
   int64_t gx = (rows + threads - 1) / threads;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
@@ -293,10 +356,11 @@ static inline dim3 grid2d_for(int64_t rows, int64_t cols, int threads) {
   return dim3((unsigned)gx, (unsigned)gy);
 }
 
-// out (N x K, ld) = d beta^T on this thread's stream; beta from the host or, when
-// beta_dev is set, from device memory (the asynchronous multi-GPU path).
-int launch_outer(double* out, int64_t ld, const double* d, int64_t N, int K,
-                 const double* beta_host, const double* beta_dev) {
+// out (N x K, ld) (+)= a * d beta^T on this thread's stream; beta from the host or,
+// when beta_dev is set, from device memory (the asynchronous multi-GPU path).
+static int launch_rank1(double* out, int64_t ld, const double* d, int64_t N, int K,
+                        const double* beta_host, const double* beta_dev, double scale,
+                        bool rmw) {
   if (N == 0 || K == 0) return SMC_OK;
   if (K > kMaxParamDoubles || (reinterpret_cast<uintptr_t>(out) & 15) || (K > 1 && (ld & 1)))
     return fail(SMC_ERR_UNSUPPORTED,
@@ -308,11 +372,37 @@ int launch_outer(double* out, int64_t ld, const double* d, int64_t N, int K,
   a.d = d;
   a.N = N;
   a.K = K;
+  a.a = scale;
   a.beta_dev = beta_dev;
   if (!beta_dev) memcpy(a.beta, beta_host, sizeof(double) * K);
-  outer_kernel<<<grid_for((N + 1) / 2, 256), 256, 0, t_ctx.stream>>>(a);
+  const int grid = grid_for((N + 1) / 2, 256);
+  if (rmw)
+    outer_kernel<true, true><<<grid, 256, 0, t_cur->stream>>>(a);
+  else if (scale != 1.0)
+    outer_kernel<false, true><<<grid, 256, 0, t_cur->stream>>>(a);
+  else
+    outer_kernel<false, false><<<grid, 256, 0, t_cur->stream>>>(a);
   SMC_CUDA(cudaGetLastError());
-  t_ctx.launches += 1;
+  t_cur->launches += 1;
+  return SMC_OK;
+}
+
+int launch_outer(double* out, int64_t ld, const double* d, int64_t N, int K,
+                 const double* beta_host, const double* beta_dev) {
+  return launch_rank1(out, ld, d, N, K, beta_host, beta_dev, 1.0, false);
+}
+
+// The deferred memset of a lazily zeroed matrix (smc_matrix_zero_lazy): runs before
+// anything reads the matrix or writes only part of it.
+int realize(const smc_matrix* mc) {
+  smc_matrix* m = const_cast<smc_matrix*>(mc);
+  if (!m || !m->zero_pending) return SMC_OK;
+  if (int rc = ensure_ctx()) return rc;
+  m->zero_pending = false;
+  if (m->rows == 0 || m->cols == 0) return SMC_OK;
+  const size_t es = m->dtype == SMC_F64 ? 8 : 4;
+  SMC_CUDA(cudaMemset2DAsync(m->data, (size_t)m->ld * es, 0, (size_t)m->rows * es,
+                             (size_t)m->cols, t_cur->stream));
   return SMC_OK;
 }
 
@@ -379,7 +469,7 @@ int smc_device_info(int* sm_count, int* cc_major, int* cc_minor,
   return SMC_OK;
 }
 
-const char* smc_last_error(void) { return ctx().last_error.c_str(); }
+const char* smc_last_error(void) { return t_ctx.last_error.c_str(); }
 int64_t smc_launch_count(void) { return ctx().launches; }
 void smc_reset_launch_count(void) { ctx().launches = 0; }
 
@@ -395,8 +485,11 @@ int smc_matrix_create(int64_t rows, int64_t cols, int dtype, smc_matrix** out) {
   m->cols = cols;
   m->dtype = dtype;
   m->device = ctx().device;
+  m->id = next_matrix_id();
+  m->home_ctx = ctx().id;
   const int64_t align = 128 / (int64_t)elem_size(dtype);
-  m->ld = cols > 1 ? (rows + align - 1) / align * align : rows;
+  // vectors (N x 1 and 1 x N) are contiguous: the kernels index them as data[i]
+  m->ld = (cols > 1 && rows > 1) ? (rows + align - 1) / align * align : rows;
   if (m->ld < 1) m->ld = 1;
   const size_t bytes = (size_t)m->ld * (size_t)(cols > 0 ? cols : 1) * elem_size(dtype);
   m->alloc_bytes = bytes < 256 ? 256 : (bytes + 255) & ~(size_t)255;
@@ -423,28 +516,47 @@ int smc_matrix_wrap(void* device_ptr, int64_t rows, int64_t cols, int64_t ld,
   m->dtype = dtype;
   m->owned = false;
   m->device = ctx().device;
+  m->id = next_matrix_id();
+  m->home_ctx = ctx().id;
   *out = m;
   return SMC_OK;
 }
 
 int smc_matrix_free(smc_matrix* m) {
   if (!m) return SMC_OK;
-  if (m->grp_perm || m->grp_off) {
+  const bool has_blocks = m->grp_perm || m->grp_off || (m->owned && m->data);
+  if (has_blocks) {
     if (int rc = ensure_ctx()) return rc;
-    if (m->grp_perm) cache_free(m->grp_perm, m->grp_perm_bytes);
-    if (m->grp_off) cache_free(m->grp_off, m->grp_off_bytes);
-  }
-  if (m->owned && m->data) {
-    if (int rc = ensure_ctx()) return rc;
-    if (m->device == ctx().device) {
-      cache_free(m->data, m->alloc_bytes);
-    } else {  // owned by another GPU than this thread's: hand it straight back
-      cudaSetDevice(m->device);
-      cudaFree(m->data);
-      cudaSetDevice(ctx().device);
-    }
+    // Recycling is stream-ordered only inside the thread (Context) that created the
+    // block and queued work on it.  Freed from anywhere else -- a finalizer thread,
+    // a TBB worker dropping the last reference, a thread bound to another GPU --
+    // the block goes straight back to the driver: cudaFree waits for the device.
+    const bool home = m->home_ctx == ctx().id && m->device == ctx().device;
+    auto give_back = [&](void* p, size_t bytes) {
+      if (!p) return;
+      if (home) {
+        cache_free(p, bytes);
+      } else {
+        cudaSetDevice(m->device);
+        cudaFree(p);
+        cudaSetDevice(ctx().device);
+      }
+    };
+    give_back(m->grp_perm, m->grp_perm_bytes);
+    give_back(m->grp_off, m->grp_off_bytes);
+    if (m->owned) give_back(m->data, m->alloc_bytes);
   }
   delete m;
+  return SMC_OK;
+}
+
+int smc_matrix_invalidate(smc_matrix* m) {
+  if (!m) return fail(SMC_ERR_INVALID_ARGUMENT, "NULL matrix");
+  std::lock_guard<std::mutex> lock(cache_mutex());
+  m->lgamma_valid = false;
+  m->range_valid = false;
+  m->binom_valid = false;
+  m->version += 1;
   return SMC_OK;
 }
 
@@ -452,7 +564,11 @@ int64_t smc_matrix_rows(const smc_matrix* m) { return m ? m->rows : 0; }
 int64_t smc_matrix_cols(const smc_matrix* m) { return m ? m->cols : 0; }
 int64_t smc_matrix_ld(const smc_matrix* m) { return m ? m->ld : 0; }
 int smc_matrix_dtype(const smc_matrix* m) { return m ? m->dtype : -1; }
-void* smc_matrix_data(const smc_matrix* m) { return m ? m->data : nullptr; }
+void* smc_matrix_data(const smc_matrix* m) {
+  if (!m) return nullptr;
+  realize(m);  // the raw pointer escapes: a deferred memset has to happen now
+  return m->data;
+}
 
 static int copy_rows(smc_matrix* m, int64_t row0, int64_t nrows, void* host,
                      int64_t ld_host, bool to_device) {
@@ -468,6 +584,10 @@ static int copy_rows(smc_matrix* m, int64_t row0, int64_t nrows, void* host,
   if (nrows == 0 || m->cols == 0) return SMC_OK;
   const size_t es = elem_size(m->dtype);
   char* dev = static_cast<char*>(m->data) + (size_t)row0 * es;
+  if (to_device && row0 == 0 && nrows == m->rows)
+    m->zero_pending = false;  // every element is overwritten
+  else if (int rc = realize(m))
+    return rc;
   if (to_device) {
     m->lgamma_valid = false;
     m->range_valid = false;
@@ -512,9 +632,19 @@ int smc_matrix_zero(smc_matrix* m) {
   m->lgamma_valid = false;
   m->range_valid = false;
   m->version += 1;
+  m->zero_pending = false;
   const size_t es = elem_size(m->dtype);
   SMC_CUDA(cudaMemset2DAsync(m->data, (size_t)m->ld * es, 0, (size_t)m->rows * es,
                              (size_t)m->cols, ctx().stream));
+  return SMC_OK;
+}
+
+int smc_matrix_zero_lazy(smc_matrix* m) {
+  if (!m) return fail(SMC_ERR_INVALID_ARGUMENT, "NULL matrix");
+  m->lgamma_valid = false;
+  m->range_valid = false;
+  m->version += 1;
+  m->zero_pending = true;
   return SMC_OK;
 }
 
@@ -524,6 +654,8 @@ int smc_matrix_copy(smc_matrix* dst, const smc_matrix* src) {
     return fail(SMC_ERR_INVALID_ARGUMENT, "copy: shape/dtype mismatch");
   if (int rc = ensure_ctx()) return rc;
   if (dst->rows == 0 || dst->cols == 0) return SMC_OK;
+  if (src->zero_pending) return dst == src ? SMC_OK : smc_matrix_zero(dst);
+  dst->zero_pending = false;
   dst->lgamma_valid = false;
   dst->range_valid = false;
   dst->version += 1;
@@ -542,10 +674,43 @@ int smc_matrix_axpy(smc_matrix* y, double a, const smc_matrix* x) {
   if (int rc = ensure_ctx()) return rc;
   const int64_t total = y->rows * y->cols;
   if (total == 0) return SMC_OK;
-  axpy_kernel<<<grid_for(total, 256), 256, 0, ctx().stream>>>(
-      static_cast<double*>(y->data), y->ld, static_cast<const double*>(x->data),
-      x->ld, y->rows, y->cols, a);
+  if (x->zero_pending) return SMC_OK;  // y += a * 0
+  y->version++;
+  if (y->zero_pending) {
+    // y = a * x: the adjoint's deferred memset and its read both drop out
+    y->zero_pending = false;
+    scale_copy_kernel<<<grid_for(total, 256), 256, 0, ctx().stream>>>(
+        static_cast<double*>(y->data), y->ld, static_cast<const double*>(x->data),
+        x->ld, y->rows, y->cols, a);
+  } else {
+    axpy_kernel<<<grid_for(total, 256), 256, 0, ctx().stream>>>(
+        static_cast<double*>(y->data), y->ld, static_cast<const double*>(x->data),
+        x->ld, y->rows, y->cols, a);
+  }
   SMC_CUDA(cudaGetLastError());
+  ctx().launches += 1;
+  return SMC_OK;
+}
+
+int smc_matrix_rank1_update(smc_matrix* y, double a, const smc_matrix* d,
+                            const double* beta) {
+  if (!y || !d || !beta || y->dtype != SMC_F64 || d->dtype != SMC_F64
+      || d->rows * d->cols != y->rows || !vec_contiguous(d))
+    return fail(SMC_ERR_INVALID_ARGUMENT, "rank1_update: shape/dtype mismatch");
+  if (int rc = ensure_ctx()) return rc;
+  if (y->rows == 0 || y->cols == 0) return SMC_OK;
+  if (int rc = realize(d)) return rc;
+  y->version++;
+  const bool rmw = !y->zero_pending;
+  y->zero_pending = false;
+  // wide matrices: column blocks of at most kMaxParamDoubles (beta travels by value)
+  for (int64_t c0 = 0; c0 < y->cols; c0 += kMaxParamDoubles) {
+    const int kc = (int)(y->cols - c0 < kMaxParamDoubles ? y->cols - c0 : kMaxParamDoubles);
+    if (int rc = launch_rank1(static_cast<double*>(y->data) + c0 * y->ld, y->ld,
+                              static_cast<const double*>(d->data), y->rows, kc, beta + c0,
+                              nullptr, a, rmw))
+      return rc;
+  }
   return SMC_OK;
 }
 
@@ -554,7 +719,9 @@ int smc_matrix_outer(smc_matrix* out, const smc_matrix* d, const double* beta) {
       || d->rows * d->cols != out->rows)
     return fail(SMC_ERR_INVALID_ARGUMENT, "outer: shape/dtype mismatch");
   if (int rc = ensure_ctx()) return rc;
+  if (int rc = realize(d)) return rc;
   out->version++;
+  out->zero_pending = false;
   return launch_outer(static_cast<double*>(out->data), out->ld,
                       static_cast<const double*>(d->data), out->rows, (int)out->cols, beta,
                       nullptr);
@@ -566,6 +733,7 @@ int smc_matrix_add_scalar(smc_matrix* y, double a) {
   if (int rc = ensure_ctx()) return rc;
   const int64_t total = y->rows * y->cols;
   if (total == 0) return SMC_OK;
+  if (int rc = realize(y)) return rc;
   y->version++;
   add_scalar_kernel<<<grid_for(total, 256), 256, 0, ctx().stream>>>(
       static_cast<double*>(y->data), y->ld, y->rows, y->cols, a);
@@ -579,7 +747,7 @@ int smc_matrix_all_finite(const smc_matrix* m, int* all_finite) {
   if (int rc = ensure_ctx()) return rc;
   *all_finite = 1;
   const int64_t total = m->rows * m->cols;
-  if (total == 0) return SMC_OK;
+  if (total == 0 || m->zero_pending) return SMC_OK;
   if (int rc = ensure_out(4096)) return rc;
   int* flag = reinterpret_cast<int*>(ctx().out_host);
   *flag = 0;
@@ -608,6 +776,7 @@ int smc_matrix_fill_synthetic(smc_matrix* m, uint64_t seed, int64_t row0,
   m->lgamma_valid = false;
   m->range_valid = false;
   m->version += 1;
+  m->zero_pending = false;
   const double c = scale / sqrt(4294967295.0 / 3.0);
   fill_synth_kernel<<<grid_for(total, 256), 256, 0, ctx().stream>>>(
       m->data, m->ld, m->rows, m->cols, m->dtype, seed, row0, kind, c, lo, hi);

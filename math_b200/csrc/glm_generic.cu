@@ -17,6 +17,10 @@ int prepare_args(const GlmCall& c, FusedArgs* ap) {
   FusedArgs& a = *ap;
   memset(&a, 0, sizeof(a));
   const smc_matrix* x = c.x;
+  for (const smc_matrix* m : {c.x, c.y, c.alpha_vec, c.aux_vec})
+    if (int rc = realize(m)) return rc;
+  for (smc_matrix* m : {c.d_alpha_vec, c.d_aux_vec, c.d_y_vec, c.d_x})
+    if (m) m->zero_pending = false;  // overwritten
   a.N = x->rows;
   a.K = (int)x->cols;
   a.x = static_cast<const double*>(x->data);
@@ -457,14 +461,40 @@ static int launch_glm_split_dx(const GlmCall& c) {
   return rc;
 }
 
+// SMC_DX_FACTORED: the caller takes the factor d of d_x = d beta^T (it applies the
+// product in its reverse sweep): the evaluation is the plain x-data sweep with d left
+// in the caller's vector.
+static int launch_glm_factored_dx(const GlmCall& c) {
+  GlmCall s = c;
+  // (SMC_VAR_X stays: it decides which terms survive propto; without d_x no kernel
+  // forms the product)
+  s.flags &= ~SMC_DX_FACTORED;
+  s.d_x = nullptr;
+  if (!c.d_alpha_vec) {
+    s.d_alpha_vec = c.d_x;
+    return launch_glm(s);
+  }
+  // a vector alpha wants the same d: evaluate into its partial and copy
+  if (int rc = launch_glm(s)) return rc;
+  c.d_x->version++;
+  c.d_x->zero_pending = false;
+  SMC_CUDA(cudaMemcpyAsync(c.d_x->data, c.d_alpha_vec->data,
+                           sizeof(double) * (size_t)c.x->rows, cudaMemcpyDeviceToDevice,
+                           ctx().stream));
+  ctx().flag_armed = false;  // the polled flag cannot cover the copy
+  return SMC_OK;
+}
+
 int launch_glm(const GlmCall& c) {
-  const char* force = getenv("SMC_FORCE_GENERIC");
+  if ((c.flags & SMC_VAR_X) && (c.flags & SMC_DX_FACTORED) && c.d_x)
+    return launch_glm_factored_dx(c);
+  const bool force_generic = knobs().force_generic;
   // (d_x leaves the fused kernel through TMA stores: same layout rules as x)
   const bool dx_ok = !((c.flags & SMC_VAR_X) && c.d_x) || fused_supported(c.d_x);
-  if (fused_supported(c.x) && dx_ok && !(force && force[0] == '1')
+  if (fused_supported(c.x) && dx_ok && !force_generic
       && c.ncuts <= 4 * 32 * ((c.x->cols + 31) / 32)) {
-    const char* fused_dx = getenv("SMC_DX_FUSED");  // A/B: d_x from the sweep itself
-    if ((c.flags & SMC_VAR_X) && c.d_x && c.x->rows > 0 && !(fused_dx && fused_dx[0] == '1'))
+    // (SMC_DX_FUSED=1: A/B switch, d_x from the sweep itself)
+    if ((c.flags & SMC_VAR_X) && c.d_x && c.x->rows > 0 && !knobs().dx_fused)
       return launch_glm_split_dx(c);
     return launch_glm_fused(c);
   }
@@ -472,7 +502,7 @@ int launch_glm(const GlmCall& c) {
   // cut points ride with the last chunk, which must be able to take them)
   if (c.x && c.x->cols > kMaxFusedK && fused_layout_ok(c.x)
       && (!((c.flags & SMC_VAR_X) && c.d_x) || fused_layout_ok(c.d_x)) && !c.params_dev
-      && c.beta_host && !(force && force[0] == '1') && c.ncuts <= 4 * 32)
+      && c.beta_host && !force_generic && c.ncuts <= 4 * 32)
     return launch_glm_chunked(c);
   return launch_glm_generic(c);
 }

@@ -181,7 +181,7 @@ int group_index(const char* fn, const smc_matrix* idxc, int64_t G) {
 }
 
 int check_index(const char* fn, const smc_matrix* idx, int64_t G) {
-  if (!idx || idx->dtype != SMC_I32 || (idx->cols != 1 && idx->rows != 1 && idx->rows * idx->cols))
+  if (!idx || idx->dtype != SMC_I32 || !vec_contiguous(idx))
     return fail(SMC_ERR_INVALID_ARGUMENT, "%s: idx must be an i32 device vector", fn);
   if (idx->rows * idx->cols == 0) return SMC_OK;
   int lo, hi;
@@ -201,9 +201,10 @@ int smc_indexing(const double* z, int64_t G, const smc_matrix* idx, smc_matrix* 
   if (int rc = ensure_ctx()) return rc;
   if (int rc = check_index(fn, idx, G)) return rc;
   const int64_t n = idx->rows * idx->cols;
-  if (!out || out->dtype != SMC_F64 || out->rows * out->cols != n)
+  if (!out || out->dtype != SMC_F64 || out->rows * out->cols != n || !vec_contiguous(out))
     return fail(SMC_ERR_INVALID_ARGUMENT, "%s: out must hold size(idx) doubles", fn);
   if (n == 0) return SMC_OK;
+  out->zero_pending = false;  // overwritten
   if (!z || G <= 0) return fail(SMC_ERR_INVALID_ARGUMENT, "%s: empty source vector", fn);
   Context& c = ctx();
   if (int rc = ensure_params(sizeof(double) * (size_t)G)) return rc;
@@ -225,9 +226,10 @@ int smc_indexing_rev(const smc_matrix* idx, const smc_matrix* res_adj, int64_t G
   if (int rc = ensure_ctx()) return rc;
   if (int rc = check_index(fn, idx, G)) return rc;
   const int64_t n = idx->rows * idx->cols;
-  if (!res_adj || res_adj->dtype != SMC_F64 || res_adj->rows * res_adj->cols != n)
+  if (!res_adj || res_adj->dtype != SMC_F64 || res_adj->rows * res_adj->cols != n
+      || !vec_contiguous(res_adj))
     return fail(SMC_ERR_INVALID_ARGUMENT, "%s: res_adj must hold size(idx) doubles", fn);
-  if (n == 0 || G <= 0) return SMC_OK;
+  if (n == 0 || G <= 0 || res_adj->zero_pending) return SMC_OK;
   if (!adj_z) return fail(SMC_ERR_INVALID_ARGUMENT, "%s: NULL adj_z", fn);
   Context& c = ctx();
   if (G > kMaxGroupsFast) {

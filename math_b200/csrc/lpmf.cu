@@ -32,7 +32,7 @@ smc_matrix empty_design(int64_t N) {
   return x;
 }
 
-bool is_vec(const smc_matrix* m) { return m->cols == 1 || m->rows == 1 || m->rows * m->cols == 0; }
+bool is_vec(const smc_matrix* m) { return vec_contiguous(m); }
 
 // theta must be an f64 vector; y (if a vector) and the other per-row operands
 // must have its length.
@@ -49,7 +49,7 @@ int theta_shapes(const char* fn, const smc_matrix* theta, const smc_matrix* y,
                 fn, (long long)(y->rows * y->cols), (long long)*N);
   const smc_matrix* vs[3] = {v1, d_theta, d_v1};
   for (const smc_matrix* v : vs)
-    if (v && (v->dtype != SMC_F64 || v->rows * v->cols != *N))
+    if (v && (v->dtype != SMC_F64 || v->rows * v->cols != *N || !is_vec(v)))
       return fail(SMC_ERR_INVALID_ARGUMENT,
                   "%s: size of a per-row vector (%lld) does not match the size of "
                   "the parameter (%lld)",
@@ -121,9 +121,11 @@ int smc_linear_predictor(const smc_matrix* x, const double* beta,
     return fail(SMC_ERR_INVALID_ARGUMENT, "%s: x must be an f64 device matrix", fn);
   const int64_t N = x->rows, K = x->cols;
   if (K > 0 && !beta) return fail(SMC_ERR_INVALID_ARGUMENT, "%s: NULL beta", fn);
-  if (!theta_out || theta_out->dtype != SMC_F64 || theta_out->rows * theta_out->cols != N)
+  if (!theta_out || theta_out->dtype != SMC_F64 || theta_out->rows * theta_out->cols != N
+      || !is_vec(theta_out))
     return fail(SMC_ERR_INVALID_ARGUMENT, "%s: theta_out must hold rows(x) doubles", fn);
-  if (alpha_vec && (alpha_vec->dtype != SMC_F64 || alpha_vec->rows * alpha_vec->cols != N))
+  if (alpha_vec && (alpha_vec->dtype != SMC_F64 || alpha_vec->rows * alpha_vec->cols != N
+                    || !is_vec(alpha_vec)))
     return fail(SMC_ERR_INVALID_ARGUMENT,
                 "%s: size of alpha (%lld) does not match rows of x (%lld)", fn,
                 (long long)(alpha_vec->rows * alpha_vec->cols), (long long)N);
@@ -148,11 +150,11 @@ int smc_linear_predictor_adjoint(const smc_matrix* x, const smc_matrix* v,
   if (!x || x->dtype != SMC_F64)
     return fail(SMC_ERR_INVALID_ARGUMENT, "%s: x must be an f64 device matrix", fn);
   const int64_t N = x->rows, K = x->cols;
-  if (!v || v->dtype != SMC_F64 || v->rows * v->cols != N)
+  if (!v || v->dtype != SMC_F64 || v->rows * v->cols != N || !is_vec(v))
     return fail(SMC_ERR_INVALID_ARGUMENT, "%s: v must hold rows(x) doubles", fn);
   if (sum_v) *sum_v = 0.0;
   if (xt_v) memset(xt_v, 0, sizeof(double) * K);
-  if (N == 0) return SMC_OK;
+  if (N == 0 || v->zero_pending) return SMC_OK;  // x^T 0
   std::vector<double> zeros((size_t)K, 0.0);
   GlmCall c;
   c.family = kLinear;
@@ -320,7 +322,7 @@ int smc_normal_lpdf(const smc_matrix* y, double y_scalar, const smc_matrix* mu,
   const int64_t N = ref->rows * ref->cols;
   const smc_matrix* vs[4] = {y, mu, d_y_vec, d_mu_vec};
   for (const smc_matrix* v : vs)
-    if (v && (v->dtype != SMC_F64 || v->rows * v->cols != N))
+    if (v && (v->dtype != SMC_F64 || v->rows * v->cols != N || !is_vec(v)))
       return fail(SMC_ERR_INVALID_ARGUMENT,
                   "%s: sizes of the random variable and the location parameter do not "
                   "match",

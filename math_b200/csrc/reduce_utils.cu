@@ -56,6 +56,7 @@ static int compute_stats(const smc_matrix* yc) {
   std::lock_guard<std::mutex> lock(cache_mutex());
   if (y->range_valid && y->lgamma_valid) return SMC_OK;
   if (int rc = ensure_ctx()) return rc;
+  if (int rc = realize(y)) return rc;
   Context& c = ctx();
   const int64_t n = y->rows * y->cols;
   if (y->cols > 1 && y->ld != y->rows)
@@ -201,7 +202,7 @@ int binom_stats(const smc_matrix* n, int n_scalar, const smc_matrix* trials,
   const int partner_scalar = n ? trials_scalar : n_scalar;
   std::lock_guard<std::mutex> lock(cache_mutex());
   if (owner && owner->binom_valid && owner->binom_self_version == owner->version
-      && owner->binom_partner == (partner ? partner->data : nullptr)
+      && owner->binom_partner_id == (partner ? partner->id : 0)
       && (partner ? owner->binom_partner_version == partner->version
                   : owner->binom_partner_scalar == partner_scalar)) {
     *in_support = owner->binom_in_support;
@@ -209,6 +210,8 @@ int binom_stats(const smc_matrix* n, int n_scalar, const smc_matrix* trials,
     return SMC_OK;
   }
   if (int rc = ensure_ctx()) return rc;
+  if (int rc = realize(n)) return rc;
+  if (int rc = realize(trials)) return rc;
   Context& c = ctx();
   int grid = (int)((count + kRedThreads - 1) / kRedThreads);
   if (grid > c.sm_count * 8) grid = c.sm_count * 8;
@@ -237,7 +240,7 @@ int binom_stats(const smc_matrix* n, int n_scalar, const smc_matrix* trials,
   if (owner) {
     owner->binom_valid = true;
     owner->binom_self_version = owner->version;
-    owner->binom_partner = partner ? partner->data : nullptr;
+    owner->binom_partner_id = partner ? partner->id : 0;
     owner->binom_partner_version = partner ? partner->version : 0;
     owner->binom_partner_scalar = partner_scalar;
     owner->binom_in_support = ok;

@@ -37,6 +37,7 @@ enum Family {
 
 // Per-host-thread state: device, stream, reusable workspace.
 struct Context {
+  uint64_t id = 0;  // process-unique, assigned when the thread binds a device
   int device = -1;
   bool inited = false;
   cudaStream_t own_stream = nullptr;
@@ -67,6 +68,12 @@ struct Context {
 };
 
 Context& ctx();
+// Makes `c` (a shard's context) the one this thread's launches go to; NULL restores
+// the thread's own.  Returns the previous shard context (NULL: the thread's own).
+Context* swap_current_context(Context* c);
+int init_context(Context& c, int device);  // binds `c` to a device: stream + workspace
+// The deferred memset of a lazily zeroed matrix; call before reading `m`.
+int realize(const smc_matrix* m);
 // Guards the caches that live ON a matrix (TMA descriptor, y statistics, binomial
 // pair statistics): several host threads -- chains -- share one read-only x / y,
 // and the first of them to need a cached item fills it in.
@@ -146,6 +153,15 @@ int binom_stats(const smc_matrix* n, int n_scalar, const smc_matrix* trials,
                 int trials_scalar, int64_t count, bool* in_support,
                 double* coef_sum);
 
+// Once-initialised A/B switches (environment variables read on first use, never on
+// the evaluation path afterwards).
+struct Knobs {
+  bool force_generic, dx_fused, cat_dx_fma, cat_no_tma;
+  int cat_ks;
+};
+const Knobs& knobs();
+uint64_t next_matrix_id();
+
 int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
                        const double* alpha_host, const double* beta_host,
                        int64_t C, unsigned flags, double* out_host_logp,
@@ -154,6 +170,12 @@ int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
 }  // namespace smc
 
 struct smc_matrix {
+  // process-unique identity (a freed block is recycled at the same address and a
+  // fresh handle restarts at version 1: caches that involve a second matrix key on
+  // (id, version), never on the data pointer)
+  uint64_t id = 0;
+  // the Context (host thread) whose block cache / stream the owned block belongs to
+  uint64_t home_ctx = 0;
   void* data = nullptr;
   int64_t rows = 0, cols = 0, ld = 0;
   int dtype = SMC_F64;
@@ -173,9 +195,12 @@ struct smc_matrix {
   // bumped by every call that writes the matrix: keys caches that involve a
   // second matrix (the binomial pair statistics below)
   uint64_t version = 0;
+  // smc_matrix_zero_lazy: every element is zero by declaration, the memset has not
+  // run (and never will if the next writer overwrites the whole matrix)
+  bool zero_pending = false;
   // cached binom_stats() of (this, partner): valid while both versions match
   bool binom_valid = false;
-  const void* binom_partner = nullptr;
+  uint64_t binom_partner_id = 0;
   uint64_t binom_partner_version = 0, binom_self_version = 0;
   int binom_partner_scalar = 0;
   bool binom_in_support = false;
@@ -190,3 +215,11 @@ struct smc_matrix {
   int64_t grp_G = 0;
   uint64_t grp_version = 0;
 };
+
+namespace smc {
+// A per-row operand (N x 1 or 1 x N) the kernels index as data[i]: contiguous.
+// smc_matrix_create lays vectors out that way; a wrapped strided row is refused.
+inline bool vec_contiguous(const smc_matrix* m) {
+  return m->cols <= 1 || m->rows * m->cols == 0 || (m->rows == 1 && m->ld == 1);
+}
+}  // namespace smc

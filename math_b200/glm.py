@@ -19,12 +19,15 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
-from ._lib import (PROPTO, VAR_ALPHA, VAR_AUX, VAR_BETA, VAR_X, VAR_Y, check, lib)
+from ._lib import (DX_FACTORED, PROPTO, VAR_ALPHA, VAR_AUX, VAR_BETA, VAR_X, VAR_Y,
+                   check, lib)
 from .matrix_cuda import MatrixCuda
 
 _DP = C.POINTER(C.c_double)
 
-_FLAG = {"x": VAR_X, "alpha": VAR_ALPHA, "beta": VAR_BETA, "sigma": VAR_AUX,
+# "x_factored": x is an autodiff variable and d_x comes back as the N x 1 factor d of
+# d_x = d beta^T (SMC_DX_FACTORED; applied with MatrixCuda.rank1_update)
+_FLAG = {"x": VAR_X, "x_factored": VAR_X | DX_FACTORED, "alpha": VAR_ALPHA, "beta": VAR_BETA, "sigma": VAR_AUX,
          "phi": VAR_AUX, "cuts": VAR_AUX, "y": VAR_Y}
 
 
@@ -74,6 +77,8 @@ def _vec_out(cond, N):
 
 
 def _dx_out(flags, x):
+    if flags & DX_FACTORED:
+        return MatrixCuda(x.rows, 1, np.float64)
     return MatrixCuda(x.rows, x.cols, np.float64) if flags & VAR_X else None
 
 

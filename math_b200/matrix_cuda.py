@@ -94,6 +94,16 @@ class MatrixCuda:
         return (self.rows, self.cols)
 
     # -- transfers -------------------------------------------------------------
+    def upload(self, a):
+        a = np.asfortranarray(np.asarray(a, dtype=self.dtype))
+        if a.ndim == 1:
+            a = a.reshape(-1, 1)
+        if a.shape != (self.rows, self.cols):
+            raise ValueError("upload: shape mismatch")
+        if a.size:
+            check(lib().smc_matrix_upload(self._h, a.ctypes.data_as(C.c_void_p),
+                                          max(a.shape[0], 1)))
+
     def upload_rows(self, row0, a):
         a = np.asfortranarray(np.asarray(a, dtype=self.dtype))
         if a.ndim == 1:
@@ -120,13 +130,37 @@ class MatrixCuda:
     def zero(self):
         check(lib().smc_matrix_zero(self._h))
 
+    def zero_lazy(self):
+        """Declares the matrix zero without touching memory (the adjoint of a device
+        var): the memset only runs if something reads it before a whole-matrix
+        writer (axpy, rank1_update, upload, copy) gets there."""
+        check(lib().smc_matrix_zero_lazy(self._h))
+
+    def invalidate(self):
+        """For wrapped memory whose contents changed behind the library's back."""
+        check(lib().smc_matrix_invalidate(self._h))
+
     def axpy(self, a, x):
         check(lib().smc_matrix_axpy(self._h, float(a), x._h))
+
+    def rank1_update(self, a, d, beta):
+        """self[i, k] += a * d[i] * beta[k]: the reverse sweep of an autodiff design
+        matrix from the factor d (rev/functor/operands_and_partials.hpp L28-38)."""
+        b = np.ascontiguousarray(beta, dtype=np.float64).ravel()
+        if b.size != self.cols:
+            raise ValueError("rank1_update: size of beta does not match the columns")
+        check(lib().smc_matrix_rank1_update(self._h, float(a), d._h,
+                                            b.ctypes.data_as(C.POINTER(C.c_double))))
 
     def fill_synthetic(self, seed, row0=0, kind=0, scale=1.0, lo=0, hi=1):
         check(lib().smc_matrix_fill_synthetic(self._h, int(seed), int(row0),
                                               int(kind), float(scale), int(lo),
                                               int(hi)))
+
+    def int_range(self):
+        lo, hi = C.c_int(), C.c_int()
+        check(lib().smc_matrix_int_range(self._h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
 
     def all_finite(self):
         r = C.c_int()

@@ -82,8 +82,19 @@ class ShardedGlm:
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
 
+    def _adopt_stream(self):
+        """The library launches on its own non-blocking stream unless told otherwise:
+        the parameter copy / broadcast before the kernel and the all-reduce after it
+        are only ordered with it when all of them share torch's current stream."""
+        if self.local_eval in (cuda_local_eval, cuda_local_eval_categorical):
+            s = self.torch.cuda.current_stream().cuda_stream
+            if s != getattr(self, "_stream", None):
+                check(lib().smc_set_stream(C.c_void_p(s)))
+                self._stream = s
+
     def evaluate(self, params_host=None, **row_outputs):
         t = self.torch
+        self._adopt_stream()
         if self.rank == 0 and params_host is not None:
             p = t.as_tensor(np.ascontiguousarray(params_host, dtype=np.float64))
             self.params.copy_(p, non_blocking=True)
@@ -137,6 +148,7 @@ class ShardedCategoricalGlm(ShardedGlm):
 
     def evaluate(self, params_host=None, **row_outputs):
         t = self.torch
+        self._adopt_stream()
         if self.rank == 0 and params_host is not None:
             p = t.as_tensor(np.ascontiguousarray(params_host, dtype=np.float64))
             self.params.copy_(p, non_blocking=True)

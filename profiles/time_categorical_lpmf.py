@@ -1,6 +1,6 @@
 """Timing of the un-fused categorical_logit_lpmf on a device N x C matrix of log odds
 (value + d_lin: reads N*C*8, writes N*C*8 bytes).  Wall-clock over synchronous C-ABI
-calls; run alone on the GPU (profiles/run_r01m.sh)."""
+calls; run alone on the GPU ."""
 import sys, time, json
 sys.path.insert(0, '/root/repo')
 import numpy as np, math_b200 as mb

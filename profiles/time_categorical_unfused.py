@@ -1,6 +1,6 @@
 """Un-fused categorical pipeline at BASELINE config 5a (N=2e6, K=512, C=32) next to the fused
 GLM: multiply_matrix (DMMA sweep 1) -> categorical_logit_lpmf -> multiply_matrix_adjoint (DMMA
-sweep 2 + column sums).  Wall-clock over synchronous calls, run alone (profiles/run_r01o.sh)."""
+sweep 2 + column sums).  Wall-clock over synchronous calls, run alone ."""
 import sys, time, json
 sys.path.insert(0, '/root/repo')
 import numpy as np, math_b200 as mb
