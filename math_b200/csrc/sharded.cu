@@ -1,0 +1,442 @@
+// Row-sharded device matrices: the GPUs of one box behind the SAME entry points.
+//
+// A sharded smc_matrix is a handle whose rows are partitioned contiguously over G
+// GPUs (shard g holds rows [g N / G, (g+1) N / G), uploaded once).  Every GLM entry
+// point of the C ABI -- and therefore every C++ overload in include/stan/math/cuda/
+// -- takes such a handle wherever it takes a plain one: one evaluation then
+//   1. launches the fused kernel on every GPU, each on its own stream, with the small
+//      parameters travelling as kernel arguments (that IS the broadcast: G launches
+//      carry beta to G devices, no copy, no collective),
+//   2. all-reduces the packed K + O(1) result in place over NCCL (NVLink / NVSwitch)
+//      on those same streams,
+//   3. reads the reduced vector back once from shard 0 into pinned host memory.
+// N-vector partials and the N x K adjoint of an autodiff x stay sharded: no exchange.
+//
+// This is the reference's "scatter static data once, broadcast parameters per call,
+// reduce results" pattern (stan/math/prim/functor/mpi_parallel_call.hpp L332-392,
+// L408-449) with one host process and one communicator rank per device, and it is
+// what the OpenCL backend's single-device limit (opencl/opencl_context.hpp L75-76)
+// keeps it from doing.
+//
+// NCCL is bound at run time (dlopen of libnccl.so.2): programs that never shard do
+// not need it.  SMC_SHARD_REDUCE=host replaces step 2 + 3 by G packed results written
+// straight into mapped host memory and summed there in shard order; that is also the
+// fallback when NCCL is missing or when several shards share one GPU (single-GPU
+// tests of the sharded logic).
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <vector>
+
+#include "smc_internal.h"
+
+namespace smc {
+
+namespace {
+
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t,
+                            ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load() {
+    if (lib) return true;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) return false;
+#define SMC_NCCL_SYM(field, sym) \
+  field = reinterpret_cast<decltype(field)>(dlsym(lib, sym)); \
+  if (!field) return false;
+    SMC_NCCL_SYM(CommInitAll, "ncclCommInitAll")
+    SMC_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    SMC_NCCL_SYM(AllReduce, "ncclAllReduce")
+    SMC_NCCL_SYM(GroupStart, "ncclGroupStart")
+    SMC_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+    SMC_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef SMC_NCCL_SYM
+    return true;
+  }
+};
+
+struct Shard {
+  int device = 0;
+  Context ctx;                  // stream + workspace of this shard
+  ncclComm_t comm = nullptr;    // this shard's rank of the communicator
+  double* out_dev = nullptr;    // packed result of the shard (all-reduced in place)
+  size_t out_bytes = 0;
+};
+
+struct ShardComm {
+  std::mutex mu;  // one sharded call at a time (chains sharing the GPUs take turns)
+  std::vector<Shard*> shards;
+  NcclApi nccl;
+  bool use_nccl = false;
+  std::string reduce_mode;  // "nccl" | "host"
+  double* host_out = nullptr;  // pinned read-back buffer of the reduced result
+  size_t host_bytes = 0;
+  std::vector<double> host_sum;
+};
+
+ShardComm& comm() {
+  static ShardComm c;
+  return c;
+}
+
+// Makes a shard's context (device, stream, workspace) the calling thread's current
+// one for the lifetime of the scope.
+struct ShardScope {
+  Context* prev;
+  explicit ShardScope(Shard* s) {
+    prev = swap_current_context(&s->ctx);
+    cudaSetDevice(s->device);
+  }
+  ~ShardScope() {
+    swap_current_context(prev);
+    Context& cur = ctx();
+    if (cur.inited) cudaSetDevice(cur.device);
+  }
+};
+
+#define SMC_NCCL(expr)                                                          \
+  do {                                                                          \
+    ncclResult_t r__ = (expr);                                                  \
+    if (r__ != ncclSuccess)                                                     \
+      return fail(SMC_ERR_CUDA, "%s failed: %s", #expr,                         \
+                  comm().nccl.GetErrorString(r__));                             \
+  } while (0)
+
+void shutdown_locked(ShardComm& sc) {
+  for (Shard* s : sc.shards) {
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->ctx.stream);
+    if (s->comm && sc.nccl.CommDestroy) sc.nccl.CommDestroy(s->comm);
+    if (s->out_dev) cudaFree(s->out_dev);
+    delete s;  // ~Context releases the stream and the workspace
+  }
+  sc.shards.clear();
+  if (sc.host_out) cudaFreeHost(sc.host_out);
+  sc.host_out = nullptr;
+  sc.host_bytes = 0;
+  sc.use_nccl = false;
+  Context& cur = ctx();
+  if (cur.inited) cudaSetDevice(cur.device);
+}
+
+}  // namespace
+
+int shard_count_of(const smc_matrix* m) { return m ? (int)m->shards.size() : 0; }
+
+bool same_partition(const smc_matrix* a, const smc_matrix* b) {
+  if (a->shards.size() != b->shards.size() || a->rows != b->rows) return false;
+  for (size_t g = 0; g < a->shards.size(); ++g)
+    if (a->shards[g]->rows != b->shards[g]->rows
+        || a->shards[g]->device != b->shards[g]->device)
+      return false;
+  return true;
+}
+
+int for_each_shard(const smc_matrix* m,
+                   const std::function<int(int, smc_matrix*, int64_t)>& fn) {
+  ShardComm& sc = comm();
+  if (m->shards.size() != sc.shards.size())
+    return fail(SMC_ERR_INVALID_ARGUMENT,
+                "sharded matrix with %zu shards, but the shard set has %zu (was "
+                "smc_shard_shutdown / smc_shard_init called since it was created?)",
+                m->shards.size(), sc.shards.size());
+  for (size_t g = 0; g < m->shards.size(); ++g) {
+    ShardScope scope(sc.shards[g]);
+    if (int rc = fn((int)g, m->shards[g], m->shard_row0[g])) return rc;
+  }
+  return SMC_OK;
+}
+
+int synchronize_shards() {
+  ShardComm& sc = comm();
+  for (Shard* s : sc.shards) {
+    SMC_CUDA(cudaSetDevice(s->device));
+    SMC_CUDA(cudaStreamSynchronize(s->ctx.stream));
+  }
+  Context& cur = ctx();
+  if (cur.inited) SMC_CUDA(cudaSetDevice(cur.device));
+  return SMC_OK;
+}
+
+// One evaluation of a memory-bound GLM family over the shards of c.x; *out points at
+// the reduced packed result (n_out doubles) in host memory.
+int run_sharded(GlmCall& c, int n_out, const double** out) {
+  ShardComm& sc = comm();
+  const int G = (int)c.x->shards.size();
+  if ((int)sc.shards.size() != G)
+    return fail(SMC_ERR_INVALID_ARGUMENT,
+                "x has %d shards, but the shard set has %zu", G, sc.shards.size());
+  // every per-row operand follows the row partition of x
+  const smc_matrix* ops[] = {c.y, c.alpha_vec, c.aux_vec, c.d_alpha_vec, c.d_aux_vec,
+                             c.d_y_vec, c.d_x};
+  for (const smc_matrix* m : ops)
+    if (m && (m->shards.empty() || !same_partition(m, c.x)))
+      return fail(SMC_ERR_INVALID_ARGUMENT,
+                  "a per-row operand is not sharded like x (create it with "
+                  "smc_matrix_create_like)");
+  std::lock_guard<std::mutex> lock(sc.mu);
+  const size_t bytes = sizeof(double) * (size_t)n_out;
+  int64_t launches = 0;
+  const bool host_reduce = !sc.use_nccl;
+  for (int g = 0; g < G; ++g) {
+    Shard* s = sc.shards[g];
+    ShardScope scope(s);
+    GlmCall cg = c;
+    cg.x = c.x->shards[g];
+    auto pick = [g](const smc_matrix* m) { return m ? m->shards[g] : nullptr; };
+    cg.y = pick(c.y);
+    cg.alpha_vec = pick(c.alpha_vec);
+    cg.aux_vec = pick(c.aux_vec);
+    cg.d_alpha_vec = const_cast<smc_matrix*>(pick(c.d_alpha_vec));
+    cg.d_aux_vec = const_cast<smc_matrix*>(pick(c.d_aux_vec));
+    cg.d_y_vec = const_cast<smc_matrix*>(pick(c.d_y_vec));
+    cg.d_x = const_cast<smc_matrix*>(pick(c.d_x));
+    cg.done_flag = nullptr;
+    cg.once_terms = g == 0;  // terms the reference adds once per call, not per row
+    if (host_reduce) {
+      // the shard's last CTA stores its packed result straight into mapped host memory
+      if (int rc = ensure_out(bytes)) return rc;
+      cg.out = s->ctx.out_host;
+    } else {
+      if (s->out_bytes < bytes) {
+        SMC_CUDA(cudaStreamSynchronize(s->ctx.stream));
+        if (s->out_dev) SMC_CUDA(cudaFree(s->out_dev));
+        s->out_dev = nullptr;
+        const size_t want = bytes < 4096 ? 4096 : bytes;
+        SMC_CUDA(cudaMalloc(&s->out_dev, want));
+        s->out_bytes = want;
+      }
+      cg.out = s->out_dev;
+    }
+    const int64_t before = s->ctx.launches;
+    if (cg.x->rows == 0) {  // more shards than rows: contributes zeros
+      if (host_reduce)
+        memset(s->ctx.out_host, 0, bytes);
+      else
+        SMC_CUDA(cudaMemsetAsync(s->out_dev, 0, bytes, s->ctx.stream));
+    } else if (int rc = launch_glm(cg)) {
+      return rc;
+    }
+    launches += s->ctx.launches - before;
+  }
+  if (sc.host_bytes < bytes) {
+    if (sc.host_out) SMC_CUDA(cudaFreeHost(sc.host_out));
+    sc.host_out = nullptr;
+    const size_t want = bytes < 4096 ? 4096 : bytes;
+    SMC_CUDA(cudaHostAlloc(&sc.host_out, want, cudaHostAllocPortable));
+    sc.host_bytes = want;
+  }
+  if (host_reduce) {
+    if (int rc = synchronize_shards()) return rc;
+    // fixed order over the shards: bit-reproducible for a given shard count
+    for (int j = 0; j < n_out; ++j) {
+      double v = 0.0;
+      for (int g = 0; g < G; ++g) v += sc.shards[g]->ctx.out_host[j];
+      sc.host_out[j] = v;
+    }
+  } else {
+    SMC_NCCL(sc.nccl.GroupStart());
+    for (int g = 0; g < G; ++g) {
+      Shard* s = sc.shards[g];
+      SMC_NCCL(sc.nccl.AllReduce(s->out_dev, s->out_dev, (size_t)n_out, ncclDouble, ncclSum,
+                                 s->comm, s->ctx.stream));
+    }
+    SMC_NCCL(sc.nccl.GroupEnd());
+    Shard* s0 = sc.shards[0];
+    SMC_CUDA(cudaSetDevice(s0->device));
+    SMC_CUDA(cudaMemcpyAsync(sc.host_out, s0->out_dev, bytes, cudaMemcpyDeviceToHost,
+                             s0->ctx.stream));
+    SMC_CUDA(cudaStreamSynchronize(s0->ctx.stream));
+    Context& cur = ctx();
+    if (cur.inited) SMC_CUDA(cudaSetDevice(cur.device));
+  }
+  own_ctx().launches += launches + (host_reduce ? 0 : G);
+  *out = sc.host_out;
+  return SMC_OK;
+}
+
+}  // namespace smc
+
+using namespace smc;
+
+extern "C" {
+
+int smc_shard_init(int n_shards, const int* devices) {
+  ShardComm& sc = comm();
+  std::lock_guard<std::mutex> lock(sc.mu);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(SMC_ERR_CUDA, "no CUDA device available (%s); libstanmath_cuda has no CPU "
+                "fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (n_shards <= 0) n_shards = ndev;  // every visible GPU
+  if (n_shards > 64) return fail(SMC_ERR_INVALID_ARGUMENT, "at most 64 shards");
+  std::vector<int> dev((size_t)n_shards);
+  bool distinct = true;
+  for (int g = 0; g < n_shards; ++g) {
+    dev[g] = devices ? devices[g] : g % ndev;
+    if (dev[g] < 0 || dev[g] >= ndev)
+      return fail(SMC_ERR_INVALID_ARGUMENT, "device %d out of range [0,%d)", dev[g], ndev);
+    for (int h = 0; h < g; ++h) distinct = distinct && dev[h] != dev[g];
+  }
+  if (!sc.shards.empty()) shutdown_locked(sc);
+  for (int g = 0; g < n_shards; ++g) {
+    Shard* s = new Shard();
+    s->device = dev[g];
+    sc.shards.push_back(s);
+    if (int rc = init_context(s->ctx, dev[g])) {
+      shutdown_locked(sc);
+      return rc;
+    }
+  }
+  const char* mode = getenv("SMC_SHARD_REDUCE");
+  const bool want_host = mode && strcmp(mode, "host") == 0;
+  sc.use_nccl = false;
+  if (!want_host && distinct && sc.nccl.load()) {
+    std::vector<ncclComm_t> comms((size_t)n_shards);
+    ncclResult_t r = sc.nccl.CommInitAll(comms.data(), n_shards, dev.data());
+    if (r == ncclSuccess) {
+      for (int g = 0; g < n_shards; ++g) sc.shards[g]->comm = comms[g];
+      sc.use_nccl = true;
+    } else if (mode && strcmp(mode, "nccl") == 0) {
+      shutdown_locked(sc);
+      return fail(SMC_ERR_CUDA, "ncclCommInitAll failed: %s", sc.nccl.GetErrorString(r));
+    }
+  } else if (mode && strcmp(mode, "nccl") == 0) {
+    shutdown_locked(sc);
+    return fail(SMC_ERR_CUDA, "SMC_SHARD_REDUCE=nccl: %s",
+                distinct ? "libnccl.so.2 could not be loaded"
+                         : "several shards share one GPU");
+  }
+  sc.reduce_mode = sc.use_nccl ? "nccl" : "host";
+  Context& cur = ctx();
+  if (cur.inited) cudaSetDevice(cur.device);
+  return SMC_OK;
+}
+
+int smc_shard_count(int* n_shards) {
+  if (!n_shards) return fail(SMC_ERR_INVALID_ARGUMENT, "n_shards is NULL");
+  *n_shards = (int)comm().shards.size();
+  return SMC_OK;
+}
+
+const char* smc_shard_reduce_mode(void) { return comm().reduce_mode.c_str(); }
+
+int smc_shard_shutdown(void) {
+  ShardComm& sc = comm();
+  std::lock_guard<std::mutex> lock(sc.mu);
+  shutdown_locked(sc);
+  return SMC_OK;
+}
+
+int smc_shard_synchronize(void) { return synchronize_shards(); }
+
+static int make_sharded(int64_t rows, int64_t cols, int dtype,
+                        const std::vector<int64_t>& shard_rows, smc_matrix** out) {
+  ShardComm& sc = comm();
+  smc_matrix* m = new smc_matrix();
+  m->rows = rows;
+  m->cols = cols;
+  m->dtype = dtype;
+  m->ld = 0;
+  m->device = -1;
+  m->id = next_matrix_id();
+  int64_t row0 = 0;
+  for (size_t g = 0; g < sc.shards.size(); ++g) {
+    ShardScope scope(sc.shards[g]);
+    smc_matrix* piece = nullptr;
+    if (int rc = smc_matrix_create(shard_rows[g], cols, dtype, &piece)) {
+      smc_matrix_free(m);
+      return rc;
+    }
+    m->shards.push_back(piece);
+    m->shard_row0.push_back(row0);
+    row0 += shard_rows[g];
+  }
+  *out = m;
+  return SMC_OK;
+}
+
+int smc_sharded_matrix_create(int64_t rows, int64_t cols, int dtype, smc_matrix** out) {
+  if (!out) return fail(SMC_ERR_INVALID_ARGUMENT, "out is NULL");
+  if (rows < 0 || cols < 0 || (dtype != SMC_F64 && dtype != SMC_I32))
+    return fail(SMC_ERR_INVALID_ARGUMENT, "bad matrix shape/dtype %lld x %lld",
+                (long long)rows, (long long)cols);
+  ShardComm& sc = comm();
+  if (sc.shards.empty())
+    return fail(SMC_ERR_INVALID_ARGUMENT, "call smc_shard_init before creating sharded matrices");
+  const int64_t G = (int64_t)sc.shards.size();
+  std::vector<int64_t> shard_rows((size_t)G);
+  for (int64_t g = 0; g < G; ++g)
+    shard_rows[g] = rows * (g + 1) / G - rows * g / G;  // [g N / G, (g+1) N / G)
+  return make_sharded(rows, cols, dtype, shard_rows, out);
+}
+
+int smc_matrix_create_like(const smc_matrix* like, int64_t cols, int dtype,
+                           smc_matrix** out) {
+  if (!like || !out) return fail(SMC_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (cols < 0) cols = like->cols;
+  if (dtype < 0) dtype = like->dtype;
+  if (like->shards.empty()) return smc_matrix_create(like->rows, cols, dtype, out);
+  if (like->shards.size() != comm().shards.size())
+    return fail(SMC_ERR_INVALID_ARGUMENT, "the shard set changed since `like` was created");
+  std::vector<int64_t> shard_rows;
+  for (const smc_matrix* p : like->shards) shard_rows.push_back(p->rows);
+  return make_sharded(like->rows, cols, dtype, shard_rows, out);
+}
+
+int smc_matrix_view(const smc_matrix* src, smc_matrix** out) {
+  if (!src || !out) return fail(SMC_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (src->shards.empty()) {
+    if (int rc = realize(src)) return rc;
+    return smc_matrix_wrap(src->data, src->rows, src->cols, src->ld, src->dtype, out);
+  }
+  smc_matrix* m = new smc_matrix();
+  m->rows = src->rows;
+  m->cols = src->cols;
+  m->dtype = src->dtype;
+  m->device = -1;
+  m->id = next_matrix_id();
+  m->shard_row0 = src->shard_row0;
+  int rc = for_each_shard(src, [&](int, smc_matrix* p, int64_t) {
+    smc_matrix* v = nullptr;
+    if (int r = realize(p)) return r;
+    if (int r = smc_matrix_wrap(p->data, p->rows, p->cols, p->ld, p->dtype, &v)) return r;
+    m->shards.push_back(v);
+    return (int)SMC_OK;
+  });
+  if (rc) {
+    m->shard_row0.resize(m->shards.size());
+    smc_matrix_free(m);
+    return rc;
+  }
+  *out = m;
+  return SMC_OK;
+}
+
+int smc_matrix_shard_count(const smc_matrix* m) { return shard_count_of(m); }
+
+int smc_matrix_shard(const smc_matrix* m, int g, smc_matrix** shard, int64_t* row0,
+                     int* device) {
+  if (!m || g < 0 || g >= (int)m->shards.size())
+    return fail(SMC_ERR_INVALID_ARGUMENT, "shard index out of range");
+  if (shard) *shard = m->shards[g];
+  if (row0) *row0 = m->shard_row0[g];
+  if (device) *device = m->shards[g]->device;
+  return SMC_OK;
+}
+
+}  // extern "C"

@@ -149,12 +149,15 @@ def test_factored_dx_is_the_same_partial(gpu, fam, N, K):
     adj.zero_lazy()
     adj.rank1_update(1.0, fact.d_x, d["beta"])
     np.testing.assert_array_equal(adj.to_host(), dx)  # lp.adj() = 1: the partial itself
+    # accumulation: adj + a * partial, to the last bit or two (the device contracts the
+    # multiply-add, Eigen may or may not)
     adj.rank1_update(-0.3, fact.d_x, d["beta"])
-    np.testing.assert_array_equal(adj.to_host(), dx + (-0.3) * dx)
+    np.testing.assert_allclose(adj.to_host(), dx + (-0.3) * dx, rtol=4e-16, atol=0)
     base = np.asfortranarray(np.random.default_rng(9).standard_normal((N, K)))
     adj2 = gpu.to_matrix_cuda(base)
     adj2.rank1_update(0.7, fact.d_x, d["beta"])
-    np.testing.assert_array_equal(adj2.to_host(), base + 0.7 * dx)
+    np.testing.assert_allclose(adj2.to_host(), base + 0.7 * dx, rtol=0,
+                               atol=4e-16 * float(np.abs(base).max() + np.abs(dx).max()))
 
 
 def test_invalidate_wrapped_buffer(gpu):
