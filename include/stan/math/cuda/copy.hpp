@@ -31,6 +31,53 @@ inline matrix_cuda<T> to_matrix_cuda(T v) {
   return m;
 }
 
+/** Eigen / std::vector -> device matrix partitioned row-wise over the GPUs of the
+ * shard set (cuda_shard_init): scattered once, then accepted by every GLM overload
+ * in place of a plain matrix_cuda. */
+template <typename Mat, require_eigen_t<Mat>* = nullptr,
+          require_st_arithmetic<Mat>* = nullptr>
+inline matrix_cuda<value_type_t<Mat>> to_matrix_cuda_sharded(const Mat& m) {
+  return matrix_cuda<value_type_t<Mat>>::sharded(m);
+}
+template <typename T, require_arithmetic_t<T>* = nullptr>
+inline matrix_cuda<T> to_matrix_cuda_sharded(const std::vector<T>& v) {
+  return matrix_cuda<T>::sharded(v);
+}
+
+/** matrix_cuda_sharded<T>: a matrix_cuda<T> whose constructors scatter over the shard
+ * set -- the multi-GPU form of the reference's one-device matrix_cl
+ * (opencl/opencl_context.hpp L75-76).  It IS a matrix_cuda<T>: every overload and
+ * every helper takes it unchanged. */
+template <typename T>
+class matrix_cuda_sharded : public matrix_cuda<T> {
+ public:
+  matrix_cuda_sharded() = default;
+  matrix_cuda_sharded(int64_t rows, int64_t cols)
+      : matrix_cuda<T>(matrix_cuda<T>::sharded(rows, cols)) {}
+  template <typename Mat, require_eigen_t<Mat>* = nullptr,
+            require_same_t<value_type_t<Mat>, T>* = nullptr>
+  explicit matrix_cuda_sharded(const Mat& m) : matrix_cuda<T>(matrix_cuda<T>::sharded(m)) {}
+  explicit matrix_cuda_sharded(const std::vector<T>& v)
+      : matrix_cuda<T>(matrix_cuda<T>::sharded(v)) {}
+};
+
+/** The shard set: one shard per visible GPU (n_shards <= 0) or the first n_shards;
+ * returns the number of shards.  Call once, before the first sharded matrix. */
+inline int cuda_shard_init(int n_shards = 0) {
+  check_cuda_status("cuda_shard_init", smc_shard_init(n_shards, nullptr));
+  int n = 0;
+  check_cuda_status("cuda_shard_init", smc_shard_count(&n));
+  return n;
+}
+inline int cuda_shard_count() {
+  int n = 0;
+  check_cuda_status("cuda_shard_count", smc_shard_count(&n));
+  return n;
+}
+inline void cuda_shard_shutdown() {
+  check_cuda_status("cuda_shard_shutdown", smc_shard_shutdown());
+}
+
 /** Already on the device: pass through. */
 template <typename T>
 inline const matrix_cuda<T>& to_matrix_cuda(const matrix_cuda<T>& m) {

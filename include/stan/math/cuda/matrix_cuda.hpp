@@ -49,10 +49,11 @@ class matrix_cuda : public matrix_cuda_base {
   /** Allocates rows x cols on the device; contents are unspecified. */
   matrix_cuda(int64_t rows, int64_t cols) { allocate(rows, cols); }
 
-  /** Deep copy on the device. */
+  /** Deep copy on the device (sharded like the source). */
   matrix_cuda(const matrix_cuda& o) {
     if (o.handle_) {
-      allocate(o.rows(), o.cols());
+      check_cuda_status("matrix_cuda(copy)",
+                        smc_matrix_create_like(o.handle_, -1, -1, &handle_));
       check_cuda_status("matrix_cuda(copy)", smc_matrix_copy(handle_, o.handle_));
     }
   }
@@ -113,14 +114,67 @@ class matrix_cuda : public matrix_cuda_base {
                                       internal::cuda_dtype<T>::value, &m.handle_));
     return m;
   }
-  /** Non-owning view of another matrix_cuda (which must outlive the view). */
+  /** Non-owning view of another matrix_cuda (which must outlive the view); a view
+   * of a row-sharded matrix is sharded the same way. */
   static matrix_cuda view(const matrix_cuda& o) {
-    if (!o.handle_) {
-      return matrix_cuda();
+    matrix_cuda m;
+    if (o.handle_) {
+      check_cuda_status("matrix_cuda::view", smc_matrix_view(o.handle_, &m.handle_));
     }
-    return view(static_cast<T*>(smc_matrix_data(o.handle_)), o.rows(), o.cols(),
-                smc_matrix_ld(o.handle_));
+    return m;
   }
+  /** Allocates rows x cols partitioned row-wise over the GPUs of the shard set
+   * (smc_shard_init / stan::math::cuda_shard_init): shard g holds rows
+   * [g N / G, (g+1) N / G).  A sharded matrix goes wherever a GLM takes a plain one
+   * -- x and its per-row operands sharded alike -- and the evaluation then runs on
+   * every GPU with one NCCL all-reduce of the packed partials. */
+  static matrix_cuda sharded(int64_t rows, int64_t cols) {
+    matrix_cuda m;
+    check_cuda_status("matrix_cuda::sharded",
+                      smc_sharded_matrix_create(rows, cols, internal::cuda_dtype<T>::value,
+                                                &m.handle_));
+    return m;
+  }
+  /** Scatters a dense column-major Eigen object over the shard set (done once, in
+   * the model constructor). */
+  template <typename Mat, require_eigen_t<Mat>* = nullptr,
+            require_same_t<value_type_t<Mat>, T>* = nullptr>
+  static matrix_cuda sharded(const Mat& m) {
+    const Eigen::Matrix<T, Eigen::Dynamic, Eigen::Dynamic> cm = m;
+    matrix_cuda out = sharded(cm.rows(), cm.cols());
+    if (cm.size() > 0) {
+      check_cuda_status("matrix_cuda::sharded(Eigen)",
+                        smc_matrix_upload(out.handle_, cm.data(), cm.rows()));
+    }
+    return out;
+  }
+  static matrix_cuda sharded(const std::vector<T>& v) {
+    matrix_cuda out = sharded(static_cast<int64_t>(v.size()), 1);
+    if (!v.empty()) {
+      check_cuda_status("matrix_cuda::sharded(std::vector)",
+                        smc_matrix_upload(out.handle_, v.data(), v.size()));
+    }
+    return out;
+  }
+  /** Allocates a matrix with the rows -- and the row partition, if `like` is sharded
+   * -- of `like` and `cols` columns (contents unspecified). */
+  template <typename U>
+  static matrix_cuda like(const matrix_cuda<U>& like, int64_t cols) {
+    return like_handle(like.handle(), like.rows(), cols);
+  }
+  static matrix_cuda like_handle(const smc_matrix* h, int64_t rows, int64_t cols) {
+    matrix_cuda m;
+    if (h) {
+      check_cuda_status("matrix_cuda::like",
+                        smc_matrix_create_like(h, cols, internal::cuda_dtype<T>::value,
+                                               &m.handle_));
+    } else {
+      m.allocate(rows, cols);
+    }
+    return m;
+  }
+  /** Number of shards (0: a plain single-GPU matrix). */
+  int shard_count() const noexcept { return handle_ ? smc_matrix_shard_count(handle_) : 0; }
   /** Takes ownership of a handle made through the C ABI. */
   static matrix_cuda adopt(smc_matrix* h) {
     matrix_cuda m;

@@ -34,7 +34,7 @@ return_type_t<T_x, T_alpha, T_beta> bernoulli_logit_glm_lpmf(
   if (N == 0) {  // size_zero(y), L80-82
     return 0;
   }
-  row_operand<int, T_y> y_op(y);
+  row_operand<int, T_y> y_op(y, x_handle(x));
   if (y_op.handle() == nullptr) {  // scalar y: check_bounded(y, 0, 1), L85
     check_bounded(function, "Vector of dependent variables", y_op.scalar(), 0, 1);
   }
@@ -49,11 +49,11 @@ return_type_t<T_x, T_alpha, T_beta> bernoulli_logit_glm_lpmf(
     return 0;
   }
 
-  row_operand<double, T_alpha> alpha_op(alpha);
+  row_operand<double, T_alpha> alpha_op(alpha, x_handle(x));
   const Eigen::VectorXd beta_val = host_values(beta);
 
   auto ops_partials = make_partials_propagator(x, alpha, beta);
-  row_partial<T_alpha> d_alpha_vec(partials<1>(ops_partials), N);
+  row_partial<T_alpha> d_alpha_vec(partials<1>(ops_partials), N, x_handle(x));
 
   const unsigned flags = (propto ? SMC_PROPTO : 0u) | dx_flags<T_x>()
                          | var_flag<T_alpha>(SMC_VAR_ALPHA)

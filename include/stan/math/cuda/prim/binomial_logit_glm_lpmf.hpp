@@ -52,13 +52,13 @@ return_type_t<T_x, T_alpha, T_beta> binomial_logit_glm_lpmf(
                      "Vector of intercepts", operand_size(alpha));
   }
 
-  row_operand<int, T_n> n_op(n);
-  row_operand<int, T_N> N_op(N);
-  row_operand<double, T_alpha> alpha_op(alpha);
+  row_operand<int, T_n> n_op(n, x_handle(x));
+  row_operand<int, T_N> N_op(N, x_handle(x));
+  row_operand<double, T_alpha> alpha_op(alpha, x_handle(x));
   const Eigen::VectorXd beta_val = host_values(beta);
 
   auto ops_partials = make_partials_propagator(x, alpha, beta);
-  row_partial<T_alpha> d_alpha_vec(partials<1>(ops_partials), N_instances);
+  row_partial<T_alpha> d_alpha_vec(partials<1>(ops_partials), N_instances, x_handle(x));
 
   const unsigned flags = (propto ? SMC_PROPTO : 0u) | dx_flags<T_x>()
                          | var_flag<T_alpha>(SMC_VAR_ALPHA)

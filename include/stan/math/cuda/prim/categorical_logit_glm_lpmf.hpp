@@ -32,7 +32,7 @@ return_type_t<T_x, T_alpha, T_beta> categorical_logit_glm_lpmf(
   if (N == 0 || C == 1) {  // L73-75
     return 0;
   }
-  row_operand<int, T_y> y_op(y);
+  row_operand<int, T_y> y_op(y, x_handle(x));
   if (y_op.handle() == nullptr) {  // L77 (a device y is checked by the call)
     check_bounded(function, "categorical outcome out of support", y_op.scalar(), 1,
                   C);

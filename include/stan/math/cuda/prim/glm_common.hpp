@@ -85,7 +85,8 @@ template <typename Elem, typename T>
 class row_operand {
  public:
   static constexpr bool is_scalar = is_stan_scalar<T>::value;
-  explicit row_operand(const T& v) {
+  /** `like`: the handle of x; a host vector is uploaded with x's row partition. */
+  explicit row_operand(const T& v, const smc_matrix* like = nullptr) {
     if constexpr (is_scalar) {
       scalar_ = static_cast<Elem>(value_of(v));
     } else if constexpr (is_matrix_cuda<T>::value) {
@@ -96,7 +97,11 @@ class row_operand {
       const auto& ref = to_ref(v);
       const auto& val = value_of(ref);
       Eigen::Matrix<Elem, Eigen::Dynamic, 1> col = as_column_vector_or_scalar(val);
-      uploaded_ = matrix_cuda<Elem>(col);
+      uploaded_ = matrix_cuda<Elem>::like_handle(like, col.size(), 1);
+      if (col.size() > 0) {
+        check_cuda_status("row_operand",
+                          smc_matrix_upload(uploaded_.handle(), col.data(), col.size()));
+      }
       handle_ = uploaded_.handle();
     }
   }
@@ -118,12 +123,12 @@ class row_partial {
   static constexpr bool is_var_vector
       = !is_constant_all<T>::value && !is_stan_scalar<T>::value;
   template <typename Edge>
-  row_partial(Edge& edge_partials, int64_t n) {
+  row_partial(Edge& edge_partials, int64_t n, const smc_matrix* like = nullptr) {
     if constexpr (is_var_vector) {
       if constexpr (is_var_matrix_cuda<T>::value) {
         handle_ = edge_partials.handle();
       } else {
-        tmp_ = matrix_cuda<double>(n, 1);
+        tmp_ = matrix_cuda<double>::like_handle(like, n, 1);
         handle_ = tmp_.handle();
       }
     }

@@ -38,15 +38,15 @@ return_type_t<T_x, T_alpha, T_beta, T_precision> neg_binomial_2_log_glm_lpmf(
   }
   const Eigen::VectorXd beta_val = host_values(beta);
   check_finite(function, "Weight vector", beta_val);  // L114
-  row_operand<double, T_alpha> alpha_op(alpha);
+  row_operand<double, T_alpha> alpha_op(alpha, x_handle(x));
   if (alpha_op.handle() == nullptr) {  // L115 (a vector alpha is checked in the sweep)
     check_finite(function, "Intercept", alpha_op.scalar());
   }
   if (N == 0) {  // size_zero(y, phi), L117-119
     return 0;
   }
-  row_operand<int, T_y> y_op(y);
-  row_operand<double, T_precision> phi_op(phi);
+  row_operand<int, T_y> y_op(y, x_handle(x));
+  row_operand<double, T_precision> phi_op(phi, x_handle(x));
   if (y_op.handle() == nullptr) {  // L129
     check_nonnegative(function, "Failures variables", y_op.scalar());
   }
@@ -63,8 +63,8 @@ return_type_t<T_x, T_alpha, T_beta, T_precision> neg_binomial_2_log_glm_lpmf(
   }
 
   auto ops_partials = make_partials_propagator(x, alpha, beta, phi);
-  row_partial<T_alpha> d_alpha_vec(partials<1>(ops_partials), N);
-  row_partial<T_precision> d_phi_vec(partials<3>(ops_partials), N);
+  row_partial<T_alpha> d_alpha_vec(partials<1>(ops_partials), N, x_handle(x));
+  row_partial<T_precision> d_phi_vec(partials<3>(ops_partials), N, x_handle(x));
 
   const unsigned flags
       = (propto ? SMC_PROPTO : 0u) | dx_flags<T_x>()

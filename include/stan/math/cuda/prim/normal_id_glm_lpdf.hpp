@@ -34,7 +34,7 @@ return_type_t<T_y, T_x, T_alpha, T_beta, T_scale> normal_id_glm_lpdf(
     check_size_match(function, "Rows of ", "x", N, "size of ", "alpha",
                      operand_size(alpha));
   }
-  row_operand<double, T_scale> sigma_op(sigma);
+  row_operand<double, T_scale> sigma_op(sigma, x_handle(x));
   if (sigma_op.handle() == nullptr) {  // check_positive_finite, L93
     check_positive_finite(function, "Scale vector", sigma_op.scalar());
   }
@@ -45,14 +45,14 @@ return_type_t<T_y, T_x, T_alpha, T_beta, T_scale> normal_id_glm_lpdf(
     return 0;  // L98-100
   }
 
-  row_operand<double, T_y> y_op(y);
-  row_operand<double, T_alpha> alpha_op(alpha);
+  row_operand<double, T_y> y_op(y, x_handle(x));
+  row_operand<double, T_alpha> alpha_op(alpha, x_handle(x));
   const Eigen::VectorXd beta_val = host_values(beta);
 
   auto ops_partials = make_partials_propagator(y, x, alpha, beta, sigma);
-  row_partial<T_y> d_y_vec(partials<0>(ops_partials), N);
-  row_partial<T_alpha> d_alpha_vec(partials<2>(ops_partials), N);
-  row_partial<T_scale> d_sigma_vec(partials<4>(ops_partials), N);
+  row_partial<T_y> d_y_vec(partials<0>(ops_partials), N, x_handle(x));
+  row_partial<T_alpha> d_alpha_vec(partials<2>(ops_partials), N, x_handle(x));
+  row_partial<T_scale> d_sigma_vec(partials<4>(ops_partials), N, x_handle(x));
 
   const unsigned flags
       = (propto ? SMC_PROPTO : 0u) | var_flag<T_y>(SMC_VAR_Y)

@@ -29,7 +29,7 @@ return_type_t<T_x, T_beta, T_cuts> ordered_logistic_glm_lpmf(
   }
   check_size_match(function, "Columns of ", "x", K, "size of ", "beta",
                    operand_size(beta));
-  row_operand<int, T_y> y_op(y);
+  row_operand<int, T_y> y_op(y, x_handle(x));
   const Eigen::VectorXd cuts_val = host_values(cuts);
   // L82-89; the range of a device y is checked by the call itself (y is data:
   // the library caches its min / max at upload)

@@ -46,6 +46,23 @@ class arena_matrix_cuda : public matrix_cuda_base {
     }
     take(std::move(m));
   }
+  /** Zeros (declared lazily) with the rows and the row partition of `like`. */
+  static arena_matrix_cuda zeros_like(const smc_matrix* like, int64_t rows, int64_t cols) {
+    arena_matrix_cuda a;
+    matrix_cuda<T> m = matrix_cuda<T>::like_handle(like, rows, cols);
+    if (m.handle()) {
+      check_cuda_status("arena_matrix_cuda(zeros)", smc_matrix_zero_lazy(m.handle()));
+    }
+    a.take(std::move(m));
+    return a;
+  }
+  /** Uninitialised, with the rows and the row partition of `like`. */
+  static arena_matrix_cuda uninitialized_like(const smc_matrix* like, int64_t rows,
+                                              int64_t cols) {
+    arena_matrix_cuda a;
+    a.take(matrix_cuda<T>::like_handle(like, rows, cols));
+    return a;
+  }
   /** rows x cols owned by the arena, contents unspecified (the producer
    * overwrites every element). */
   static arena_matrix_cuda uninitialized(int64_t rows, int64_t cols) {
@@ -69,7 +86,7 @@ class arena_matrix_cuda : public matrix_cuda_base {
 
   /** Copy to an owning matrix (device-to-device). */
   matrix_cuda<T> to_matrix_cuda() const {
-    matrix_cuda<T> out(rows(), cols());
+    matrix_cuda<T> out = matrix_cuda<T>::like_handle(h_, rows(), cols());
     if (h_) {
       check_cuda_status("arena_matrix_cuda::to_matrix_cuda",
                         smc_matrix_copy(out.handle(), h_));

@@ -42,6 +42,19 @@ inline var_value<matrix_cuda<double>> to_matrix_cuda(const T& src) {
   return res;
 }
 
+/** Eigen matrix of var -> device var sharded over the GPUs of the shard set. */
+template <typename T, require_eigen_vt<is_var, T>* = nullptr>
+inline var_value<matrix_cuda<double>> to_matrix_cuda_sharded(const T& src) {
+  arena_t<plain_type_t<T>> src_arena(src);
+  var_value<matrix_cuda<double>> res(to_matrix_cuda_sharded(src_arena.val().eval()));
+  reverse_pass_callback([src_arena, res]() mutable {
+    src_arena.adj() += from_matrix_cuda<
+        Eigen::Matrix<double, T::RowsAtCompileTime, T::ColsAtCompileTime>>(
+        res.adj().to_matrix_cuda());
+  });
+  return res;
+}
+
 /** std::vector<var> -> device var column. */
 inline var_value<matrix_cuda<double>> to_matrix_cuda(const std::vector<var>& src) {
   arena_t<Eigen::Matrix<var, Eigen::Dynamic, 1>> src_arena(
@@ -65,7 +78,14 @@ template <typename T_dst = Eigen::MatrixXd, require_eigen_t<T_dst>* = nullptr>
 inline var_value<T_dst> from_matrix_cuda(const var_value<matrix_cuda<double>>& a) {
   var_value<T_dst> res(from_matrix_cuda<T_dst>(a.val().to_matrix_cuda()));
   reverse_pass_callback([a, res]() mutable {
-    matrix_cuda<double> g(res.adj().eval());
+    // (laid out -- and sharded -- like the adjoint it is added to)
+    matrix_cuda<double> g
+        = matrix_cuda<double>::like_handle(a.adj().handle(), a.rows(), a.cols());
+    const Eigen::MatrixXd g_host = res.adj();
+    if (g_host.size() > 0) {
+      check_cuda_status("from_matrix_cuda(var)",
+                        smc_matrix_upload(g.handle(), g_host.data(), g_host.rows()));
+    }
     check_cuda_status("from_matrix_cuda(var)",
                       smc_matrix_axpy(a.adj().handle(), 1.0, g.handle()));
   });

@@ -36,19 +36,21 @@ namespace math {
 class cuda_edge_partial {
  public:
   cuda_edge_partial() = default;
-  cuda_edge_partial(int64_t rows, int64_t cols) : rows_(rows), cols_(cols) {}
+  /** `like`: the operand's value handle; the partial follows its row partition. */
+  cuda_edge_partial(const smc_matrix* like, int64_t rows, int64_t cols)
+      : like_(like), rows_(rows), cols_(cols) {}
 
   /** The full rows x cols partial (allocated on first use, contents unspecified). */
   smc_matrix* handle() {
     if (!full_.handle()) {
-      full_ = arena_matrix_cuda<double>::uninitialized(rows_, cols_);
+      full_ = arena_matrix_cuda<double>::uninitialized_like(like_, rows_, cols_);
     }
     return full_.handle();
   }
   /** The rank-one form: returns the rows x 1 device vector the kernel writes d
    * into; beta (cols doubles) is copied into the arena. */
   smc_matrix* factored(const double* beta) {
-    d_ = arena_matrix_cuda<double>::uninitialized(rows_, 1);
+    d_ = arena_matrix_cuda<double>::uninitialized_like(like_, rows_, 1);
     beta_ = ChainableStack::instance_->memalloc_.alloc_array<double>(
         static_cast<size_t>(cols_ > 0 ? cols_ : 1));
     std::copy(beta, beta + cols_, beta_);
@@ -66,6 +68,7 @@ class cuda_edge_partial {
   arena_matrix_cuda<double> full_;
   arena_matrix_cuda<double> d_;
   double* beta_{nullptr};
+  const smc_matrix* like_{nullptr};
   int64_t rows_{0}, cols_{0};
 };
 
@@ -108,7 +111,9 @@ class ops_partials_edge<double, var_value<matrix_cuda<double>>, void> {
   partials_t partials_;
   broadcast_array<partials_t> partials_vec_;
   explicit ops_partials_edge(const var_value<matrix_cuda<double>>& ops)
-      : partials_(ops.rows(), ops.cols()), partials_vec_(partials_), operands_(ops) {}
+      : partials_(ops.val().handle(), ops.rows(), ops.cols()),
+        partials_vec_(partials_),
+        operands_(ops) {}
   inline auto& partial() noexcept { return partials_; }
   inline auto& operand() const noexcept { return operands_; }
   var_value<matrix_cuda<double>> operands_;

@@ -32,12 +32,16 @@ class vari_value<matrix_cuda<double>, void> : public vari_base {
 
   /** Takes ownership of the value buffer. */
   explicit vari_value(matrix_cuda<double>&& v)
-      : val_(std::move(v)), adj_(val_.rows(), val_.cols()) {
+      : val_(std::move(v)),
+        adj_(arena_matrix_cuda<double>::zeros_like(val_.handle(), val_.rows(),
+                                                   val_.cols())) {
     ChainableStack::instance_->var_nochain_stack_.push_back(this);
   }
   /** Views the value buffer: `v` must outlive the reverse sweep. */
   explicit vari_value(const matrix_cuda<double>& v)
-      : val_(arena_matrix_cuda<double>::view(v)), adj_(val_.rows(), val_.cols()) {
+      : val_(arena_matrix_cuda<double>::view(v)),
+        adj_(arena_matrix_cuda<double>::zeros_like(val_.handle(), val_.rows(),
+                                                   val_.cols())) {
     ChainableStack::instance_->var_nochain_stack_.push_back(this);
   }
 

@@ -162,6 +162,47 @@ int smc_matrix_int_range(const smc_matrix* m, int* min_out, int* max_out);
 int smc_matrix_fill_synthetic(smc_matrix* m, uint64_t seed, int64_t row0,
                               int kind, double scale, int lo, int hi);
 
+/* ---- row-sharded matrices: the GPUs of one box behind the same entry points -- */
+/* A sharded smc_matrix partitions its rows contiguously over the shard set (shard g
+ * holds rows [g N / G, (g+1) N / G) on its GPU; uploaded once).  It is accepted
+ * wherever the GLM entry points below -- all seven families, smc_linear_predictor and
+ * its adjoint -- and the matrix calls above (upload / download incl. row blocks, zero,
+ * zero_lazy, copy, axpy, rank1_update, outer, add_scalar, all_finite, int_range,
+ * fill_synthetic, free) take a plain one, provided x and every per-row operand of a
+ * call are sharded alike (smc_matrix_create_like).  One evaluation launches the fused
+ * kernel on every GPU (small parameters travel as kernel arguments: that is the
+ * broadcast), all-reduces the packed K + O(1) result in place over NCCL on the
+ * compute streams, and reads it back once; N-vector partials and the N x K adjoint
+ * of an autodiff x stay sharded.  This is the reference's scatter-once / broadcast-
+ * parameters / reduce pattern (prim/functor/mpi_parallel_call.hpp L332-392,
+ * L408-449) in one process, beyond the one device of the OpenCL backend
+ * (opencl/opencl_context.hpp L75-76).  Entry points without a sharded form
+ * (un-fused densities, indexing, the matrix product with a K x C weight matrix,
+ * smc_matrix_wrap / smc_matrix_data) return SMC_ERR_UNSUPPORTED or NULL.
+ *
+ * smc_shard_init: n_shards <= 0 takes every visible GPU; `devices` (n_shards ids)
+ * or NULL for 0, 1, ...  NCCL is loaded at run time (libnccl.so.2).  If it is
+ * missing, if SMC_SHARD_REDUCE=host is set, or if several shards share a GPU
+ * (single-GPU tests of the sharded logic), the packed results are read back per
+ * shard and summed on the host in shard order instead.  Re-initialising invalidates
+ * existing sharded matrices.  One sharded evaluation runs at a time per process. */
+int smc_shard_init(int n_shards, const int* devices);
+int smc_shard_count(int* n_shards);
+const char* smc_shard_reduce_mode(void); /* "nccl" | "host" | "" before init */
+int smc_shard_synchronize(void);
+int smc_shard_shutdown(void);
+int smc_sharded_matrix_create(int64_t rows, int64_t cols, int dtype, smc_matrix** out);
+/* A matrix with the rows -- and the row partition -- of `like`: `cols` columns
+ * (< 0: as many as `like`) of `dtype` (< 0: the same).  Plain when `like` is plain. */
+int smc_matrix_create_like(const smc_matrix* like, int64_t cols, int dtype,
+                           smc_matrix** out);
+/* A non-owning alias of `src` (plain or sharded), which must outlive it. */
+int smc_matrix_view(const smc_matrix* src, smc_matrix** out);
+int smc_matrix_shard_count(const smc_matrix* m); /* 0: a plain matrix */
+/* Shard g of a sharded matrix (borrowed: owned by `m`), its first global row and GPU. */
+int smc_matrix_shard(const smc_matrix* m, int g, smc_matrix** shard, int64_t* row0,
+                     int* device);
+
 /* ---- GLM log density + gradient ------------------------------------------ */
 /* Common argument meaning (N = x rows, K = x cols):
  *   y            N x 1 device vector (i32; f64 for normal_id) or NULL to

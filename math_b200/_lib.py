@@ -70,6 +70,16 @@ SIGNATURES = {
     "smc_matrix_all_finite": (_I, [_P, C.POINTER(_I)]),
     "smc_matrix_int_range": (_I, [_P, C.POINTER(_I), C.POINTER(_I)]),
     "smc_matrix_fill_synthetic": (_I, [_P, C.c_uint64, _I64, _I, _D, _I, _I]),
+    "smc_shard_init": (_I, [_I, C.POINTER(_I)]),
+    "smc_shard_count": (_I, [C.POINTER(_I)]),
+    "smc_shard_reduce_mode": (C.c_char_p, []),
+    "smc_shard_synchronize": (_I, []),
+    "smc_shard_shutdown": (_I, []),
+    "smc_sharded_matrix_create": (_I, [_I64, _I64, _I, C.POINTER(_P)]),
+    "smc_matrix_create_like": (_I, [_P, _I64, _I, C.POINTER(_P)]),
+    "smc_matrix_view": (_I, [_P, C.POINTER(_P)]),
+    "smc_matrix_shard_count": (_I, [_P]),
+    "smc_matrix_shard": (_I, [_P, _I, C.POINTER(_P), C.POINTER(_I64), C.POINTER(_I)]),
     "smc_bernoulli_logit_glm": (_I, [_P, _I, _P, _P, _D, _DP, _U, _DP, _DP, _P,
                                      _DP, _P]),
     "smc_binomial_logit_glm": (_I, [_P, _I, _P, _I, _P, _P, _D, _DP, _U, _DP, _DP,

@@ -75,6 +75,13 @@ int check_dx(const char* fn, unsigned flags, const smc_matrix* x,
 namespace smc {
 // Runs the call with the packed result in pinned host memory; returns it.
 int run_sync(GlmCall& c, int n_out, const double** out) {
+  if (is_sharded(c.x)) return run_sharded(c, n_out, out);
+  for (const smc_matrix* m : {c.y, c.alpha_vec, c.aux_vec, (const smc_matrix*)c.d_alpha_vec,
+                              (const smc_matrix*)c.d_aux_vec, (const smc_matrix*)c.d_y_vec,
+                              (const smc_matrix*)c.d_x})
+    if (is_sharded(m))
+      return fail(SMC_ERR_INVALID_ARGUMENT,
+                  "a per-row operand is sharded but x is not (shard x too)");
   Context& cx = ctx();
   if (int rc = ensure_out(sizeof(double) * ((size_t)n_out + 1))) return rc;
   c.out = cx.out_host;

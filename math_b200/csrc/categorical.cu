@@ -1021,7 +1021,7 @@ static int launch_cat_impl(CatMode mode, const smc_matrix* y, int y_scalar,
     // beta and alpha in one piece (a D2D copy keeps every alignment assumption of
     // the kernels on cx.params_dev)
     SMC_CUDA(cudaMemcpyAsync(cx.params_dev, params_user, sizeof(double) * nparam,
-                             cudaMemcpyDeviceToDevice, cx.stream));
+                             cudaMemcpyDefault, cx.stream));
   } else {
     if (a.K && mode != kCatAdj)
       SMC_CUDA(cudaMemcpyAsync(cx.params_dev, beta_host, sizeof(double) * a.K * a.C,
@@ -1321,6 +1321,7 @@ extern "C" int smc_linear_predictor_matrix(const smc_matrix* x, const double* be
                                            smc_matrix* lin_out) {
   static const char* fn = "linear_predictor_matrix";
   if (int rc = ensure_ctx()) return rc;
+  if (int rc = refuse_sharded(fn, {x, lin_out})) return rc;
   if (!x || x->dtype != SMC_F64)
     return fail(SMC_ERR_INVALID_ARGUMENT, "%s: x must be an f64 device matrix", fn);
   const int64_t N = x->rows, K = x->cols, C = n_classes;
@@ -1348,6 +1349,7 @@ extern "C" int smc_linear_predictor_matrix_adjoint(const smc_matrix* x,
                                                    double* colsum) {
   static const char* fn = "linear_predictor_matrix_adjoint";
   if (int rc = ensure_ctx()) return rc;
+  if (int rc = refuse_sharded(fn, {x, adj})) return rc;
   if (!x || x->dtype != SMC_F64)
     return fail(SMC_ERR_INVALID_ARGUMENT, "%s: x must be an f64 device matrix", fn);
   const int64_t N = x->rows, K = x->cols;
@@ -1464,6 +1466,7 @@ extern "C" int smc_categorical_logit_glm_device(const smc_matrix* y, int y_scala
                                                 double* out_dev, smc_matrix* d_x) {
   static const char* fn = "categorical_logit_glm_device";
   if (int rc = ensure_ctx()) return rc;
+  if (int rc = refuse_sharded(fn, {x, y, d_x})) return rc;
   if (!x || x->dtype != SMC_F64)
     return fail(SMC_ERR_INVALID_ARGUMENT, "%s: x must be an f64 device matrix", fn);
   const int64_t N = x->rows, K = x->cols, C = n_classes;
@@ -1521,7 +1524,23 @@ extern "C" int smc_categorical_logit_glm(const smc_matrix* y, int y_scalar,
   if ((flags & SMC_PROPTO) && !(flags & (SMC_VAR_X | SMC_VAR_ALPHA | SMC_VAR_BETA)))
     return SMC_OK;  // L80-82
   double lp = 0.0;
-  if (((C + 7) & ~(int64_t)7) > kCatBlock) {
+  if (is_sharded(x) || is_sharded(y) || is_sharded(d_x)) {
+    // row-sharded x: the device form on every GPU, packed results reduced (sharded.cu)
+    if (!is_sharded(x)) return fail(SMC_ERR_INVALID_ARGUMENT, "%s: y / d_x is sharded but x is not", fn);
+    if (((C + 7) & ~(int64_t)7) > kCatBlock)
+      return fail(SMC_ERR_UNSUPPORTED, "%s: more than %d classes over sharded x", fn,
+                  kCatBlock);
+    std::vector<double> params((size_t)K * C + C);
+    memcpy(params.data(), beta, sizeof(double) * (size_t)K * C);
+    memcpy(params.data() + (size_t)K * C, alpha, sizeof(double) * (size_t)C);
+    const double* o;
+    if (int rc = run_sharded_categorical(y, y_scalar, x, params.data(), C, flags, d_x, &o))
+      return rc;
+    lp = o[0];
+    if (d_alpha && (flags & SMC_VAR_ALPHA)) memcpy(d_alpha, o + 2, sizeof(double) * (size_t)C);
+    if (d_beta && (flags & SMC_VAR_BETA))
+      memcpy(d_beta, o + 2 + C, sizeof(double) * (size_t)K * C);
+  } else if (((C + 7) & ~(int64_t)7) > kCatBlock) {
     if (int rc = categorical_wide(fn, y, y_scalar, x, alpha, beta, C, flags, &lp, d_alpha,
                                   d_beta, d_x))
       return rc;

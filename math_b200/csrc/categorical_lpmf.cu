@@ -228,6 +228,7 @@ extern "C" int smc_categorical_logit_lpmf(const smc_matrix* y, int y_scalar,
                                           double* logp, smc_matrix* d_lin) {
   static const char* fn = "categorical_logit_lpmf";
   if (int rc = ensure_ctx()) return rc;
+  if (int rc = refuse_sharded(fn, {y, lin, d_lin})) return rc;
   if (!lin || lin->dtype != SMC_F64)
     return fail(SMC_ERR_INVALID_ARGUMENT, "%s: lin must be an f64 device matrix", fn);
   const int64_t N = lin->rows, C = lin->cols;

@@ -16,6 +16,7 @@ static thread_local Context t_ctx;
 static thread_local Context* t_cur = &t_ctx;
 
 Context& ctx() { return *t_cur; }
+Context& own_ctx() { return t_ctx; }
 Context* swap_current_context(Context* c) {
   Context* prev = t_cur;
   t_cur = c ? c : &t_ctx;
@@ -451,7 +452,7 @@ int smc_set_stream(void* s) {
 int smc_synchronize(void) {
   if (int rc = ensure_ctx()) return rc;
   SMC_CUDA(cudaStreamSynchronize(ctx().stream));
-  return SMC_OK;
+  return synchronize_shards();  // (no shards: nothing to wait for)
 }
 
 int smc_device_info(int* sm_count, int* cc_major, int* cc_minor,
@@ -524,6 +525,17 @@ int smc_matrix_wrap(void* device_ptr, int64_t rows, int64_t cols, int64_t ld,
 
 int smc_matrix_free(smc_matrix* m) {
   if (!m) return SMC_OK;
+  if (is_sharded(m)) {
+    // every piece goes back under its own shard's context (its recycling cache); if
+    // the shard set is gone the pieces fall through to the foreign-context path
+    const int rc = for_each_shard(m, [](int, smc_matrix* p, int64_t) {
+      return smc_matrix_free(p);
+    });
+    if (rc)
+      for (smc_matrix* p : m->shards) smc_matrix_free(p);
+    delete m;
+    return SMC_OK;
+  }
   const bool has_blocks = m->grp_perm || m->grp_off || (m->owned && m->data);
   if (has_blocks) {
     if (int rc = ensure_ctx()) return rc;
@@ -552,6 +564,7 @@ int smc_matrix_free(smc_matrix* m) {
 
 int smc_matrix_invalidate(smc_matrix* m) {
   if (!m) return fail(SMC_ERR_INVALID_ARGUMENT, "NULL matrix");
+  for (smc_matrix* p : m->shards) smc_matrix_invalidate(p);
   std::lock_guard<std::mutex> lock(cache_mutex());
   m->lgamma_valid = false;
   m->range_valid = false;
@@ -565,7 +578,7 @@ int64_t smc_matrix_cols(const smc_matrix* m) { return m ? m->cols : 0; }
 int64_t smc_matrix_ld(const smc_matrix* m) { return m ? m->ld : 0; }
 int smc_matrix_dtype(const smc_matrix* m) { return m ? m->dtype : -1; }
 void* smc_matrix_data(const smc_matrix* m) {
-  if (!m) return nullptr;
+  if (!m || is_sharded(m)) return nullptr;  // (a sharded matrix has no one buffer)
   realize(m);  // the raw pointer escapes: a deferred memset has to happen now
   return m->data;
 }
@@ -580,6 +593,18 @@ static int copy_rows(smc_matrix* m, int64_t row0, int64_t nrows, void* host,
                 "%lld)",
                 (long long)row0, (long long)(row0 + nrows), (long long)m->rows,
                 (long long)ld_host);
+  if (is_sharded(m)) {
+    // scatter / gather: every shard moves its part of the row block (the copies of
+    // the shards run back to back; each waits for its own stream)
+    const size_t es = m->dtype == SMC_F64 ? 8 : 4;
+    return for_each_shard(m, [&](int, smc_matrix* p, int64_t p0) {
+      const int64_t lo = row0 > p0 ? row0 : p0;
+      const int64_t hi = row0 + nrows < p0 + p->rows ? row0 + nrows : p0 + p->rows;
+      if (hi <= lo) return (int)SMC_OK;
+      return copy_rows(p, lo - p0, hi - lo, static_cast<char*>(host) + (size_t)(lo - row0) * es,
+                       ld_host, to_device);
+    });
+  }
   if (int rc = ensure_ctx()) return rc;
   if (nrows == 0 || m->cols == 0) return SMC_OK;
   const size_t es = elem_size(m->dtype);
@@ -627,6 +652,8 @@ int smc_matrix_download_rows(const smc_matrix* m, int64_t row0, int64_t nrows,
 
 int smc_matrix_zero(smc_matrix* m) {
   if (!m) return fail(SMC_ERR_INVALID_ARGUMENT, "NULL matrix");
+  if (is_sharded(m))
+    return for_each_shard(m, [](int, smc_matrix* p, int64_t) { return smc_matrix_zero(p); });
   if (int rc = ensure_ctx()) return rc;
   if (m->rows == 0 || m->cols == 0) return SMC_OK;
   m->lgamma_valid = false;
@@ -641,6 +668,7 @@ int smc_matrix_zero(smc_matrix* m) {
 
 int smc_matrix_zero_lazy(smc_matrix* m) {
   if (!m) return fail(SMC_ERR_INVALID_ARGUMENT, "NULL matrix");
+  for (smc_matrix* p : m->shards) smc_matrix_zero_lazy(p);
   m->lgamma_valid = false;
   m->range_valid = false;
   m->version += 1;
@@ -652,6 +680,13 @@ int smc_matrix_copy(smc_matrix* dst, const smc_matrix* src) {
   if (!dst || !src || dst->rows != src->rows || dst->cols != src->cols
       || dst->dtype != src->dtype)
     return fail(SMC_ERR_INVALID_ARGUMENT, "copy: shape/dtype mismatch");
+  if (is_sharded(dst) || is_sharded(src)) {
+    if (!is_sharded(dst) || !is_sharded(src) || !same_partition(dst, src))
+      return fail(SMC_ERR_INVALID_ARGUMENT, "copy: the operands are not sharded alike");
+    return for_each_shard(dst, [&](int g, smc_matrix* p, int64_t) {
+      return smc_matrix_copy(p, src->shards[g]);
+    });
+  }
   if (int rc = ensure_ctx()) return rc;
   if (dst->rows == 0 || dst->cols == 0) return SMC_OK;
   if (src->zero_pending) return dst == src ? SMC_OK : smc_matrix_zero(dst);
@@ -671,6 +706,13 @@ int smc_matrix_axpy(smc_matrix* y, double a, const smc_matrix* x) {
   if (!y || !x || y->rows != x->rows || y->cols != x->cols
       || y->dtype != SMC_F64 || x->dtype != SMC_F64)
     return fail(SMC_ERR_INVALID_ARGUMENT, "axpy: shape/dtype mismatch");
+  if (is_sharded(y) || is_sharded(x)) {
+    if (!is_sharded(y) || !is_sharded(x) || !same_partition(y, x))
+      return fail(SMC_ERR_INVALID_ARGUMENT, "axpy: the operands are not sharded alike");
+    return for_each_shard(y, [&](int g, smc_matrix* p, int64_t) {
+      return smc_matrix_axpy(p, a, x->shards[g]);
+    });
+  }
   if (int rc = ensure_ctx()) return rc;
   const int64_t total = y->rows * y->cols;
   if (total == 0) return SMC_OK;
@@ -697,6 +739,14 @@ int smc_matrix_rank1_update(smc_matrix* y, double a, const smc_matrix* d,
   if (!y || !d || !beta || y->dtype != SMC_F64 || d->dtype != SMC_F64
       || d->rows * d->cols != y->rows || !vec_contiguous(d))
     return fail(SMC_ERR_INVALID_ARGUMENT, "rank1_update: shape/dtype mismatch");
+  if (is_sharded(y) || is_sharded(d)) {
+    if (!is_sharded(y) || !is_sharded(d) || !same_partition(y, d))
+      return fail(SMC_ERR_INVALID_ARGUMENT,
+                  "rank1_update: the operands are not sharded alike");
+    return for_each_shard(y, [&](int g, smc_matrix* p, int64_t) {
+      return smc_matrix_rank1_update(p, a, d->shards[g], beta);
+    });
+  }
   if (int rc = ensure_ctx()) return rc;
   if (y->rows == 0 || y->cols == 0) return SMC_OK;
   if (int rc = realize(d)) return rc;
@@ -718,6 +768,13 @@ int smc_matrix_outer(smc_matrix* out, const smc_matrix* d, const double* beta) {
   if (!out || !d || !beta || out->dtype != SMC_F64 || d->dtype != SMC_F64
       || d->rows * d->cols != out->rows)
     return fail(SMC_ERR_INVALID_ARGUMENT, "outer: shape/dtype mismatch");
+  if (is_sharded(out) || is_sharded(d)) {
+    if (!is_sharded(out) || !is_sharded(d) || !same_partition(out, d))
+      return fail(SMC_ERR_INVALID_ARGUMENT, "outer: the operands are not sharded alike");
+    return for_each_shard(out, [&](int g, smc_matrix* p, int64_t) {
+      return smc_matrix_outer(p, d->shards[g], beta);
+    });
+  }
   if (int rc = ensure_ctx()) return rc;
   if (int rc = realize(d)) return rc;
   out->version++;
@@ -730,6 +787,10 @@ int smc_matrix_outer(smc_matrix* out, const smc_matrix* d, const double* beta) {
 int smc_matrix_add_scalar(smc_matrix* y, double a) {
   if (!y || y->dtype != SMC_F64)
     return fail(SMC_ERR_INVALID_ARGUMENT, "add_scalar: need an f64 matrix");
+  if (is_sharded(y))
+    return for_each_shard(y, [&](int, smc_matrix* p, int64_t) {
+      return smc_matrix_add_scalar(p, a);
+    });
   if (int rc = ensure_ctx()) return rc;
   const int64_t total = y->rows * y->cols;
   if (total == 0) return SMC_OK;
@@ -744,6 +805,15 @@ int smc_matrix_add_scalar(smc_matrix* y, double a) {
 int smc_matrix_all_finite(const smc_matrix* m, int* all_finite) {
   if (!m || !all_finite || m->dtype != SMC_F64)
     return fail(SMC_ERR_INVALID_ARGUMENT, "all_finite: need an f64 matrix");
+  if (is_sharded(m)) {
+    *all_finite = 1;
+    return for_each_shard(m, [&](int, smc_matrix* p, int64_t) {
+      int ok = 1;
+      const int rc = smc_matrix_all_finite(p, &ok);
+      if (!ok) *all_finite = 0;
+      return rc;
+    });
+  }
   if (int rc = ensure_ctx()) return rc;
   *all_finite = 1;
   const int64_t total = m->rows * m->cols;
@@ -770,6 +840,10 @@ int smc_matrix_fill_synthetic(smc_matrix* m, uint64_t seed, int64_t row0,
   if (!m || (kind != 0 && kind != 1) || (kind == 0 && m->dtype != SMC_F64)
       || (kind == 1 && hi < lo))
     return fail(SMC_ERR_INVALID_ARGUMENT, "fill_synthetic: bad arguments");
+  if (is_sharded(m))  // the same values as one GPU would hold: keyed by the global row
+    return for_each_shard(m, [&](int, smc_matrix* p, int64_t p0) {
+      return smc_matrix_fill_synthetic(p, seed, row0 + p0, kind, scale, lo, hi);
+    });
   if (int rc = ensure_ctx()) return rc;
   const int64_t total = m->rows * m->cols;
   if (total == 0) return SMC_OK;

@@ -69,7 +69,7 @@ int prepare_args(const GlmCall& c, FusedArgs* ap) {
           // elements of y as passed (once), the neg-binomial GLM scales by N
           // (L165-168) -- both reproduced as the reference has them
           lg = std::lgamma(c.y_scalar + 1.0)
-               * (c.family == kPoisson && !c.unfused ? 1.0 : Nd);
+               * (c.family == kPoisson && !c.unfused ? (c.once_terms ? 1.0 : 0.0) : Nd);
         }
         a.c0 -= lg;
       }

@@ -199,6 +199,7 @@ extern "C" {
 int smc_indexing(const double* z, int64_t G, const smc_matrix* idx, smc_matrix* out) {
   static const char* fn = "indexing";
   if (int rc = ensure_ctx()) return rc;
+  if (int rc = refuse_sharded(fn, {idx, out})) return rc;
   if (int rc = check_index(fn, idx, G)) return rc;
   const int64_t n = idx->rows * idx->cols;
   if (!out || out->dtype != SMC_F64 || out->rows * out->cols != n || !vec_contiguous(out))
@@ -224,6 +225,7 @@ int smc_indexing_rev(const smc_matrix* idx, const smc_matrix* res_adj, int64_t G
                      double* adj_z) {
   static const char* fn = "indexing_rev";
   if (int rc = ensure_ctx()) return rc;
+  if (int rc = refuse_sharded(fn, {idx, res_adj})) return rc;
   if (int rc = check_index(fn, idx, G)) return rc;
   const int64_t n = idx->rows * idx->cols;
   if (!res_adj || res_adj->dtype != SMC_F64 || res_adj->rows * res_adj->cols != n

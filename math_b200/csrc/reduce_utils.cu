@@ -190,6 +190,24 @@ int binom_stats(const smc_matrix* n, int n_scalar, const smc_matrix* trials,
   *in_support = true;
   *coef_sum = 0.0;
   if (count <= 0) return SMC_OK;
+  if (is_sharded(n) || is_sharded(trials)) {
+    const smc_matrix* ref = is_sharded(n) ? n : trials;
+    if ((n && !is_sharded(n)) || (trials && !is_sharded(trials))
+        || (n && trials && !same_partition(n, trials)))
+      return fail(SMC_ERR_INVALID_ARGUMENT,
+                  "binomial: successes and trials are not sharded alike");
+    return for_each_shard(ref, [&](int g, smc_matrix* p, int64_t) {
+      bool ok = true;
+      double s = 0.0;
+      if (int rc = binom_stats(n ? n->shards[g] : nullptr, n_scalar,
+                               trials ? trials->shards[g] : nullptr, trials_scalar, p->rows,
+                               &ok, &s))
+        return rc;
+      *in_support = *in_support && ok;
+      *coef_sum += s;
+      return (int)SMC_OK;
+    });
+  }
   // the cache lives on whichever operand is a matrix (n first)
   smc_matrix* owner = const_cast<smc_matrix*>(n ? n : trials);
   if (!owner) {  // two broadcast scalars: one pair, evaluated on the host
@@ -254,6 +272,17 @@ int y_range(const smc_matrix* y, int* lo, int* hi) {
     *lo = INT_MAX;
     *hi = INT_MIN;
     return SMC_OK;
+  }
+  if (is_sharded(y)) {
+    *lo = INT_MAX;
+    *hi = INT_MIN;
+    return for_each_shard(y, [&](int, smc_matrix* p, int64_t) {
+      int l, h;
+      if (int rc = y_range(p, &l, &h)) return rc;
+      *lo = l < *lo ? l : *lo;
+      *hi = h > *hi ? h : *hi;
+      return (int)SMC_OK;
+    });
   }
   if (int rc = compute_stats(y)) return rc;
   *lo = y->imin;

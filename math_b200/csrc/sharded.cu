@@ -19,8 +19,8 @@
 // keeps it from doing.
 //
 // NCCL is bound at run time (dlopen of libnccl.so.2): programs that never shard do
-// not need it.  SMC_SHARD_REDUCE=host replaces step 2 + 3 by G packed results written
-// straight into mapped host memory and summed there in shard order; that is also the
+// not need it.  SMC_SHARD_REDUCE=host replaces step 2 + 3 by G read-backs into pinned
+// host memory and a sum there in shard order; that is also the
 // fallback when NCCL is missing or when several shards share one GPU (single-GPU
 // tests of the sharded logic).
 #include <dlfcn.h>
@@ -171,22 +171,19 @@ int synchronize_shards() {
   return SMC_OK;
 }
 
-// One evaluation of a memory-bound GLM family over the shards of c.x; *out points at
-// the reduced packed result (n_out doubles) in host memory.
-int run_sharded(GlmCall& c, int n_out, const double** out) {
+// The common skeleton of a sharded evaluation: launch(g, shard, out_g) queues shard
+// g's work on its stream with the packed result (n_out doubles) going to out_g; the
+// G results are then summed -- NCCL all-reduce in place on those streams and one
+// read-back from shard 0, or (host mode) G results in mapped host memory added in
+// shard order -- and *out points at the reduced vector in host memory.
+static int run_over_shards(const smc_matrix* x, int n_out,
+                           const std::function<int(int, Shard*, double*)>& launch,
+                           const double** out) {
   ShardComm& sc = comm();
-  const int G = (int)c.x->shards.size();
+  const int G = (int)x->shards.size();
   if ((int)sc.shards.size() != G)
     return fail(SMC_ERR_INVALID_ARGUMENT,
                 "x has %d shards, but the shard set has %zu", G, sc.shards.size());
-  // every per-row operand follows the row partition of x
-  const smc_matrix* ops[] = {c.y, c.alpha_vec, c.aux_vec, c.d_alpha_vec, c.d_aux_vec,
-                             c.d_y_vec, c.d_x};
-  for (const smc_matrix* m : ops)
-    if (m && (m->shards.empty() || !same_partition(m, c.x)))
-      return fail(SMC_ERR_INVALID_ARGUMENT,
-                  "a per-row operand is not sharded like x (create it with "
-                  "smc_matrix_create_like)");
   std::lock_guard<std::mutex> lock(sc.mu);
   const size_t bytes = sizeof(double) * (size_t)n_out;
   int64_t launches = 0;
@@ -194,57 +191,44 @@ int run_sharded(GlmCall& c, int n_out, const double** out) {
   for (int g = 0; g < G; ++g) {
     Shard* s = sc.shards[g];
     ShardScope scope(s);
-    GlmCall cg = c;
-    cg.x = c.x->shards[g];
-    auto pick = [g](const smc_matrix* m) { return m ? m->shards[g] : nullptr; };
-    cg.y = pick(c.y);
-    cg.alpha_vec = pick(c.alpha_vec);
-    cg.aux_vec = pick(c.aux_vec);
-    cg.d_alpha_vec = const_cast<smc_matrix*>(pick(c.d_alpha_vec));
-    cg.d_aux_vec = const_cast<smc_matrix*>(pick(c.d_aux_vec));
-    cg.d_y_vec = const_cast<smc_matrix*>(pick(c.d_y_vec));
-    cg.d_x = const_cast<smc_matrix*>(pick(c.d_x));
-    cg.done_flag = nullptr;
-    cg.once_terms = g == 0;  // terms the reference adds once per call, not per row
-    if (host_reduce) {
-      // the shard's last CTA stores its packed result straight into mapped host memory
-      if (int rc = ensure_out(bytes)) return rc;
-      cg.out = s->ctx.out_host;
-    } else {
-      if (s->out_bytes < bytes) {
-        SMC_CUDA(cudaStreamSynchronize(s->ctx.stream));
-        if (s->out_dev) SMC_CUDA(cudaFree(s->out_dev));
-        s->out_dev = nullptr;
-        const size_t want = bytes < 4096 ? 4096 : bytes;
-        SMC_CUDA(cudaMalloc(&s->out_dev, want));
-        s->out_bytes = want;
-      }
-      cg.out = s->out_dev;
+    if (s->out_bytes < bytes) {
+      SMC_CUDA(cudaStreamSynchronize(s->ctx.stream));
+      if (s->out_dev) SMC_CUDA(cudaFree(s->out_dev));
+      s->out_dev = nullptr;
+      const size_t want = bytes < 4096 ? 4096 : bytes;
+      SMC_CUDA(cudaMalloc(&s->out_dev, want));
+      s->out_bytes = want;
     }
+    double* out_g = s->out_dev;
     const int64_t before = s->ctx.launches;
-    if (cg.x->rows == 0) {  // more shards than rows: contributes zeros
-      if (host_reduce)
-        memset(s->ctx.out_host, 0, bytes);
-      else
-        SMC_CUDA(cudaMemsetAsync(s->out_dev, 0, bytes, s->ctx.stream));
-    } else if (int rc = launch_glm(cg)) {
+    if (x->shards[g]->rows == 0) {  // more shards than rows: contributes zeros
+      SMC_CUDA(cudaMemsetAsync(out_g, 0, bytes, s->ctx.stream));
+    } else if (int rc = launch(g, s, out_g)) {
       return rc;
     }
     launches += s->ctx.launches - before;
   }
-  if (sc.host_bytes < bytes) {
+  const size_t host_need = host_reduce ? bytes * (size_t)(G + 1) : bytes;
+  if (sc.host_bytes < host_need) {
     if (sc.host_out) SMC_CUDA(cudaFreeHost(sc.host_out));
     sc.host_out = nullptr;
-    const size_t want = bytes < 4096 ? 4096 : bytes;
+    const size_t want = host_need < 4096 ? 4096 : host_need;
     SMC_CUDA(cudaHostAlloc(&sc.host_out, want, cudaHostAllocPortable));
     sc.host_bytes = want;
   }
   if (host_reduce) {
+    // G packed results -> pinned host memory behind the reduced vector, summed in
+    // shard order: bit-reproducible for a given shard count
+    for (int g = 0; g < G; ++g) {
+      Shard* s = sc.shards[g];
+      SMC_CUDA(cudaSetDevice(s->device));
+      SMC_CUDA(cudaMemcpyAsync(sc.host_out + (size_t)(g + 1) * n_out, s->out_dev, bytes,
+                               cudaMemcpyDeviceToHost, s->ctx.stream));
+    }
     if (int rc = synchronize_shards()) return rc;
-    // fixed order over the shards: bit-reproducible for a given shard count
     for (int j = 0; j < n_out; ++j) {
       double v = 0.0;
-      for (int g = 0; g < G; ++g) v += sc.shards[g]->ctx.out_host[j];
+      for (int g = 0; g < G; ++g) v += sc.host_out[(size_t)(g + 1) * n_out + j];
       sc.host_out[j] = v;
     }
   } else {
@@ -266,6 +250,59 @@ int run_sharded(GlmCall& c, int n_out, const double** out) {
   own_ctx().launches += launches + (host_reduce ? 0 : G);
   *out = sc.host_out;
   return SMC_OK;
+}
+
+static int check_partition(const smc_matrix* x,
+                           std::initializer_list<const smc_matrix*> ops) {
+  // every per-row operand follows the row partition of x
+  for (const smc_matrix* m : ops)
+    if (m && (m->shards.empty() || !same_partition(m, x)))
+      return fail(SMC_ERR_INVALID_ARGUMENT,
+                  "a per-row operand is not sharded like x (create it with "
+                  "smc_matrix_create_like)");
+  return SMC_OK;
+}
+
+// One evaluation of a memory-bound GLM family over the shards of c.x.  The small
+// parameters travel as kernel arguments of every shard's launch.
+int run_sharded(GlmCall& c, int n_out, const double** out) {
+  if (int rc = check_partition(c.x, {c.y, c.alpha_vec, c.aux_vec, c.d_alpha_vec, c.d_aux_vec,
+                                     c.d_y_vec, c.d_x}))
+    return rc;
+  return run_over_shards(c.x, n_out, [&](int g, Shard*, double* out_g) {
+    GlmCall cg = c;
+    auto pick = [g](const smc_matrix* m) {
+      return m ? const_cast<smc_matrix*>(m->shards[g]) : nullptr;
+    };
+    cg.x = pick(c.x);
+    cg.y = pick(c.y);
+    cg.alpha_vec = pick(c.alpha_vec);
+    cg.aux_vec = pick(c.aux_vec);
+    cg.d_alpha_vec = pick(c.d_alpha_vec);
+    cg.d_aux_vec = pick(c.d_aux_vec);
+    cg.d_y_vec = pick(c.d_y_vec);
+    cg.d_x = pick(c.d_x);
+    cg.done_flag = nullptr;
+    cg.once_terms = g == 0;  // terms the reference adds once per call, not per row
+    cg.out = out_g;
+    return launch_glm(cg);
+  }, out);
+}
+
+// The categorical GLM over the shards of x: beta (K x C) and alpha (C) are copied to
+// every shard (params_host: K C + C doubles, beta first; the device form takes any
+// pointer a cudaMemcpyDefault can read), the packed result is
+// [logp, #non-finite, d_alpha[C], d_beta[K x C]].
+int run_sharded_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
+                            const double* params_host, int64_t C, unsigned flags,
+                            smc_matrix* d_x, const double** out) {
+  if (int rc = check_partition(x, {y, d_x})) return rc;
+  const int n_out = (int)(2 + C + x->cols * C);
+  return run_over_shards(x, n_out, [&](int g, Shard*, double* out_g) {
+    return smc_categorical_logit_glm_device(y ? y->shards[g] : nullptr, y_scalar,
+                                            x->shards[g], params_host, C, flags, out_g,
+                                            d_x ? d_x->shards[g] : nullptr);
+  }, out);
 }
 
 }  // namespace smc

@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -68,6 +69,7 @@ struct Context {
 };
 
 Context& ctx();
+Context& own_ctx();  // the calling thread's own context, whatever is current
 // Makes `c` (a shard's context) the one this thread's launches go to; NULL restores
 // the thread's own.  Returns the previous shard context (NULL: the thread's own).
 Context* swap_current_context(Context* c);
@@ -114,6 +116,10 @@ struct GlmCall {
   // un-fused density on a device linear predictor (lpmf.cu): the constant terms
   // of a broadcast scalar y follow prim/prob/<family>_lpmf.hpp, not the GLM
   bool unfused = false;
+  // row-sharded evaluation: false on every shard but the first, for the terms the
+  // reference adds once per call rather than once per row (the poisson GLM's
+  // lgamma(y + 1) of a broadcast scalar y)
+  bool once_terms = true;
   double* out = nullptr;  // packed result, device-accessible
   unsigned long long* done_flag = nullptr;  // see FusedArgs::done_flag
   unsigned long long done_val = 0;
@@ -161,6 +167,22 @@ struct Knobs {
 };
 const Knobs& knobs();
 uint64_t next_matrix_id();
+
+// ---- row-sharded matrices (sharded.cu) ------------------------------------------
+int shard_count_of(const smc_matrix* m);  // 0: a plain matrix
+bool same_partition(const smc_matrix* a, const smc_matrix* b);
+// fn(g, shard, first global row) for every shard, with that shard's device, stream
+// and workspace current; stops at the first non-zero status.
+int for_each_shard(const smc_matrix* m,
+                   const std::function<int(int, smc_matrix*, int64_t)>& fn);
+int synchronize_shards();
+// One evaluation over the shards of c.x; *out = the reduced packed result (host).
+int run_sharded(GlmCall& c, int n_out, const double** out);
+// categorical_logit_glm_lpmf over the shards of x; params_host = [beta K x C, alpha C],
+// *out = [logp, #non-finite, d_alpha[C], d_beta[K x C]] reduced, in host memory.
+int run_sharded_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
+                            const double* params_host, int64_t C, unsigned flags,
+                            smc_matrix* d_x, const double** out);
 
 int launch_categorical(const smc_matrix* y, int y_scalar, const smc_matrix* x,
                        const double* alpha_host, const double* beta_host,
@@ -214,11 +236,24 @@ struct smc_matrix {
   size_t grp_perm_bytes = 0, grp_off_bytes = 0;
   int64_t grp_G = 0;
   uint64_t grp_version = 0;
+  // A row-sharded matrix (sharded.cu): data is NULL and shard g -- a plain matrix on
+  // GPU g -- holds rows [shard_row0[g], shard_row0[g] + shards[g]->rows).
+  std::vector<smc_matrix*> shards;
+  std::vector<int64_t> shard_row0;
 };
 
 namespace smc {
 // A per-row operand (N x 1 or 1 x N) the kernels index as data[i]: contiguous.
 // smc_matrix_create lays vectors out that way; a wrapped strided row is refused.
+inline bool is_sharded(const smc_matrix* m) { return m && !m->shards.empty(); }
+// Entry points that have no row-sharded form yet refuse sharded handles up front.
+inline int refuse_sharded(const char* fn, std::initializer_list<const smc_matrix*> ms) {
+  for (const smc_matrix* m : ms)
+    if (is_sharded(m))
+      return fail(SMC_ERR_UNSUPPORTED, "%s: row-sharded operands are not supported here",
+                  fn);
+  return SMC_OK;
+}
 inline bool vec_contiguous(const smc_matrix* m) {
   return m->cols <= 1 || m->rows * m->cols == 0 || (m->rows == 1 && m->ld == 1);
 }

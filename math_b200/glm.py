@@ -72,14 +72,15 @@ def _beta(beta, K):
     return b
 
 
-def _vec_out(cond, N):
-    return MatrixCuda(N, 1, np.float64) if cond else None
+def _vec_out(cond, x):
+    """An N x 1 output vector laid out (and sharded) like the rows of x."""
+    return MatrixCuda.like(x, 1, np.float64) if cond else None
 
 
 def _dx_out(flags, x):
     if flags & DX_FACTORED:
-        return MatrixCuda(x.rows, 1, np.float64)
-    return MatrixCuda(x.rows, x.cols, np.float64) if flags & VAR_X else None
+        return MatrixCuda.like(x, 1, np.float64)
+    return MatrixCuda.like(x) if flags & VAR_X else None
 
 
 def _glm4(fn, y, x, alpha, beta, propto, var):
@@ -90,7 +91,7 @@ def _glm4(fn, y, x, alpha, beta, propto, var):
     logp = C.c_double()
     d_alpha = C.c_double()
     d_beta = np.zeros(x.cols)
-    d_av = _vec_out(av is not None and flags & VAR_ALPHA, x.rows)
+    d_av = _vec_out(av is not None and flags & VAR_ALPHA, x)
     d_x = _dx_out(flags, x)
     check(fn(_h(yv), ys, x.handle, _h(av), a0, _dp(b), flags, C.byref(logp),
              C.byref(d_alpha), _h(d_av), _dp(d_beta), _h(d_x)))
@@ -123,7 +124,7 @@ def binomial_logit_glm_lpmf(n, trials, x, alpha, beta, propto=False,
     logp = C.c_double()
     d_alpha = C.c_double()
     d_beta = np.zeros(x.cols)
-    d_av = _vec_out(av is not None and flags & VAR_ALPHA, x.rows)
+    d_av = _vec_out(av is not None and flags & VAR_ALPHA, x)
     d_x = _dx_out(flags, x)
     check(lib().smc_binomial_logit_glm(
         _h(nv), ns, _h(tv), ts, x.handle, _h(av), a0, _dp(b), flags,
@@ -145,9 +146,9 @@ def normal_id_glm_lpdf(y, x, alpha, beta, sigma, propto=False,
     N = x.rows
     logp, d_alpha, d_sigma, d_y = (C.c_double() for _ in range(4))
     d_beta = np.zeros(x.cols)
-    d_av = _vec_out(av is not None and flags & VAR_ALPHA, N)
-    d_sv = _vec_out(sv is not None and flags & VAR_AUX, N)
-    d_yv = _vec_out(yv is not None and flags & VAR_Y, N)
+    d_av = _vec_out(av is not None and flags & VAR_ALPHA, x)
+    d_sv = _vec_out(sv is not None and flags & VAR_AUX, x)
+    d_yv = _vec_out(yv is not None and flags & VAR_Y, x)
     d_x = _dx_out(flags, x)
     check(lib().smc_normal_id_glm(
         _h(yv), ys, x.handle, _h(av), a0, _dp(b), _h(sv), s0, flags,
@@ -172,8 +173,8 @@ def neg_binomial_2_log_glm_lpmf(y, x, alpha, beta, phi, propto=False,
     N = x.rows
     logp, d_alpha, d_phi = (C.c_double() for _ in range(3))
     d_beta = np.zeros(x.cols)
-    d_av = _vec_out(av is not None and flags & VAR_ALPHA, N)
-    d_pv = _vec_out(pv is not None and flags & VAR_AUX, N)
+    d_av = _vec_out(av is not None and flags & VAR_ALPHA, x)
+    d_pv = _vec_out(pv is not None and flags & VAR_AUX, x)
     d_x = _dx_out(flags, x)
     check(lib().smc_neg_binomial_2_log_glm(
         _h(yv), ys, x.handle, _h(av), a0, _dp(b), _h(pv), p0, flags,

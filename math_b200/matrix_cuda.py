@@ -46,6 +46,43 @@ class MatrixCuda:
                                           max(a.shape[0], 1)))
         return m
 
+    # -- row-sharded over the GPUs of the box (runtime.shard_init first) ---------
+    @classmethod
+    def sharded(cls, rows, cols=1, dtype=np.float64):
+        """rows x cols partitioned contiguously over the shard set: accepted wherever
+        a GLM takes a plain matrix (x and its per-row operands sharded alike)."""
+        code = I32 if np.dtype(dtype) == np.int32 else F64
+        h = C.c_void_p()
+        check(lib().smc_sharded_matrix_create(int(rows), int(cols), code, C.byref(h)))
+        return cls(rows, cols, dtype, _handle=h)
+
+    @classmethod
+    def from_host_sharded(cls, a):
+        """Scatter a host vector / matrix over the shard set (once per model)."""
+        a = np.asarray(a)
+        a = a.astype(np.int32) if a.dtype.kind in "iub" else a.astype(np.float64)
+        if a.ndim == 1:
+            a = a.reshape(-1, 1)
+        a = np.asfortranarray(a)
+        m = cls.sharded(a.shape[0], a.shape[1], a.dtype)
+        if a.size:
+            check(lib().smc_matrix_upload(m._h, a.ctypes.data_as(C.c_void_p),
+                                          max(a.shape[0], 1)))
+        return m
+
+    @classmethod
+    def like(cls, other, cols=None, dtype=None):
+        """A matrix with the rows -- and the row partition -- of `other`."""
+        code = -1 if dtype is None else (I32 if np.dtype(dtype) == np.int32 else F64)
+        h = C.c_void_p()
+        check(lib().smc_matrix_create_like(other._h, -1 if cols is None else int(cols),
+                                           code, C.byref(h)))
+        return cls(0, 0, _handle=h)
+
+    @property
+    def shard_count(self):
+        return lib().smc_matrix_shard_count(self._h)
+
     @classmethod
     def wrap(cls, device_ptr, rows, cols, ld, dtype=np.float64, keep=None):
         """Adopt an existing device buffer (e.g. a torch tensor's data_ptr)."""

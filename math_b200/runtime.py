@@ -24,6 +24,32 @@ def synchronize():
     check(lib().smc_synchronize())
 
 
+def shard_init(n_shards=0, devices=None):
+    """Set up the shard set for row-sharded matrices: one shard per GPU (all visible
+    ones by default); `devices` may repeat an id to put several shards on one GPU
+    (host-side reduction then; for tests on a single-GPU box)."""
+    arr = None
+    if devices is not None:
+        n_shards = len(devices)
+        arr = (C.c_int * n_shards)(*devices)
+    check(lib().smc_shard_init(int(n_shards), arr))
+    return shard_count()
+
+
+def shard_count():
+    n = C.c_int()
+    check(lib().smc_shard_count(C.byref(n)))
+    return n.value
+
+
+def shard_reduce_mode():
+    return (lib().smc_shard_reduce_mode() or b"").decode()
+
+
+def shard_shutdown():
+    check(lib().smc_shard_shutdown())
+
+
 def device_info():
     sm, maj, mnr = C.c_int(), C.c_int(), C.c_int()
     fr, tot = C.c_size_t(), C.c_size_t()

@@ -30,8 +30,10 @@ constexpr double kAbsFloor = 1e-12;
 /** Where an argument lives for the device evaluation. */
 struct host_t {};
 struct dev_t {};
+struct shard_t {};  // on the device, row-sharded over the shard set
 constexpr host_t HOST{};
 constexpr dev_t DEV{};
+constexpr shard_t SHARD{};
 
 inline void expect_close(const std::string& what, double dev, double cpu, double rel,
                          double scale) {
@@ -66,6 +68,8 @@ template <typename P, typename T>
 decltype(auto) place(P, const T& a) {
   if constexpr (std::is_same<P, dev_t>::value) {
     return stan::math::to_matrix_cuda(a);
+  } else if constexpr (std::is_same<P, shard_t>::value) {
+    return stan::math::to_matrix_cuda_sharded(a);
   } else {
     return (a);
   }

@@ -18,7 +18,8 @@ BUILD = os.path.join(HERE, "cpp", "_build")
 TESTS = ["matrix_cuda_test", "bernoulli_logit_glm_test", "poisson_log_glm_test",
          "normal_id_glm_test", "neg_binomial_2_log_glm_test",
          "ordered_logistic_glm_test", "categorical_logit_glm_test",
-         "binomial_logit_glm_test", "unfused_lpmf_test", "reduce_sum_threads_test"]
+         "binomial_logit_glm_test", "unfused_lpmf_test", "reduce_sum_threads_test",
+         "sharded_glm_test"]
 
 
 @pytest.mark.gpu
