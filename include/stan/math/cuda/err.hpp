@@ -17,6 +17,26 @@
 namespace stan {
 namespace math {
 
+/** Error category of backend failures (the codes are smc_status values, not errno). */
+class cuda_backend_category_t : public std::error_category {
+ public:
+  const char* name() const noexcept override { return "stanmath_cuda"; }
+  std::string message(int status) const override {
+    switch (status) {
+      case SMC_ERR_CUDA:
+        return "CUDA backend failure";
+      case SMC_ERR_UNSUPPORTED:
+        return "not supported by the CUDA backend";
+      default:
+        return "stanmath_cuda status " + std::to_string(status);
+    }
+  }
+};
+inline const std::error_category& cuda_backend_category() {
+  static const cuda_backend_category_t c;
+  return c;
+}
+
 inline void check_cuda_status(const char* function, int status) {
   if (status == SMC_OK) {
     return;
@@ -29,7 +49,7 @@ inline void check_cuda_status(const char* function, int status) {
     case SMC_ERR_DOMAIN:
       throw std::domain_error(msg);
     default:
-      throw std::system_error(status, std::generic_category(), msg);
+      throw std::system_error(status, cuda_backend_category(), msg);
   }
 }
 

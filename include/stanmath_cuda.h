@@ -90,6 +90,13 @@ int smc_synchronize(void);
 int smc_trim_cache(void);
 int smc_device_info(int* sm_count, int* cc_major, int* cc_minor,
                     size_t* free_bytes, size_t* total_bytes);
+/* Device-side timing (CUDA events on the calling thread's stream, and on every
+ * shard's stream: the maximum is reported) of the work queued between the calls. */
+int smc_timer_start(void);
+int smc_timer_stop(double* ms);
+/* The FP64 tensor-core (DMMA) rate this GPU sustains from registers, in TFLOP/s: the
+ * measured ceiling the categorical GLM's contraction rate is quoted against. */
+int smc_measure_dmma_peak(double* tflops);
 const char* smc_last_error(void);
 /* Number of GLM kernel launches issued by the calling thread since the last
  * smc_reset_launch_count (bench.py's gpu_launches). */
@@ -135,7 +142,8 @@ int smc_matrix_invalidate(smc_matrix* m);
 int smc_matrix_copy(smc_matrix* dst, const smc_matrix* src);
 /* out[i, k] = beta[k] * d[i] for an N x 1 f64 device vector d and K host doubles
  * (K <= 256): the N x K partial beta (x) d of an autodiff design matrix written as a
- * pure store stream.  out: N x K f64, 16-byte aligned, even leading dimension. */
+ * pure store stream (16-byte stores when `out` is 16-byte aligned with an even leading
+ * dimension -- what smc_matrix_create lays out -- else element by element). */
 int smc_matrix_outer(smc_matrix* out, const smc_matrix* d, const double* beta);
 /* y += a * x on the device: update_adjoints for a device-resident operand
  * (rev/functor/operands_and_partials.hpp L28-38). */
@@ -146,7 +154,7 @@ int smc_matrix_axpy(smc_matrix* y, double a, const smc_matrix* x);
  * (rev/functor/operands_and_partials.hpp L28-38;
  * prim/prob/neg_binomial_2_log_glm_lpmf.hpp L221-222) as ONE read-modify-write of the
  * adjoint -- or one pure store when y is lazily zero -- without ever forming the
- * N x K partial.  y: 16-byte aligned, even leading dimension. */
+ * N x K partial. */
 int smc_matrix_rank1_update(smc_matrix* y, double a, const smc_matrix* d,
                             const double* beta);
 /* Lazy value checks (cf. check_cl in opencl/prim/ *_glm_*.hpp). */

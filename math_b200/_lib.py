@@ -45,6 +45,9 @@ SIGNATURES = {
     "smc_trim_cache": (_I, []),
     "smc_device_info": (_I, [C.POINTER(_I), C.POINTER(_I), C.POINTER(_I),
                              C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "smc_timer_start": (_I, []),
+    "smc_timer_stop": (_I, [_DP]),
+    "smc_measure_dmma_peak": (_I, [_DP]),
     "smc_last_error": (C.c_char_p, []),
     "smc_launch_count": (_I64, []),
     "smc_reset_launch_count": (None, []),

@@ -36,6 +36,8 @@ Context::~Context() {
   if (params_dev) cudaFree(params_dev);
   if (scratch) cudaFree(scratch);
   if (out_host) cudaFreeHost(out_host);
+  for (cudaEvent_t e : timer_ev)
+    if (e) cudaEventDestroy(e);
   if (own_stream) cudaStreamDestroy(own_stream);
 }
 
@@ -304,6 +306,21 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// The same update for layouts the paired kernel cannot take (odd leading dimension,
+// unaligned base: one-row shards, wrapped buffers): one element per thread.
+template <bool RMW>
+__global__ void outer_scalar_kernel(const __grid_constant__ OuterArgs a) {
+  const int64_t total = a.N * a.K;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = i / a.N, r = i - k * a.N;
+    const double b = a.beta_dev ? __ldg(a.beta_dev + k) : a.beta[k];
+    const double v = (b * a.d[r]) * a.a;
+    double* o = a.out + k * a.ld + r;
+    *o = (RMW ? *o : 0.0) + v;
+  }
+}
+
 __host__ __device__ inline uint64_t synth_hash(uint64_t seed, uint64_t row,
                                                uint64_t col) {
   uint64_t z = seed + row * 0x9E3779B97F4A7C15ull + col * 0xBF58476D1CE4E5B9ull;
@@ -363,10 +380,9 @@ static int launch_rank1(double* out, int64_t ld, const double* d, int64_t N, int
                         const double* beta_host, const double* beta_dev, double scale,
                         bool rmw) {
   if (N == 0 || K == 0) return SMC_OK;
-  if (K > kMaxParamDoubles || (reinterpret_cast<uintptr_t>(out) & 15) || (K > 1 && (ld & 1)))
-    return fail(SMC_ERR_UNSUPPORTED,
-                "outer: needs K <= %d and a 16-byte aligned matrix with an even ld",
-                kMaxParamDoubles);
+  if (K > kMaxParamDoubles)
+    return fail(SMC_ERR_UNSUPPORTED, "outer: needs K <= %d", kMaxParamDoubles);
+  const bool paired = !(reinterpret_cast<uintptr_t>(out) & 15) && !(K > 1 && (ld & 1));
   OuterArgs a;
   a.out = out;
   a.ld = ld;
@@ -376,8 +392,12 @@ static int launch_rank1(double* out, int64_t ld, const double* d, int64_t N, int
   a.a = scale;
   a.beta_dev = beta_dev;
   if (!beta_dev) memcpy(a.beta, beta_host, sizeof(double) * K);
-  const int grid = grid_for((N + 1) / 2, 256);
-  if (rmw)
+  const int grid = grid_for(paired ? (N + 1) / 2 : N * K, 256);
+  if (!paired && rmw)
+    outer_scalar_kernel<true><<<grid, 256, 0, t_cur->stream>>>(a);
+  else if (!paired)
+    outer_scalar_kernel<false><<<grid, 256, 0, t_cur->stream>>>(a);
+  else if (rmw)
     outer_kernel<true, true><<<grid, 256, 0, t_cur->stream>>>(a);
   else if (scale != 1.0)
     outer_kernel<false, true><<<grid, 256, 0, t_cur->stream>>>(a);
@@ -467,6 +487,35 @@ int smc_device_info(int* sm_count, int* cc_major, int* cc_minor,
   SMC_CUDA(cudaMemGetInfo(&f, &t));
   if (free_bytes) *free_bytes = f;
   if (total_bytes) *total_bytes = t;
+  return SMC_OK;
+}
+
+// Device-side timing of whatever the calling thread queues between the two calls:
+// CUDA events on the launching stream(s), as bench.py's roofline figures need them.
+int smc_timer_start(void) {
+  if (int rc = ensure_ctx()) return rc;
+  Context& c = ctx();
+  for (cudaEvent_t& e : c.timer_ev)
+    if (!e) SMC_CUDA(cudaEventCreate(&e));
+  SMC_CUDA(cudaEventRecord(c.timer_ev[0], c.stream));
+  return shards_timer_start();
+}
+
+int smc_timer_stop(double* ms) {
+  if (!ms) return fail(SMC_ERR_INVALID_ARGUMENT, "ms is NULL");
+  if (int rc = ensure_ctx()) return rc;
+  Context& c = ctx();
+  if (!c.timer_ev[0] || !c.timer_ev[1])
+    return fail(SMC_ERR_INVALID_ARGUMENT, "smc_timer_stop without smc_timer_start");
+  SMC_CUDA(cudaEventRecord(c.timer_ev[1], c.stream));
+  double shard_ms = 0.0;
+  bool any = false;
+  if (int rc = shards_timer_stop(&shard_ms, &any)) return rc;
+  SMC_CUDA(cudaSetDevice(c.device));
+  SMC_CUDA(cudaEventSynchronize(c.timer_ev[1]));
+  float own = 0.f;
+  SMC_CUDA(cudaEventElapsedTime(&own, c.timer_ev[0], c.timer_ev[1]));
+  *ms = any && shard_ms > own ? shard_ms : (double)own;
   return SMC_OK;
 }
 

@@ -171,6 +171,42 @@ int synchronize_shards() {
   return SMC_OK;
 }
 
+int shards_timer_start() {
+  ShardComm& sc = comm();
+  for (Shard* s : sc.shards) {
+    SMC_CUDA(cudaSetDevice(s->device));
+    for (cudaEvent_t& e : s->ctx.timer_ev)
+      if (!e) SMC_CUDA(cudaEventCreate(&e));
+    SMC_CUDA(cudaEventRecord(s->ctx.timer_ev[0], s->ctx.stream));
+  }
+  Context& cur = ctx();
+  if (cur.inited) SMC_CUDA(cudaSetDevice(cur.device));
+  return SMC_OK;
+}
+
+int shards_timer_stop(double* ms_max, bool* any) {
+  ShardComm& sc = comm();
+  *ms_max = 0.0;
+  *any = false;
+  for (Shard* s : sc.shards) {
+    if (!s->ctx.timer_ev[0] || !s->ctx.timer_ev[1]) continue;
+    SMC_CUDA(cudaSetDevice(s->device));
+    SMC_CUDA(cudaEventRecord(s->ctx.timer_ev[1], s->ctx.stream));
+  }
+  for (Shard* s : sc.shards) {
+    if (!s->ctx.timer_ev[0] || !s->ctx.timer_ev[1]) continue;
+    SMC_CUDA(cudaSetDevice(s->device));
+    SMC_CUDA(cudaEventSynchronize(s->ctx.timer_ev[1]));
+    float ms = 0.f;
+    SMC_CUDA(cudaEventElapsedTime(&ms, s->ctx.timer_ev[0], s->ctx.timer_ev[1]));
+    if (ms > *ms_max) *ms_max = ms;
+    *any = true;
+  }
+  Context& cur = ctx();
+  if (cur.inited) SMC_CUDA(cudaSetDevice(cur.device));
+  return SMC_OK;
+}
+
 // The common skeleton of a sharded evaluation: launch(g, shard, out_g) queues shard
 // g's work on its stream with the packed result (n_out doubles) going to out_g; the
 // G results are then summed -- NCCL all-reduce in place on those streams and one

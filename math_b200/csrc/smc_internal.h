@@ -55,6 +55,7 @@ struct Context {
   double* scratch = nullptr;   // generic device scratch (N-vectors for fallbacks)
   size_t scratch_bytes = 0;
   int64_t launches = 0;
+  cudaEvent_t timer_ev[2] = {nullptr, nullptr};  // smc_timer_start / smc_timer_stop
   unsigned long long sync_seq = 0;  // value the next polled completion flag takes
   bool flag_armed = false;          // the last launch will store its completion flag
   // Recycled device blocks, keyed by exact size.  An HMC run allocates the same
@@ -176,6 +177,9 @@ bool same_partition(const smc_matrix* a, const smc_matrix* b);
 int for_each_shard(const smc_matrix* m,
                    const std::function<int(int, smc_matrix*, int64_t)>& fn);
 int synchronize_shards();
+// smc_timer_*: the same two events on every shard's stream (stop: max over shards)
+int shards_timer_start();
+int shards_timer_stop(double* ms_max, bool* any);
 // One evaluation over the shards of c.x; *out = the reduced packed result (host).
 int run_sharded(GlmCall& c, int n_out, const double** out);
 // categorical_logit_glm_lpmf over the shards of x; params_host = [beta K x C, alpha C],

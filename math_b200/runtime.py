@@ -50,6 +50,24 @@ def shard_shutdown():
     check(lib().smc_shard_shutdown())
 
 
+def timer_start():
+    """CUDA events on the launching stream(s): device time of what follows."""
+    check(lib().smc_timer_start())
+
+
+def timer_stop():
+    ms = C.c_double()
+    check(lib().smc_timer_stop(C.byref(ms)))
+    return ms.value
+
+
+def measure_dmma_peak():
+    """TFLOP/s of the FP64 tensor pipe from registers (a few milliseconds)."""
+    v = C.c_double()
+    check(lib().smc_measure_dmma_peak(C.byref(v)))
+    return v.value
+
+
 def device_info():
     sm, maj, mnr = C.c_int(), C.c_int(), C.c_int()
     fr, tot = C.c_size_t(), C.c_size_t()

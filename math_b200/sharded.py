@@ -38,6 +38,12 @@ def packed_size(K, ncuts=0):
     return OUT_HEADER + K + ncuts
 
 
+def _ptr(buf):
+    """Device address of a torch tensor or of a MatrixCuda."""
+    p = buf.data_ptr
+    return C.c_void_p(p() if callable(p) else p)
+
+
 def cuda_local_eval(family, y, x, alpha, aux, params_t, ncuts, flags, out_t,
                     d_alpha_vec=None, d_aux_vec=None, d_y_vec=None, d_x=None):
     """Asynchronous evaluation of this rank's shard on the current torch stream:
@@ -54,9 +60,8 @@ def cuda_local_eval(family, y, x, alpha, aux, params_t, ncuts, flags, out_t,
     h = lambda m: m.handle if m is not None else None  # noqa: E731
     check(lib().smc_glm_eval_device(
         FAMILY[family], yh, ys, x.handle, ah, a0, xh, x0,
-        C.c_void_p(params_t.data_ptr()), int(ncuts), int(flags),
-        C.c_void_p(out_t.data_ptr()), h(d_alpha_vec), h(d_aux_vec), h(d_y_vec),
-        h(d_x)))
+        _ptr(params_t), int(ncuts), int(flags), _ptr(out_t), h(d_alpha_vec),
+        h(d_aux_vec), h(d_y_vec), h(d_x)))
 
 
 class ShardedGlm:
@@ -123,8 +128,8 @@ def cuda_local_eval_categorical(y, x, params_t, n_classes, flags, out_t, d_x=Non
     from .matrix_cuda import MatrixCuda
     yh, ys = (y.handle, 0) if isinstance(y, MatrixCuda) else (None, int(y))
     check(lib().smc_categorical_logit_glm_device(
-        yh, ys, x.handle, C.c_void_p(params_t.data_ptr()), int(n_classes), int(flags),
-        C.c_void_p(out_t.data_ptr()), d_x.handle if d_x is not None else None))
+        yh, ys, x.handle, _ptr(params_t), int(n_classes), int(flags), _ptr(out_t),
+        d_x.handle if d_x is not None else None))
 
 
 class ShardedCategoricalGlm(ShardedGlm):

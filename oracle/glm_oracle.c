@@ -816,3 +816,79 @@ int oracle_binomial_logit_glm(long N, long K, const int* n, long nn,
   free(d);
   return 0;
 }
+
+/* ------------------------------------------------------------------ synthetic inputs
+ * Host replica of the counter-based generator behind smc_matrix_fill_synthetic
+ * (include/stanmath_cuda.h): splitmix-style hash of (seed, global row, column), exact
+ * integer arithmetic and one correctly rounded multiply, so host and device hold the
+ * same bits.  Column-major with leading dimension ld.  This is how the CPU arms of
+ * bench.py get the GPU arm's inputs at full size without a 20 GB transfer; the
+ * threads only spread the row range over the host cores. */
+#include <pthread.h>
+#include <stdint.h>
+#include <unistd.h>
+
+static inline uint64_t synth_hash(uint64_t seed, uint64_t row, uint64_t col) {
+  uint64_t z = seed + row * 0x9E3779B97F4A7C15ull + col * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+typedef struct {
+  void* out;
+  long ld, r_lo, r_hi, cols, row0;
+  uint64_t seed;
+  int kind, lo, hi;
+  double c;
+} synth_job;
+
+static void* synth_worker(void* arg) {
+  const synth_job* j = (const synth_job*)arg;
+  const uint64_t span = (uint64_t)((int64_t)j->hi - (int64_t)j->lo + 1);
+  for (long k = 0; k < j->cols; ++k)
+    for (long r = j->r_lo; r < j->r_hi; ++r) {
+      const uint64_t z = synth_hash(j->seed, (uint64_t)(j->row0 + r), (uint64_t)k);
+      if (j->kind == 0) {
+        const uint32_t u = (uint32_t)(z & 0xffff) + (uint32_t)((z >> 16) & 0xffff)
+                           + (uint32_t)((z >> 32) & 0xffff) + (uint32_t)(z >> 48);
+        ((double*)j->out)[k * j->ld + r] = ((double)u - 131070.0) * j->c;
+      } else {
+        ((int*)j->out)[k * j->ld + r] = (int)((int64_t)j->lo + (int64_t)(z % span));
+      }
+    }
+  return NULL;
+}
+
+static void synth_run(synth_job base, long rows) {
+  long nt = sysconf(_SC_NPROCESSORS_ONLN);
+  if (nt < 1) nt = 1;
+  if (nt > 64) nt = 64;
+  if (rows * base.cols < 1000000) nt = 1;
+  pthread_t th[64];
+  synth_job jobs[64];
+  for (long t = 0; t < nt; ++t) {
+    jobs[t] = base;
+    jobs[t].r_lo = rows * t / nt;
+    jobs[t].r_hi = rows * (t + 1) / nt;
+    if (nt == 1)
+      synth_worker(&jobs[t]);
+    else
+      pthread_create(&th[t], NULL, synth_worker, &jobs[t]);
+  }
+  if (nt > 1)
+    for (long t = 0; t < nt; ++t) pthread_join(th[t], NULL);
+}
+
+void oracle_synthetic_f64(double* out, long ld, long rows, long cols, uint64_t seed,
+                          long row0, double scale) {
+  synth_job j = {out, ld, 0, 0, cols, row0, seed, 0, 0, 0,
+                 scale / sqrt(4294967295.0 / 3.0)};
+  synth_run(j, rows);
+}
+
+void oracle_synthetic_i32(int* out, long ld, long rows, long cols, uint64_t seed, long row0,
+                          int lo, int hi) {
+  synth_job j = {out, ld, 0, 0, cols, row0, seed, 1, lo, hi, 0.0};
+  synth_run(j, rows);
+}

@@ -60,6 +60,23 @@ def oracle_lib():
     return _oracle
 
 
+def synthetic(seed, row0, nrows, ncols, kind=0, scale=1.0, lo=0, hi=1):
+    """The inputs smc_matrix_fill_synthetic puts on the GPU, generated on the host by
+    the C oracle (column-major; all host cores): bit-identical by construction."""
+    lib = oracle_lib()
+    if kind == 0:
+        out = np.empty((nrows, ncols), dtype=np.float64, order="F")
+        lib.oracle_synthetic_f64(out.ctypes.data_as(C.c_void_p), C.c_long(max(nrows, 1)),
+                                 C.c_long(nrows), C.c_long(ncols), C.c_uint64(seed),
+                                 C.c_long(row0), C.c_double(scale))
+    else:
+        out = np.empty((nrows, ncols), dtype=np.int32, order="F")
+        lib.oracle_synthetic_i32(out.ctypes.data_as(C.c_void_p), C.c_long(max(nrows, 1)),
+                                 C.c_long(nrows), C.c_long(ncols), C.c_uint64(seed),
+                                 C.c_long(row0), C.c_int(lo), C.c_int(hi))
+    return out
+
+
 def ref_available(mt=False):
     return os.path.exists(os.path.join(
         HERE, "_ref", "libstan_ref_mt.so" if mt else "libstan_ref.so"))

@@ -44,7 +44,9 @@ def test_bernoulli_sharded(gpu, shard_set, N, K):
     _close(rs.d_beta, r1.d_beta, "d_beta vs one GPU")
     _close(rs.d_alpha, r1.d_alpha, "d_alpha vs one GPU")
     assert rs.d_x.shard_count == shard_set
-    np.testing.assert_array_equal(rs.d_x.to_host(), r1.d_x.to_host())
+    # (to the last bit or two: a one-row shard takes the general kernel, whose dot
+    # product associates differently from the fused one)
+    _close(rs.d_x.to_host(), r1.d_x.to_host(), "d_x vs one GPU")
     assert_logp(rs.logp, o["logp"])
     assert_grad(rs.d_beta, o["d_beta"], "d_beta")
     assert_grad(rs.d_x.to_host(), o["d_x"], "d_x")
@@ -54,7 +56,7 @@ def test_bernoulli_sharded(gpu, shard_set, N, K):
     adj = gpu.MatrixCuda.like(xs)
     adj.zero_lazy()
     adj.rank1_update(1.0, rf.d_x, d["beta"])
-    np.testing.assert_array_equal(adj.to_host(), r1.d_x.to_host())
+    np.testing.assert_array_equal(adj.to_host(), rs.d_x.to_host())
     # propto with nothing autodiff: 0, and the y check still runs on every shard
     assert gpu.bernoulli_logit_glm_lpmf(ys, xs, d["alpha"], d["beta"], propto=True,
                                         var=()).logp == 0.0
