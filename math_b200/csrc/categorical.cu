@@ -447,18 +447,27 @@ __global__ void __launch_bounds__(kLinThreads, 1)
   // the moment the slot becomes free.
   const uint64_t pol = policy_evict_first();
   const uint64_t pol_keep = policy_evict_last();  // beta is re-read by every row block
-  auto issue = [&](int64_t q, int st) {  // q-th stage load of this CTA, into slot st
-    const int64_t blk = blockIdx.x + (q / ksteps) * gridDim.x;
-    const int ks = (int)(q % ksteps);
+  // stage load (first row `row` of its row block, k-step ks) into slot st
+  auto issue = [&](int row, int ks, int st) {
     double* dst = ring + (size_t)st * (stage_bytes / 8);
     mbar_expect_tx(&full_bar[st], stage_bytes);
-    tma_load_2d(dst, &tmx, (int)(blk * kLinRows), ks * KS, &full_bar[st], pol);
-    tma_load_2d(dst + xbox, &tmx, (int)(blk * kLinRows + 128), ks * KS, &full_bar[st],
-                pol);
+    tma_load_2d(dst, &tmx, row, ks * KS, &full_bar[st], pol);
+    tma_load_2d(dst + xbox, &tmx, row + 128, ks * KS, &full_bar[st], pol);
     tma_load_2d(dst + 2 * xbox, &tmb, 0, ks * KS, &full_bar[st], pol_keep);
   };
-  if (tid == 0)
-    for (int64_t q = 0; q < kLinStages && q < total; ++q) issue(q, (int)q);
+  // Every warp tracks (row block, k-step) of the stage load that refills the slot it is
+  // about to leave -- stage q + kLinStages -- by increments: whichever warp leaves last
+  // issues it, and that warp is the one every other warp is waiting for (two 64-bit
+  // divisions on its path showed up as ~8 % of the sweep, profiles/r02/r02_cat_hack.jsonl).
+  int n_row = blockIdx.x * kLinRows, n_ks = 0;
+  const int row_step = gridDim.x * kLinRows;
+  for (int q0 = 0; q0 < kLinStages; ++q0) {
+    if (tid == 0 && q0 < total) issue(n_row, n_ks, q0);
+    if (++n_ks == ksteps) {
+      n_ks = 0;
+      n_row += row_step;
+    }
+  }
 
   double lp_acc = 0.0, bad_acc = 0.0;
   double dal[NT][2];
@@ -479,6 +488,9 @@ __global__ void __launch_bounds__(kLinThreads, 1)
       for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
     for (int ks = 0; ks < ksteps; ++ks, ++q) {
+#if defined(SMC_CAT_HACK) && (SMC_CAT_HACK & 2)
+      if (q < kLinStages)
+#endif
       mbar_wait(&full_bar[st], ph);
       // A: x[r0 + 2 grp + {0, 1}][KS ks + 4 h + tig]      one double2
       // B: beta[KS ks + 4 h + tig][16 p + 2 grp + {0, 1}]  one double2 per pair
@@ -506,14 +518,27 @@ __global__ void __launch_bounds__(kLinThreads, 1)
         }
       }
       // release the slot; the last warp out refills it
+#if !defined(SMC_CAT_HACK) || !(SMC_CAT_HACK & 4)
       __syncwarp();
       if (lane == 0) {
+#if !defined(SMC_CAT_HACK) || !(SMC_CAT_HACK & 8)
         __threadfence_block();
+#endif
         if (atomicAdd(&rel_cnt[st], 1) == kLinWarps - 1) {
           rel_cnt[st] = 0;
+#if !defined(SMC_CAT_HACK) || !(SMC_CAT_HACK & 8)
           __threadfence_block();
-          if (q + kLinStages < total) issue(q + kLinStages, st);
+#endif
+#if defined(SMC_CAT_HACK) && (SMC_CAT_HACK & 2)
+          if (false)
+#endif
+          if (q + kLinStages < total) issue(n_row, n_ks, st);
         }
+      }
+#endif
+      if (++n_ks == ksteps) {
+        n_ks = 0;
+        n_row += row_step;
       }
       if (++st == kLinStages) {
         st = 0;
@@ -521,6 +546,16 @@ __global__ void __launch_bounds__(kLinThreads, 1)
       }
     }
     if (r0 >= a.N) continue;
+#if defined(SMC_CAT_HACK) && (SMC_CAT_HACK & 1)
+    {
+      double sacc = 0.0;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) sacc += acc[0][nt][0] + acc[0][nt][1] + acc[1][nt][0] + acc[1][nt][1];
+      if (sacc == 1.2345e-300) a.T[0] = sacc;
+      lp_acc += sacc;
+      continue;
+    }
+#endif
 
     if (a.lin_only) {
       // rows 2 grp, 2 grp + 1 of a class are adjacent: one 16-byte store
@@ -968,7 +1003,7 @@ static bool cat_tma_ok(const smc_matrix* x) {
   if (!get_encode()) return false;
   if ((reinterpret_cast<uintptr_t>(x->data) & 15) != 0) return false;
   if (x->cols > 1 && (x->ld & 1)) return false;
-  return x->rows < 0x7fffff00ll && x->cols >= 1;
+  return x->rows < 0x7ff00000ll && x->cols >= 1;  // (row coordinates are 32-bit, one sweep of the grid past N)
 }
 
 // The two sweeps are also the matrix products either side of an un-fused
