@@ -48,6 +48,26 @@ __device__ __forceinline__ double softmax_row(double* v, double* outp) {
   return log(inv) - m;
 }
 
+__device__ __forceinline__ float softmax_row_f(float* v, double* outp) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m = fmaxf(m, v[i]);
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+  float se = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] = expf(v[i] - m);
+    se += v[i];
+  }
+  se += __shfl_xor_sync(0xffffffffu, se, 1);
+  se += __shfl_xor_sync(0xffffffffu, se, 2);
+  const float inv = 1.0f / se;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) outp[i * 32] = v[i] * -inv;
+  return logf(inv) - m;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(512, 1) epi_kernel(int blocks, double* out) {
   extern __shared__ double smem[];
@@ -214,7 +234,19 @@ __global__ void __launch_bounds__(512, 1) epi_kernel(int blocks, double* out) {
         if (++st == 2) st = 0;
         if (MODE == 2 && pending && ks < 14) slice(ks);
       }
-      if (MODE == 1) {
+      if (MODE == 5) {
+        float v0[8], v1[8];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            v0[2 * nt + j] = (float)acc[0][nt][j];
+            v1[2 * nt + j] = (float)acc[1][nt][j];
+          }
+        lp += softmax_row_f(v0, my);
+        lp += softmax_row_f(v1, my + 8 * 32);
+      }
+      if (MODE == 1 || MODE == 4) {
         double v0[8], v1[8];
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
@@ -225,6 +257,10 @@ __global__ void __launch_bounds__(512, 1) epi_kernel(int blocks, double* out) {
           }
         lp += softmax_row(v0, my);
         lp += softmax_row(v1, my + 8 * 32);
+        if (MODE == 4) {
+          lp += softmax_row(v0, my);
+          lp += softmax_row(v1, my + 8 * 32);
+        }
       }
       if (MODE == 2) {
 #pragma unroll
@@ -235,7 +271,10 @@ __global__ void __launch_bounds__(512, 1) epi_kernel(int blocks, double* out) {
             for (int j = 0; j < 2; ++j) my[(8 * mt + 2 * nt + j) * 32] = acc[mt][nt][j];
         pending = true;
       }
-      if (MODE == 0) lp += acc[0][0][0] + acc[1][1][1] + acc[0][2][0] + acc[1][3][1];
+      if (MODE == 0) {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) lp += acc[0][nt][0] + acc[0][nt][1] + acc[1][nt][0] + acc[1][nt][1];
+      }
     }
   }
   if (lp == 12345.678) out[0] = lp;
@@ -271,5 +310,7 @@ int main() {
   run<1>(sms, out);
   run<2>(sms, out);
   run<3>(sms, out);
+  run<4>(sms, out);
+  run<5>(sms, out);
   return 0;
 }
