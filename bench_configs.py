@@ -92,8 +92,13 @@ def run_one(cfg, reps=None):
         flags = _lib.VAR_ALPHA | _lib.VAR_BETA | _lib.VAR_AUX
         params, out = dev_vec(beta), mb.MatrixCuda(_lib.OUT_HEADER + K, 1)
         n = reps or 500
-        ms = device(lambda: cuda_local_eval("normal_id", y, x, 0.1, 1.3, params, 0, flags, out),
-                    n)
+        # the launches must come faster than the ~10 us kernel or the figure is the host's
+        # call rate: the C entry point with pre-converted arguments, not the Python wrapper
+        from math_b200.sharded import FAMILY, _ptr
+        fn = _lib.lib().smc_glm_eval_device
+        args = (FAMILY["normal_id"], y.handle, 0.0, x.handle, None, 0.1, None, 1.3,
+                _ptr(params), 0, int(flags), _ptr(out), None, None, None, None)
+        ms = device(lambda: fn(*args), n)
         e2e = wall(lambda: mb.normal_id_glm_lpdf(y, x, 0.1, beta, 1.3), n)
         byt = N * K * 8
         rec["workload"] = ("normal_id_glm_lpdf N=1e4 K=100, alpha/beta/sigma var (8 MB: "

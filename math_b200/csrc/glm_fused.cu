@@ -29,6 +29,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 #include "glm_link.cuh"
 #include "tma_utils.cuh"
@@ -134,12 +135,51 @@ __global__ void __launch_bounds__(256, 1)
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* part_bar = empty_bar + kStages;  // [G][2]: partial dot products published
   uint64_t* d_bar = part_bar + 2 * G;        // [G][2]: d published by the lead warp
-  double* hdr_s = reinterpret_cast<double*>(d_bar + 2 * G);  // [warps][8] row sums
+  uint64_t* fin_bar = d_bar + 2 * G;         // the CTAs' partials have landed (last CTA)
+  double* hdr_s = reinterpret_cast<double*>(fin_bar + 1);  // [warps][8] row sums
   double* dv_s = hdr_s + (size_t)n_cons_warps * kHdr;  // [2][R] (lead-only links)
   __shared__ int s_last;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
+#ifdef SMC_FUSED_TRACE
+  // profiling build: %globaltimer (ns) of thread 0 at the phases of the kernel
+  auto stamp = [&](int k) {
+    if (tid == 0 && a.trace) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      a.trace[blockIdx.x * 8 + k] = t;
+    }
+  };
+  stamp(0);
+#else
+  auto stamp = [&](int) {};
+#endif
+
+  // Thread 0 doubles as the TMA producer (a ninth warp would put three warps
+  // on one SM sub-partition and cap every thread at 168 registers).  It sets the
+  // barriers up and fills the ring before anything else: the first tile is in flight
+  // while the CTA stages its parameters (0.3 us of a 10 us evaluation at N = 1e4).
+  uint64_t pol = 0;
+  if (tid == 0) {
+    for (int st = 0; st < kStages; ++st) {
+      mbar_init(&full_bar[st], 1);
+      mbar_init(&empty_bar[st], n_cons_warps);
+    }
+    for (int j = 0; j < 2 * G; ++j) mbar_init(&part_bar[j], S);
+    for (int j = 0; j < 2 * G; ++j) mbar_init(&d_bar[j], 1);
+    mbar_init(fin_bar, 1);
+    fence_barrier_init();
+    pol = policy_evict_first();
+    for (int j = 0; j < kStages; ++j) {
+      const int64_t tile = (int64_t)blockIdx.x + (int64_t)j * gridDim.x;
+      if (tile < a.ntiles) {
+        mbar_expect_tx(&full_bar[j], stage_bytes);
+        tma_load_2d(tiles + (size_t)j * (stage_bytes / 8), &tmap, (int)tile * R, 0,
+                    &full_bar[j], pol);
+      }
+    }
+  }
 
   // parameters -> shared memory
   const double* params = a.params_dev ? a.params_dev : a.inline_params;
@@ -168,16 +208,8 @@ __global__ void __launch_bounds__(256, 1)
       }
     }
   }
-  if (tid == 0) {
-    for (int st = 0; st < kStages; ++st) {
-      mbar_init(&full_bar[st], 1);
-      mbar_init(&empty_bar[st], n_cons_warps);
-    }
-    for (int j = 0; j < 2 * G; ++j) mbar_init(&part_bar[j], S);
-    for (int j = 0; j < 2 * G; ++j) mbar_init(&d_bar[j], 1);
-    fence_barrier_init();
-  }
   __syncthreads();
+  stamp(1);
 
   // consumer identity: slab-major, so the S warps of a row group share one SM
   // sub-partition when G = 4 and the row groups spread over all four
@@ -191,22 +223,7 @@ __global__ void __launch_bounds__(256, 1)
   constexpr bool need_dx = DX;
   const bool need_cuts = FAM == kOrdered && (a.flags & SMC_VAR_AUX);
 
-  // Thread 0 doubles as the TMA producer (a ninth warp would put three warps
-  // on one SM sub-partition and cap every thread at 168 registers).  Prologue:
-  // fill the ring.
-  uint64_t pol = 0;
   const uint64_t pol_dx = DX && lane == 0 ? policy_evict_first() : 0;
-  if (tid == 0) {
-    pol = policy_evict_first();
-    for (int j = 0; j < kStages; ++j) {
-      const int64_t tile = (int64_t)blockIdx.x + (int64_t)j * gridDim.x;
-      if (tile < a.ntiles) {
-        mbar_expect_tx(&full_bar[j], stage_bytes);
-        tma_load_2d(tiles + (size_t)j * (stage_bytes / 8), &tmap, (int)tile * R, 0,
-                    &full_bar[j], pol);
-      }
-    }
-  }
   {
     // Software pipeline over this CTA's tiles t = blockIdx.x + it * gridDim.x:
     //   stage A(it)  wait for the tile, pull the warp's 32 x 32 slab into
@@ -271,6 +288,7 @@ __global__ void __launch_bounds__(256, 1)
       if (need_dx) nxt = load_row<FAM>(a, (int64_t)blockIdx.x * R + rloc);
       stage_a(0);
     }
+    stamp(2);
     for (int it = 0; it < my_tiles; ++it) {
       const int par = it & 1;
       const int tile = blockIdx.x + it * gridDim.x;
@@ -390,16 +408,30 @@ __global__ void __launch_bounds__(256, 1)
   // ------------------------------------------------ CTA-level reduction
   if (DX && lane == 0) bulk_wait_read0();  // the last d_x slabs have left
   __syncthreads();  // every tile consumed; the ring is reusable as scratch
+  stamp(3);
   double* red = tiles;  // [G][pstride]
   const int ps = a.pstride;
-  for (int j = tid; j < G * ps; j += blockDim.x) red[j] = 0.0;
-  __syncthreads();
+  // (only the d_cuts columns can stay unwritten below)
+  for (int j = tid; j < G * ps; j += blockDim.x)
+    if (j % ps >= kHdr + CW) red[j] = 0.0;
+  if (need_cuts) __syncthreads();
   {
+    // column sums of the warp's 32 x 32 slab: a transposing butterfly -- each step
+    // halves the number of columns a lane carries (the lane keeps one half and sends
+    // the other to its partner), 31 shuffles instead of 32 five-step warp sums; lane l
+    // ends up with the total of column l (fixed association)
+    static_assert(kColsPerThread == 32, "one column per lane");
 #pragma unroll
-    for (int kk = 0; kk < kColsPerThread; ++kk) {
-      const double v = warp_sum(acc[kk]);
-      if (lane == kk) red[g * ps + kHdr + 32 * s + kk] = v;
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool upper = lane & off;
+#pragma unroll
+      for (int i = 0; i < off; ++i) {
+        const double send = upper ? acc[i] : acc[i + off];
+        const double keep = upper ? acc[i + off] : acc[i];
+        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
     }
+    red[g * ps + kHdr + 32 * s + lane] = acc[0];
     {
       // every warp led some of its row group's tiles: row sums per warp
       const double v0 = warp_sum(racc.lp), v1 = warp_sum(racc.sd),
@@ -443,6 +475,7 @@ __global__ void __launch_bounds__(256, 1)
   }
 
   // ------------------------------------------------ grid-level reduction
+  stamp(4);
   __threadfence();
   __syncthreads();
   if (tid == 0) {
@@ -450,20 +483,52 @@ __global__ void __launch_bounds__(256, 1)
     s_last = ticket == gridDim.x - 1;
   }
   __syncthreads();
+  stamp(5);
   if (s_last) {
     __threadfence();
     const int nb = gridDim.x;
+    // The CTAs' partials come into the (now free) ring with bulk copies when they fit:
+    // one thread walking 148 L2 lines per column, sixteen loads at a time, was 4 us of
+    // the 11 us this kernel takes at N = 1e4 (profiles/r02/r02_fused_trace_cfg1.txt);
+    // the copy engine fetches the same 160 KB in a third of that.
+    const uint32_t fin_bytes = (uint32_t)nb * ps * 8u;
+    const bool staged = fin_bytes <= (uint32_t)kStages * stage_bytes;
+    const double* part = a.partials;
+    if (staged) {
+      if (tid == 0) {
+        // the ring was written by generic-proxy stores (red), the partials by other
+        // CTAs' generic-proxy stores: order both before the async-proxy copy
+        asm volatile("fence.proxy.async;" ::: "memory");
+        mbar_expect_tx(fin_bar, fin_bytes);
+        for (uint32_t off = 0; off < fin_bytes; off += 32768u) {
+          const uint32_t n = fin_bytes - off < 32768u ? fin_bytes - off : 32768u;
+          bulk_load_1d(reinterpret_cast<unsigned char*>(tiles) + off,
+                       reinterpret_cast<const unsigned char*>(a.partials) + off, n, fin_bar);
+        }
+      }
+      mbar_wait(fin_bar, 0);
+      part = tiles;
+    }
     for (int j = tid; j < ps; j += blockDim.x) {
       // fixed order over CTAs in eight interleaved chains (still one fixed
-      // association), so that sixteen independent L2 loads are in flight per thread
+      // association), so that sixteen independent loads are in flight per thread
       double v8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       int b = 0;
+      if (staged) {
 #pragma unroll 2
-      for (; b + 7 < nb; b += 8) {
+        for (; b + 7 < nb; b += 8) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v8[u] += __ldcg(a.partials + (size_t)(b + u) * ps + j);
+          for (int u = 0; u < 8; ++u) v8[u] += part[(size_t)(b + u) * ps + j];
+        }
+        for (; b < nb; ++b) v8[0] += part[(size_t)b * ps + j];
+      } else {
+#pragma unroll 2
+        for (; b + 7 < nb; b += 8) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v8[u] += __ldcg(part + (size_t)(b + u) * ps + j);
+        }
+        for (; b < nb; ++b) v8[0] += __ldcg(part + (size_t)b * ps + j);
       }
-      for (; b < nb; ++b) v8[0] += __ldcg(a.partials + (size_t)b * ps + j);
       double v = ((v8[0] + v8[1]) + (v8[2] + v8[3])) + ((v8[4] + v8[5]) + (v8[6] + v8[7]));
       if (j == SMC_OUT_LOGP) v += a.c0;
       // packed output: header, d_beta[K], d_cuts[ncuts]
@@ -475,6 +540,7 @@ __global__ void __launch_bounds__(256, 1)
         a.out[kHdr + a.out_K_total + (j - kHdr - CW)] = v;
     }
     __syncthreads();  // (uniform: s_last is shared) every store to out is issued
+    stamp(6);
     if (tid == 0) {
       *a.counter = 0;  // ready for the next launch on this stream
       if (a.done_flag) {
@@ -582,11 +648,27 @@ static size_t fused_smem_bytes(const GlmCall& c, const FusedArgs& a, bool dx) {
                                                          : 0)
          + (size_t)2 * a.S * R * 8
          + (size_t)4 * R * 8 + (size_t)2 * R * 4 + 8 + 2 * kStages * 8
-         + (size_t)4 * a.G * 8 + (size_t)a.S * a.G * kHdr * 8
+         + (size_t)4 * a.G * 8 + 8 + (size_t)a.S * a.G * kHdr * 8
          + (c.family == kOrdered && a.S > 1 ? (size_t)2 * R * 8 : 0);  // dv_s
 }
 
 constexpr size_t kMaxDynamicSmem = 227 * 1024;  // opt-in limit per CTA on sm_100
+
+#ifdef SMC_FUSED_TRACE
+static void dump_fused_trace(const FusedArgs& a, int grid) {
+  if (const char* f = getenv("SMC_FUSED_TRACE_FILE")) {
+    std::vector<unsigned long long> h(8 * 1024);
+    cudaDeviceSynchronize();
+    cudaMemcpy(h.data(), a.trace, 8 * 8 * 1024, cudaMemcpyDeviceToHost);
+    if (FILE* fp = fopen(f, "wb")) {
+      long long g = grid;
+      fwrite(&g, 8, 1, fp);
+      fwrite(h.data(), 8, 8 * 1024, fp);
+      fclose(fp);
+    }
+  }
+}
+#endif
 
 int launch_glm_fused(const GlmCall& c) {
   Context& cx = ctx();
@@ -625,6 +707,13 @@ int launch_glm_fused(const GlmCall& c) {
   a.pstride = kHdr + CW + ((a.ncuts + 3) & ~3);
   int grid = cx.sm_count;
   if (grid > a.ntiles) grid = a.ntiles;
+  // the fewest CTAs that finish in the same number of tile rounds: 157 tiles are two
+  // rounds on 148 CTAs and on 79, and the last CTA then sums half as many partials
+  // (the tail of a small evaluation, nothing for a large one)
+  if (grid > 0) {
+    const int rounds = (a.ntiles + grid - 1) / grid;
+    grid = (a.ntiles + rounds - 1) / rounds;
+  }
   if (int rc = ensure_partials(sizeof(double) * (size_t)grid * a.pstride)) return rc;
   a.partials = cx.partials;
   a.counter = cx.counter;
@@ -635,6 +724,11 @@ int launch_glm_fused(const GlmCall& c) {
   a.out_K_total = c.out_K_total > 0 ? c.out_K_total : a.K;
   a.out_skip_header = c.out_skip_header ? 1 : 0;
   cx.flag_armed = c.done_flag != nullptr;
+#ifdef SMC_FUSED_TRACE
+  static unsigned long long* trace_dev = nullptr;
+  if (!trace_dev) cudaMalloc(&trace_dev, 8 * 8 * 1024);
+  a.trace = trace_dev;
+#endif
 
   CUtensorMap tmap, tmap_dx;
   if (int rc = get_tmap(x, R, CW, &tmap)) return rc;
@@ -654,6 +748,13 @@ int launch_glm_fused(const GlmCall& c) {
     return fail(SMC_ERR_UNSUPPORTED, "reduction scratch exceeds the tile ring");
   const int threads = 32 * a.S * a.G;
 
+#ifdef SMC_FUSED_TRACE
+  struct Dump {
+    const FusedArgs& a;
+    int grid;
+    ~Dump() { dump_fused_trace(a, grid); }
+  } dump{a, grid};
+#endif
   switch (c.family) {
     case kNormal:
       return launch_t<kNormal>(tmap, tmap_dx, a, grid, threads, smem);

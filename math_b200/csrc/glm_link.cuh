@@ -13,6 +13,9 @@ namespace smc {
 constexpr int kHdr = SMC_OUT_HEADER;
 
 struct FusedArgs {
+#ifdef SMC_FUSED_TRACE
+  unsigned long long* trace;  // profiling build: per-CTA phase stamps (glm_fused.cu)
+#endif
   int64_t N;
   int K, S, G, ntiles;
   const double* x;  // general path only (the fused kernel goes through TMA)

@@ -49,9 +49,18 @@ struct NcclApi {
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool load() {
     if (lib) return true;
+    // One NCCL per process: a second copy under the same soname would shadow the one
+    // another component (a framework that bundles its own, newer NCCL) links against.
+    // So: the copy that is already loaded, else the one SMC_NCCL_LIB names (the
+    // Python binding points it at the bundled copy), else the system's.
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL | RTLD_NOLOAD);
+    if (!lib) {
+      const char* named = getenv("SMC_NCCL_LIB");
+      if (named && named[0]) lib = dlopen(named, RTLD_NOW | RTLD_LOCAL);
+    }
     for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
-      lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
       if (lib) break;
+      lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
     }
     if (!lib) return false;
 #define SMC_NCCL_SYM(field, sym) \

@@ -52,6 +52,16 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map,
       "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
+// Bulk copy global -> shared (1-D, 16-byte aligned, a multiple of 16 bytes), completion
+// on an mbarrier.
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes,
+                                             uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, "
+      "[%3];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
 // TMA: 2-D tiled bulk tensor store shared -> global (bulk async-group
 // completion); elements outside the tensor are clipped.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1,

@@ -24,10 +24,31 @@ def synchronize():
     check(lib().smc_synchronize())
 
 
+def _point_at_bundled_nccl():
+    """A Python process usually carries an NCCL of its own (the nvidia-nccl wheel
+    torch links against).  The library must bind THAT copy, not the system's older
+    one under the same soname -- whichever is loaded first is the one the whole
+    process gets -- so SMC_NCCL_LIB names it before the first sharded call."""
+    import os
+    if os.environ.get("SMC_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (spec.submodule_search_locations if spec else []):
+            path = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(path):
+                os.environ["SMC_NCCL_LIB"] = path
+                return
+    except Exception:
+        pass
+
+
 def shard_init(n_shards=0, devices=None):
     """Set up the shard set for row-sharded matrices: one shard per GPU (all visible
     ones by default); `devices` may repeat an id to put several shards on one GPU
     (host-side reduction then; for tests on a single-GPU box)."""
+    _point_at_bundled_nccl()
     arr = None
     if devices is not None:
         n_shards = len(devices)
