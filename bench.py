@@ -615,6 +615,12 @@ def run_ours(args):
 
 
 def main():
+    # stdout carries ONE JSON line: whatever libraries print there while the run is set up
+    # (NCCL's version banner, for one) goes to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     args = parse()
     if args.impl == "reference":
         run_reference(args)

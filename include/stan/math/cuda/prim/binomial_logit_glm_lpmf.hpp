@@ -15,7 +15,8 @@ namespace math {
 
 template <bool propto, typename T_n, typename T_N, typename T_x,
           typename T_alpha, typename T_beta,
-          require_cuda_design_matrix_t<T_x>* = nullptr>
+          require_cuda_design_matrix_t<T_x>* = nullptr,
+          require_not_t<is_cuda_operand<T_beta>>* = nullptr>
 return_type_t<T_x, T_alpha, T_beta> binomial_logit_glm_lpmf(
     const T_n& n, const T_N& N, const T_x& x, const T_alpha& alpha,
     const T_beta& beta) {
@@ -88,6 +89,19 @@ return_type_t<T_x, T_alpha, T_beta> binomial_logit_glm_lpmf(
                                N_attributes);
   }
   return ops_partials.build(logp);
+}
+
+/** beta on the device (the OpenCL overloads' signature): K doubles come to the host,
+ * see cuda_internal::host_param. */
+template <bool propto, typename T_n, typename T_N, typename T_x,
+          typename T_alpha, typename T_beta,
+          require_cuda_design_matrix_t<T_x>* = nullptr,
+          require_t<is_cuda_operand<T_beta>>* = nullptr>
+return_type_t<T_x, T_alpha, T_beta> binomial_logit_glm_lpmf(
+    const T_n& n, const T_N& N, const T_x& x, const T_alpha& alpha,
+    const T_beta& beta) {
+  return binomial_logit_glm_lpmf<propto>(n, N, x, alpha,
+                                         cuda_internal::host_param(beta));
 }
 
 // The propto = false forwarding overload is the reference's own

@@ -75,6 +75,17 @@ return_type_t<T_x, T_alpha, T_beta> categorical_logit_glm_lpmf(
   return ops_partials.build(logp);
 }
 
+/** alpha and / or beta on the device (the OpenCL overloads' signature): C + K C doubles
+ * come to the host, see cuda_internal::host_param. */
+template <bool propto, typename T_y, typename T_x, typename T_alpha,
+          typename T_beta, require_cuda_design_matrix_t<T_x>* = nullptr,
+          require_any_t<is_cuda_operand<T_alpha>, is_cuda_operand<T_beta>>* = nullptr>
+return_type_t<T_x, T_alpha, T_beta> categorical_logit_glm_lpmf(
+    const T_y& y, const T_x& x, const T_alpha& alpha, const T_beta& beta) {
+  return categorical_logit_glm_lpmf<propto>(y, x, cuda_internal::host_param(alpha),
+                                            cuda_internal::host_param_matrix(beta));
+}
+
 // The propto = false forwarding overload is the reference's own
 // (prim/prob/categorical_logit_glm_lpmf.hpp L197-201).
 

@@ -28,6 +28,7 @@
 #include <stan/math/prim/fun/to_ref.hpp>
 #include <stan/math/prim/fun/value_of.hpp>
 #include <stan/math/prim/functor/partials_propagator.hpp>
+#include <stan/math/rev/core/reverse_pass_callback.hpp>
 
 #include <type_traits>
 #include <vector>
@@ -77,6 +78,53 @@ inline Eigen::VectorXd host_values(const T& v) {
     const auto& val = value_of(ref);
     return Eigen::VectorXd(as_column_vector_or_scalar(val));
   }
+}
+
+/** A small parameter (beta, cut points, the categorical alpha / beta) that the caller
+ * keeps on the device -- the OpenCL overloads take every argument as matrix_cl, and a
+ * model compiled for that backend passes them so
+ * (opencl/prim/bernoulli_logit_glm_lpmf.hpp L52-58) -- comes to the host, K doubles;
+ * for a device var the adjoints flow back through one upload + axpy in the reverse
+ * sweep.  Host arguments pass through untouched. */
+template <typename T, require_not_t<is_cuda_operand<T>>* = nullptr>
+inline const T& host_param(const T& v) {
+  return v;
+}
+inline Eigen::VectorXd host_param(const matrix_cuda<double>& v) {
+  const Eigen::MatrixXd m = from_matrix_cuda<Eigen::MatrixXd>(v);
+  return Eigen::VectorXd(Eigen::Map<const Eigen::VectorXd>(m.data(), m.size()));
+}
+inline var_value<Eigen::VectorXd> host_param(const var_value<matrix_cuda<double>>& a) {
+  const Eigen::MatrixXd m = from_matrix_cuda<Eigen::MatrixXd>(a.val().to_matrix_cuda());
+  var_value<Eigen::VectorXd> res(
+      Eigen::VectorXd(Eigen::Map<const Eigen::VectorXd>(m.data(), m.size())));
+  reverse_pass_callback([a, res]() mutable {
+    if (res.size() == 0) {
+      return;
+    }
+    // (column-major: the flat host adjoint has the layout of the n x 1 or 1 x n device
+    // matrix it is added to)
+    matrix_cuda<double> g
+        = matrix_cuda<double>::like_handle(a.adj().handle(), a.rows(), a.cols());
+    const Eigen::VectorXd g_host = res.adj();
+    check_cuda_status("host_param(var)",
+                      smc_matrix_upload(g.handle(), g_host.data(), a.rows()));
+    check_cuda_status("host_param(var)",
+                      smc_matrix_axpy(a.adj().handle(), 1.0, g.handle()));
+  });
+  return res;
+}
+/** The same for a matrix-valued parameter (the categorical K x C beta). */
+template <typename T, require_not_t<is_cuda_operand<T>>* = nullptr>
+inline const T& host_param_matrix(const T& v) {
+  return v;
+}
+inline Eigen::MatrixXd host_param_matrix(const matrix_cuda<double>& v) {
+  return from_matrix_cuda<Eigen::MatrixXd>(v);
+}
+inline var_value<Eigen::MatrixXd> host_param_matrix(
+    const var_value<matrix_cuda<double>>& a) {
+  return from_matrix_cuda<Eigen::MatrixXd>(a);
 }
 
 /** A per-row operand (y, vector alpha / sigma / phi) as the C ABI wants it:

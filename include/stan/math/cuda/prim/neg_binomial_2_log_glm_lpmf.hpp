@@ -13,7 +13,8 @@ namespace math {
 
 template <bool propto, typename T_y, typename T_x, typename T_alpha,
           typename T_beta, typename T_precision,
-          require_cuda_design_matrix_t<T_x>* = nullptr>
+          require_cuda_design_matrix_t<T_x>* = nullptr,
+          require_not_t<is_cuda_operand<T_beta>>* = nullptr>
 return_type_t<T_x, T_alpha, T_beta, T_precision> neg_binomial_2_log_glm_lpmf(
     const T_y& y, const T_x& x, const T_alpha& alpha, const T_beta& beta,
     const T_precision& phi) {
@@ -98,6 +99,19 @@ return_type_t<T_x, T_alpha, T_beta, T_precision> neg_binomial_2_log_glm_lpmf(
     }
   }
   return ops_partials.build(logp);
+}
+
+/** beta on the device (the OpenCL overloads' signature): K doubles come to the host,
+ * see cuda_internal::host_param. */
+template <bool propto, typename T_y, typename T_x, typename T_alpha,
+          typename T_beta, typename T_precision,
+          require_cuda_design_matrix_t<T_x>* = nullptr,
+          require_t<is_cuda_operand<T_beta>>* = nullptr>
+return_type_t<T_x, T_alpha, T_beta, T_precision> neg_binomial_2_log_glm_lpmf(
+    const T_y& y, const T_x& x, const T_alpha& alpha, const T_beta& beta,
+    const T_precision& phi) {
+  return neg_binomial_2_log_glm_lpmf<propto>(y, x, alpha,
+                                             cuda_internal::host_param(beta), phi);
 }
 
 // The propto = false forwarding overload is the reference's own

@@ -11,7 +11,8 @@ namespace math {
 
 template <bool propto, typename T_y, typename T_x, typename T_alpha,
           typename T_beta, typename T_scale,
-          require_cuda_design_matrix_t<T_x>* = nullptr>
+          require_cuda_design_matrix_t<T_x>* = nullptr,
+          require_not_t<is_cuda_operand<T_beta>>* = nullptr>
 return_type_t<T_y, T_x, T_alpha, T_beta, T_scale> normal_id_glm_lpdf(
     const T_y& y, const T_x& x, const T_alpha& alpha, const T_beta& beta,
     const T_scale& sigma) {
@@ -94,6 +95,18 @@ return_type_t<T_y, T_x, T_alpha, T_beta, T_scale> normal_id_glm_lpdf(
     }
   }
   return ops_partials.build(logp);
+}
+
+/** beta on the device (the OpenCL overloads' signature): K doubles come to the host,
+ * see cuda_internal::host_param. */
+template <bool propto, typename T_y, typename T_x, typename T_alpha,
+          typename T_beta, typename T_scale,
+          require_cuda_design_matrix_t<T_x>* = nullptr,
+          require_t<is_cuda_operand<T_beta>>* = nullptr>
+return_type_t<T_y, T_x, T_alpha, T_beta, T_scale> normal_id_glm_lpdf(
+    const T_y& y, const T_x& x, const T_alpha& alpha, const T_beta& beta,
+    const T_scale& sigma) {
+  return normal_id_glm_lpdf<propto>(y, x, alpha, cuda_internal::host_param(beta), sigma);
 }
 
 // The propto = false forwarding overload is the reference's own

@@ -81,6 +81,17 @@ return_type_t<T_x, T_beta, T_cuts> ordered_logistic_glm_lpmf(
   return ops_partials.build(logp);
 }
 
+/** beta and / or the cut points on the device (the OpenCL overloads' signature): they
+ * come to the host, see cuda_internal::host_param. */
+template <bool propto, typename T_y, typename T_x, typename T_beta,
+          typename T_cuts, require_cuda_design_matrix_t<T_x>* = nullptr,
+          require_any_t<is_cuda_operand<T_beta>, is_cuda_operand<T_cuts>>* = nullptr>
+return_type_t<T_x, T_beta, T_cuts> ordered_logistic_glm_lpmf(
+    const T_y& y, const T_x& x, const T_beta& beta, const T_cuts& cuts) {
+  return ordered_logistic_glm_lpmf<propto>(y, x, cuda_internal::host_param(beta),
+                                           cuda_internal::host_param(cuts));
+}
+
 // The propto = false forwarding overload is the reference's own
 // (prim/prob/ordered_logistic_glm_lpmf.hpp L212-216).
 

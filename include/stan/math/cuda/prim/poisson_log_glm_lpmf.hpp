@@ -13,7 +13,8 @@ namespace stan {
 namespace math {
 
 template <bool propto, typename T_y, typename T_x, typename T_alpha,
-          typename T_beta, require_cuda_design_matrix_t<T_x>* = nullptr>
+          typename T_beta, require_cuda_design_matrix_t<T_x>* = nullptr,
+          require_not_t<is_cuda_operand<T_beta>>* = nullptr>
 return_type_t<T_x, T_alpha, T_beta> poisson_log_glm_lpmf(
     const T_y& y, const T_x& x, const T_alpha& alpha, const T_beta& beta) {
   using namespace cuda_internal;  // NOLINT
@@ -78,6 +79,16 @@ return_type_t<T_x, T_alpha, T_beta> poisson_log_glm_lpmf(
     store_host_partial<T_beta>(partials<2>(ops_partials), d_beta.data(), K);
   }
   return ops_partials.build(logp);
+}
+
+/** beta on the device (the OpenCL overloads' signature): K doubles come to the host,
+ * see cuda_internal::host_param. */
+template <bool propto, typename T_y, typename T_x, typename T_alpha,
+          typename T_beta, require_cuda_design_matrix_t<T_x>* = nullptr,
+          require_t<is_cuda_operand<T_beta>>* = nullptr>
+return_type_t<T_x, T_alpha, T_beta> poisson_log_glm_lpmf(
+    const T_y& y, const T_x& x, const T_alpha& alpha, const T_beta& beta) {
+  return poisson_log_glm_lpmf<propto>(y, x, alpha, cuda_internal::host_param(beta));
 }
 
 // The propto = false forwarding overload is the reference's own

@@ -305,14 +305,31 @@ int smc_poisson_log_glm(const smc_matrix* y, int y_scalar, const smc_matrix* x,
   c.d_x = d_x;
   const double* o;
   if (int rc = run_sync(c, SMC_OUT_HEADER + (int)K, &o)) return rc;
-  if (!std::isfinite(o[SMC_OUT_SUM_D])) {  // L120-124
+  // Lazy checks.  prim (L120-124) runs them when the sum of the derivatives is not
+  // finite; the reference's device overload also when any linear predictor is
+  // (opencl/prim/poisson_log_glm_lpmf.hpp L97-98, L112-121: a -inf entry of x throws there
+  // and returns -inf in prim).  A device backend is held to the device overload's tests
+  // (test/unit/math/opencl/rev/poisson_log_glm_lpmf_test.cpp L83-85): its rule.
+  if (!std::isfinite(o[SMC_OUT_SUM_D]) || o[SMC_OUT_NONFINITE] > 0) {
     if (!host_all_finite(beta, K))
       return fail(SMC_ERR_DOMAIN, "%s: Weight vector is not finite", fn);
     if (!alpha_vec && !std::isfinite(alpha))
       return fail(SMC_ERR_DOMAIN, "%s: Intercept is not finite", fn);
-    if (o[SMC_OUT_NONFINITE] > 0)
+    std::vector<double> keep(o, o + SMC_OUT_HEADER + K);  // (the scans reuse the result buffer)
+    int ok = 1;
+    if (alpha_vec) {
+      if (int rc = smc_matrix_all_finite(alpha_vec, &ok)) return rc;
+      if (!ok) return fail(SMC_ERR_DOMAIN, "%s: Intercept is not finite", fn);
+    }
+    if (int rc = smc_matrix_all_finite(x, &ok)) return rc;
+    if (!ok || !std::isfinite(keep[SMC_OUT_SUM_D]))
       return fail(SMC_ERR_DOMAIN,
                   "%s: Matrix of independent variables is not finite", fn);
+    *logp = keep[SMC_OUT_LOGP];
+    if (d_alpha && (flags & SMC_VAR_ALPHA)) *d_alpha = keep[SMC_OUT_SUM_D];
+    if (d_beta && (flags & SMC_VAR_BETA))
+      memcpy(d_beta, keep.data() + SMC_OUT_HEADER, sizeof(double) * K);
+    return SMC_OK;
   }
   *logp = o[SMC_OUT_LOGP];
   if (d_alpha && (flags & SMC_VAR_ALPHA)) *d_alpha = o[SMC_OUT_SUM_D];

@@ -31,7 +31,7 @@ TEST(CudaPoissonLogGLM, error_checking) {
   x << -12, 46, -42, 24, 25, 27;
   x_size1 << -12, 46, -42, 24;
   x_size2 << -12, 46, -42;
-  x_value << -12, 46, -42, 24, 25, NAN;  // prim returns -inf (no throw) for -INFINITY here
+  x_value << -12, 46, -42, 24, 25, NAN;  // (-INFINITY: prim returns -inf, the device overloads throw: ref_poisson_log_glm_lpmf_test)
   VectorXd beta(M), beta_size(M + 1), beta_value(M);
   beta << 0.3, 2;
   beta_size << 0.3, 2, 0.4;

@@ -20,10 +20,17 @@ TESTS = ["matrix_cuda_test", "bernoulli_logit_glm_test", "poisson_log_glm_test",
          "ordered_logistic_glm_test", "categorical_logit_glm_test",
          "binomial_logit_glm_test", "unfused_lpmf_test", "reduce_sum_threads_test",
          "sharded_glm_test"]
+# The reference's OWN device tests of the GLMs (test/unit/math/opencl/rev/*_glm_*_test.cpp
+# with test/unit/math/opencl/util.hpp), compiled unmodified against tests/cpp/ref_shim:
+# error_checking, small_simple, broadcast_*, zero_instances, zero_attributes, big, ...
+REF_TESTS = ["ref_bernoulli_logit_glm_lpmf_test", "ref_poisson_log_glm_lpmf_test",
+             "ref_normal_id_glm_lpdf_test", "ref_neg_binomial_2_log_glm_lpmf_test",
+             "ref_ordered_logistic_glm_lpmf_test", "ref_categorical_logit_glm_lpmf_test",
+             "ref_binomial_logit_glm_lpmf_test"]
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", TESTS)
+@pytest.mark.parametrize("name", TESTS + REF_TESTS)
 def test_cpp_backend(gpu, name):
     exe = os.path.join(BUILD, name)
     if not os.path.exists(exe):
