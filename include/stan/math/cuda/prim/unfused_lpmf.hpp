@@ -38,6 +38,31 @@ inline smc_matrix* dvec_handle(Edge& edge_partials) {
     return nullptr;
   }
 }
+/** A scalar parameter next to a device random variable (the reference's device overloads
+ * broadcast it, e.g. opencl/prim/bernoulli_logit_lpmf.hpp L25-86 with a scalar theta):
+ * n copies on the device; a var collects the sum of the adjoints in the reverse sweep. */
+template <typename T, require_arithmetic_t<T>* = nullptr>
+inline matrix_cuda<double> broadcast_to_device(T v, int64_t n) {
+  matrix_cuda<double> m(n, 1);
+  if (n > 0) {
+    check_cuda_status("broadcast_to_device", smc_matrix_zero(m.handle()));
+    check_cuda_status("broadcast_to_device",
+                      smc_matrix_add_scalar(m.handle(), static_cast<double>(v)));
+  }
+  return m;
+}
+inline var_value<matrix_cuda<double>> broadcast_to_device(const var& v, int64_t n) {
+  var_value<matrix_cuda<double>> res(broadcast_to_device(v.val(), n));
+  reverse_pass_callback([v, res]() mutable {
+    double sum = 0;
+    if (res.size() > 0) {
+      check_cuda_status("broadcast_to_device(var)",
+                        smc_vector_sum(res.adj().handle(), &sum));
+    }
+    v.adj() += sum;
+  });
+  return res;
+}
 }  // namespace cuda_internal
 
 template <bool propto, typename T_n, typename T_prob,
@@ -61,6 +86,15 @@ return_type_t<T_prob> bernoulli_logit_lpmf(const T_n& n, const T_prob& theta) {
     return 0.0;
   }
   return ops_partials.build(logp);
+}
+
+/** device n, scalar theta */
+template <bool propto, typename T_n, typename T_prob,
+          require_t<is_cuda_operand<T_n>>* = nullptr,
+          require_stan_scalar_t<T_prob>* = nullptr>
+return_type_t<T_prob> bernoulli_logit_lpmf(const T_n& n, const T_prob& theta) {
+  return bernoulli_logit_lpmf<propto>(
+      n, cuda_internal::broadcast_to_device(theta, n.size()));
 }
 
 template <bool propto, typename T_n, typename T_log_rate,
@@ -88,6 +122,15 @@ return_type_t<T_log_rate> poisson_log_lpmf(const T_n& n, const T_log_rate& alpha
     return 0.0;
   }
   return ops_partials.build(logp);
+}
+
+/** device n, scalar log rate */
+template <bool propto, typename T_n, typename T_log_rate,
+          require_t<is_cuda_operand<T_n>>* = nullptr,
+          require_stan_scalar_t<T_log_rate>* = nullptr>
+return_type_t<T_log_rate> poisson_log_lpmf(const T_n& n, const T_log_rate& alpha) {
+  return poisson_log_lpmf<propto>(n,
+                                  cuda_internal::broadcast_to_device(alpha, n.size()));
 }
 
 /** phi: an arithmetic or var scalar (a per-row phi goes through the GLM entry). */
