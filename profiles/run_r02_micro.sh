@@ -1,7 +1,7 @@
 #!/bin/bash
-# gpurun (1 GPU): FP64 pipe microbenchmark + config 1 timing + quick parity of the fused kernel
-mkdir -p gpurun_out
-profiles/micro/fp64_pipes | tee gpurun_out/r02_fp64_pipes.jsonl
-python -m pytest tests/test_glm_gpu.py tests/test_golden_gpu.py -x -q 2>&1 | tail -3
-tests/cpp/_build/glm_bench 10000 100 2000 100 normal | tee gpurun_out/r02_cpp_cfg1_new.json
-python profiles/time_configs.py 1 2 5b > gpurun_out/r02_configs_new.jsonl 2> gpurun_out/configs.err; cat gpurun_out/r02_configs_new.jsonl
+# gpurun (1 GPU): the FP64 microbenchmarks behind DESIGN.md section 4.3 (compiled on the box)
+mkdir -p gpurun_out /tmp/micro
+for m in fp64_pipes dmma_loop dmma_epilogue; do
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/micro/$m profiles/micro/$m.cu || exit 1
+  timeout 120 /tmp/micro/$m | tee gpurun_out/r02_$m.jsonl
+done
