@@ -16,6 +16,7 @@
 // The prim templates are switched off for device operands by the reference's own
 // kernel-expression trait (see matrix_cuda.hpp).
 #include <stan/math/cuda/prim/glm_common.hpp>
+#include <stan/math/cuda/prim/normal_id_glm_lpdf.hpp>
 
 namespace stan {
 namespace math {
@@ -133,20 +134,28 @@ return_type_t<T_log_rate> poisson_log_lpmf(const T_n& n, const T_log_rate& alpha
                                   cuda_internal::broadcast_to_device(alpha, n.size()));
 }
 
-/** phi: an arithmetic or var scalar (a per-row phi goes through the GLM entry). */
+/** eta on the device; phi an arithmetic / var scalar or a device vector (data or var). */
 template <bool propto, typename T_n, typename T_log_location, typename T_precision,
           require_t<is_cuda_operand<T_log_location>>* = nullptr,
-          require_stan_scalar_t<T_precision>* = nullptr>
+          require_any_t<is_stan_scalar<T_precision>,
+                        is_cuda_operand<T_precision>>* = nullptr>
 return_type_t<T_log_location, T_precision> neg_binomial_2_log_lpmf(
     const T_n& n, const T_log_location& eta, const T_precision& phi) {
   using namespace cuda_internal;  // NOLINT
   static constexpr const char* function = "neg_binomial_2_log_lpmf(CUDA)";
   check_rv_size(function, n, eta);
+  if (!is_stan_scalar<T_precision>::value) {
+    check_size_match(function, "Size of ", "Log location parameter", operand_size(eta),
+                     "size of ", "Precision parameter", operand_size(phi));
+  }
   row_operand<int, T_n> n_op(n);
   if (n_op.handle() == nullptr) {
     check_nonnegative(function, "Failures variable", n_op.scalar());
   }
-  check_positive_finite(function, "Precision parameter", value_of(phi));
+  row_operand<double, T_precision> phi_op(phi);
+  if (phi_op.handle() == nullptr) {  // (a device phi is checked by the call)
+    check_positive_finite(function, "Precision parameter", phi_op.scalar());
+  }
   if (eta.size() == 0 || operand_size(n) == 0) {
     return 0.0;
   }
@@ -157,17 +166,35 @@ return_type_t<T_log_location, T_precision> neg_binomial_2_log_lpmf(
                          | var_flag<T_precision>(SMC_VAR_AUX);
   check_cuda_status(
       function,
-      smc_neg_binomial_2_log_lpmf(n_op.handle(), n_op.scalar(), x_handle(eta), nullptr,
-                                  value_of(phi), flags, &logp,
+      smc_neg_binomial_2_log_lpmf(n_op.handle(), n_op.scalar(), x_handle(eta),
+                                  phi_op.handle(), phi_op.scalar(), flags, &logp,
                                   dvec_handle<T_log_location>(partials<0>(ops_partials)),
-                                  &d_phi, nullptr));
+                                  &d_phi,
+                                  dvec_handle<T_precision>(partials<1>(ops_partials))));
   if (!include_summand<propto, T_log_location, T_precision>::value) {
     return 0.0;
   }
-  if constexpr (!is_constant_all<T_precision>::value) {
+  if constexpr (!is_constant_all<T_precision>::value
+                && is_stan_scalar<T_precision>::value) {
     partials<1>(ops_partials)[0] = d_phi;
   }
   return ops_partials.build(logp);
+}
+
+/** scalar eta next to a device n and / or a device phi: broadcast on the device */
+template <bool propto, typename T_n, typename T_log_location, typename T_precision,
+          require_stan_scalar_t<T_log_location>* = nullptr,
+          require_any_t<is_cuda_operand<T_n>, is_cuda_operand<T_precision>>* = nullptr>
+return_type_t<T_log_location, T_precision> neg_binomial_2_log_lpmf(
+    const T_n& n, const T_log_location& eta, const T_precision& phi) {
+  using namespace cuda_internal;  // NOLINT
+  int64_t size = 0;
+  if constexpr (is_cuda_operand<T_n>::value) {
+    size = n.size();
+  } else {
+    size = phi.size();
+  }
+  return neg_binomial_2_log_lpmf<propto>(n, broadcast_to_device(eta, size), phi);
 }
 
 /** c: one host cut-point vector (Eigen column vector of double or var). */
@@ -250,6 +277,23 @@ return_type_t<T_y, T_loc, T_scale> normal_lpdf(T_y&& y, T_loc&& mu, T_scale&& si
     partials<2>(ops_partials)[0] = d_sigma;
   }
   return ops_partials.build(logp);
+}
+
+/** normal_lpdf with a per-row scale on the device (data or autodiff): the linear-
+ * regression GLM with no attributes -- normal_id_glm_lpdf(y | x = N x 0, alpha = mu,
+ * beta = [], sigma) is the same density, partials and constant terms
+ * (prim/prob/normal_id_glm_lpdf.hpp L122-213 with x beta = 0), so the fused entry takes it. */
+template <bool propto, typename T_y, typename T_loc, typename T_scale,
+          require_t<is_cuda_operand<T_scale>>* = nullptr>
+return_type_t<T_y, T_loc, T_scale> normal_lpdf(const T_y& y, const T_loc& mu,
+                                              const T_scale& sigma) {
+  if (!is_stan_scalar<T_y>::value) {
+    check_size_match("normal_lpdf(CUDA)", "Size of ", "Random variable",
+                     cuda_internal::operand_size(y), "size of ", "Scale parameter",
+                     sigma.size());
+  }
+  const matrix_cuda<double> no_attributes(sigma.size(), 0);
+  return normal_id_glm_lpdf<propto>(y, no_attributes, mu, Eigen::VectorXd(0), sigma);
 }
 
 /** categorical_logit_lpmf with one row of log odds per outcome: `lin` is an N x C

@@ -28,7 +28,8 @@ REF_TESTS = ["ref_bernoulli_logit_glm_lpmf_test", "ref_poisson_log_glm_lpmf_test
              "ref_ordered_logistic_glm_lpmf_test", "ref_categorical_logit_glm_lpmf_test",
              "ref_binomial_logit_glm_lpmf_test",
              # the un-fused densities whose every device signature the backend has
-             "ref_bernoulli_logit_lpmf_test", "ref_poisson_log_lpmf_test"]
+             "ref_bernoulli_logit_lpmf_test", "ref_poisson_log_lpmf_test",
+             "ref_neg_binomial_2_log_lpmf_test", "ref_normal_lpdf_test"]
 
 
 @pytest.mark.gpu
