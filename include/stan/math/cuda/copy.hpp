@@ -23,6 +23,14 @@ inline matrix_cuda<T> to_matrix_cuda(const std::vector<T>& v) {
   return matrix_cuda<T>(v);
 }
 
+/** std::vector of Eigen vectors -> device matrix, one vector per column
+ * (opencl/copy.hpp L57-60 through matrix_cl.hpp L246-268). */
+template <typename Vec, require_std_vector_vt<is_eigen, Vec>* = nullptr,
+          require_st_arithmetic<Vec>* = nullptr>
+inline matrix_cuda<scalar_type_t<Vec>> to_matrix_cuda(const Vec& v) {
+  return matrix_cuda<scalar_type_t<Vec>>(v);
+}
+
 /** Scalar -> 1 x 1 device matrix (matrix_cl.hpp L349-356). */
 template <typename T, require_arithmetic_t<T>* = nullptr>
 inline matrix_cuda<T> to_matrix_cuda(T v) {
@@ -124,8 +132,22 @@ inline Eigen::Matrix<T, Eigen::Dynamic, Eigen::Dynamic> from_matrix_cuda(
   return from_matrix_cuda<Eigen::Matrix<T, Eigen::Dynamic, Eigen::Dynamic>>(src);
 }
 
+/** Device -> std::vector of Eigen vectors, one per column (opencl/copy.hpp L213-224). */
+template <typename T_dst, typename T,
+          require_std_vector_vt<is_eigen_vector, T_dst>* = nullptr>
+inline T_dst from_matrix_cuda(const matrix_cuda<T>& src) {
+  Eigen::Matrix<T, Eigen::Dynamic, Eigen::Dynamic> tmp = from_matrix_cuda(src);
+  T_dst dst;
+  dst.reserve(src.cols());
+  for (int64_t i = 0; i < src.cols(); ++i) {
+    dst.emplace_back(tmp.col(i));
+  }
+  return dst;
+}
+
 /** Device -> std::vector (column-major order). */
-template <typename T_dst, typename T, require_std_vector_t<T_dst>* = nullptr>
+template <typename T_dst, typename T, require_std_vector_t<T_dst>* = nullptr,
+          require_not_std_vector_vt<is_eigen_vector, T_dst>* = nullptr>
 inline T_dst from_matrix_cuda(const matrix_cuda<T>& src) {
   Eigen::Matrix<T, Eigen::Dynamic, Eigen::Dynamic> tmp = from_matrix_cuda(src);
   return T_dst(tmp.data(), tmp.data() + tmp.size());

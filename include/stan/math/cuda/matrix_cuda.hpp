@@ -88,6 +88,28 @@ class matrix_cuda : public matrix_cuda_base {
     }
   }
 
+  /** Uploads a std::vector of Eigen vectors of equal length, one per COLUMN
+   * (matrix_cl.hpp L246-268): the form in which per-outcome cut points reach
+   * ordered_logistic_lpmf. */
+  template <typename Vec, require_std_vector_vt<is_eigen, Vec>* = nullptr,
+            require_st_same<Vec, T>* = nullptr>
+  explicit matrix_cuda(const Vec& A) {
+    const int64_t rows = A.empty() ? 0 : static_cast<int64_t>(A[0].size());
+    const int64_t cols = static_cast<int64_t>(A.size());
+    Eigen::Matrix<T, Eigen::Dynamic, Eigen::Dynamic> cm(rows, cols);
+    for (int64_t i = 0; i < cols; ++i) {
+      check_size_match("matrix constructor", "input rows", A[i].size(),
+                       "matrix_cuda rows", rows);
+      cm.col(i) = Eigen::Map<const Eigen::Matrix<T, Eigen::Dynamic, 1>>(
+          A[i].eval().data(), rows);
+    }
+    allocate(rows, cols);
+    if (cm.size() > 0) {
+      check_cuda_status("matrix_cuda(std::vector<Eigen>)",
+                        smc_matrix_upload(handle_, cm.data(), rows));
+    }
+  }
+
   ~matrix_cuda() { release(); }
 
   matrix_cuda& operator=(const matrix_cuda& o) {
@@ -120,6 +142,14 @@ class matrix_cuda : public matrix_cuda_base {
     matrix_cuda m;
     if (o.handle_) {
       check_cuda_status("matrix_cuda::view", smc_matrix_view(o.handle_, &m.handle_));
+    }
+    return m;
+  }
+  /** Non-owning view of the matrix behind a C-ABI handle (which must outlive it). */
+  static matrix_cuda view_of_handle(const smc_matrix* h) {
+    matrix_cuda m;
+    if (h) {
+      check_cuda_status("matrix_cuda::view", smc_matrix_view(h, &m.handle_));
     }
     return m;
   }

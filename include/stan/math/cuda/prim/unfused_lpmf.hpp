@@ -232,6 +232,44 @@ return_type_t<T_loc, T_cut> ordered_logistic_lpmf(const T_y& y, const T_loc& lam
   return ops_partials.build(logp);
 }
 
+/** cuts on the device (data or autodiff), as every argument of the OpenCL overload is
+ * (opencl/prim/ordered_logistic_lpmf.hpp L68-160): a (C-1) x 1 matrix is one cut-point
+ * vector for all outcomes, a (C-1) x N matrix holds one cut-point vector per outcome in
+ * its columns -- prim's std::vector<Eigen::VectorXd> form (prim L72-200), which
+ * to_matrix_cuda uploads that way.  The partial of the cut points is written on the
+ * device, straight into the edge. */
+template <bool propto, typename T_y, typename T_loc, typename T_cut,
+          require_t<is_cuda_operand<T_loc>>* = nullptr,
+          require_t<is_cuda_operand<T_cut>>* = nullptr>
+return_type_t<T_loc, T_cut> ordered_logistic_lpmf(const T_y& y, const T_loc& lambda,
+                                                  const T_cut& cuts) {
+  using namespace cuda_internal;  // NOLINT
+  static constexpr const char* function = "ordered_logistic_lpmf(CUDA)";
+  check_rv_size(function, y, lambda);
+  const int64_t N = lambda.size();
+  if (cuts.cols() > 1) {
+    check_size_match(function, "Length of location variables ", N,
+                     "Number of cutpoint vectors ", cuts.cols());
+  }
+  row_operand<int, T_y> y_op(y);
+  auto ops_partials = make_partials_propagator(lambda, cuts);
+  double logp = 0;
+  const unsigned flags = (propto ? SMC_PROPTO : 0u) | var_flag<T_loc>(SMC_VAR_ALPHA)
+                         | var_flag<T_cut>(SMC_VAR_AUX);
+  if (N == 0 || cuts.cols() == 0) {
+    return 0.0;
+  }
+  check_cuda_status(function,
+                    smc_ordered_logistic_lpmf_rows(
+                        y_op.handle(), y_op.scalar(), x_handle(lambda), x_handle(cuts),
+                        flags, &logp, dvec_handle<T_loc>(partials<0>(ops_partials)),
+                        dvec_handle<T_cut>(partials<1>(ops_partials))));
+  if (!include_summand<propto, T_loc, T_cut>::value) {
+    return 0.0;
+  }
+  return ops_partials.build(logp);
+}
+
 /** normal_lpdf(y | mu, sigma) with y and / or mu on the device (data or autodiff)
  * and a host scalar sigma: prim/prob/normal_lpdf.hpp L41-104. */
 template <bool propto, typename T_y, typename T_loc, typename T_scale,

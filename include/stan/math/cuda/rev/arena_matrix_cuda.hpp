@@ -84,6 +84,31 @@ class arena_matrix_cuda : public matrix_cuda_base {
   int64_t size() const noexcept { return rows() * cols(); }
   smc_matrix* handle() const noexcept { return h_; }
 
+  /** Overwrites the contents with those of a device matrix of the same shape
+   * (`x.adj() = expr` of the OpenCL backend, opencl/rev/arena_matrix_cl.hpp L60-75). */
+  arena_matrix_cuda& operator=(const matrix_cuda<T>& m) {
+    check_size_match("arena_matrix_cuda::operator=", "rows", rows(), "rows of the source",
+                     m.rows());
+    check_size_match("arena_matrix_cuda::operator=", "cols", cols(), "cols of the source",
+                     m.cols());
+    if (h_ && size() > 0) {
+      check_cuda_status("arena_matrix_cuda::operator=", smc_matrix_copy(h_, m.handle()));
+    }
+    return *this;
+  }
+  /** this += m on the device (`a.adj() += to_matrix_cl(...)`, opencl/rev/copy.hpp L118-125). */
+  arena_matrix_cuda& operator+=(const matrix_cuda<T>& m) {
+    check_size_match("arena_matrix_cuda::operator+=", "rows", rows(),
+                     "rows of the source", m.rows());
+    check_size_match("arena_matrix_cuda::operator+=", "cols", cols(),
+                     "cols of the source", m.cols());
+    if (h_ && size() > 0) {
+      check_cuda_status("arena_matrix_cuda::operator+=",
+                        smc_matrix_axpy(h_, 1.0, m.handle()));
+    }
+    return *this;
+  }
+
   /** Copy to an owning matrix (device-to-device). */
   matrix_cuda<T> to_matrix_cuda() const {
     matrix_cuda<T> out = matrix_cuda<T>::like_handle(h_, rows(), cols());

@@ -68,6 +68,36 @@ inline var_value<matrix_cuda<double>> to_matrix_cuda(const std::vector<var>& src
   return res;
 }
 
+/** std::vector of Eigen vectors of var -> device var, one vector per column
+ * (opencl/rev/copy.hpp L88-104): per-outcome cut points of ordered_logistic_lpmf. */
+template <typename T, require_eigen_vt<is_var, T>* = nullptr>
+inline var_value<matrix_cuda<double>> to_matrix_cuda(const std::vector<T>& src) {
+  using arena_vec = arena_t<plain_type_t<T>>;
+  const size_t n = src.size();
+  // (arena storage, trivially destructible: captured by the callback)
+  arena_vec* src_arena = ChainableStack::instance_->memalloc_.alloc_array<arena_vec>(n);
+  std::vector<Eigen::VectorXd> vals;
+  vals.reserve(n);
+  for (size_t i = 0; i < n; ++i) {
+    new (src_arena + i) arena_vec(src[i]);
+    vals.emplace_back(Eigen::Map<const Eigen::VectorXd>(src_arena[i].val().eval().data(),
+                                                        src_arena[i].size()));
+  }
+  var_value<matrix_cuda<double>> res(to_matrix_cuda(vals));
+  reverse_pass_callback([src_arena, n, res]() mutable {
+    if (res.size() == 0) {
+      return;
+    }
+    const Eigen::MatrixXd adj
+        = from_matrix_cuda<Eigen::MatrixXd>(res.adj().to_matrix_cuda());
+    for (size_t i = 0; i < n; ++i) {
+      src_arena[i].adj() += Eigen::Map<const plain_type_t<decltype(src_arena[i].adj())>>(
+          adj.data() + adj.rows() * i, src_arena[i].rows(), src_arena[i].cols());
+    }
+  });
+  return res;
+}
+
 /** Values of a device var as an owning device matrix (copy). */
 inline matrix_cuda<double> value_of(const var_value<matrix_cuda<double>>& a) {
   return a.val().to_matrix_cuda();

@@ -37,6 +37,19 @@ class vari_value<matrix_cuda<double>, void> : public vari_base {
                                                    val_.cols())) {
     ChainableStack::instance_->var_nochain_stack_.push_back(this);
   }
+  /** The constructor rev/core/callback_vari.hpp L16-19 calls, so that the reference's
+   * own make_callback_var(device value, functor) yields a device vari whose chain()
+   * runs the functor: `stacked` puts it on the chaining stack. */
+  vari_value(matrix_cuda<double>&& v, bool stacked)
+      : val_(std::move(v)),
+        adj_(arena_matrix_cuda<double>::zeros_like(val_.handle(), val_.rows(),
+                                                   val_.cols())) {
+    if (stacked) {
+      ChainableStack::instance_->var_stack_.push_back(this);
+    } else {
+      ChainableStack::instance_->var_nochain_stack_.push_back(this);
+    }
+  }
   /** Views the value buffer: `v` must outlive the reverse sweep. */
   explicit vari_value(const matrix_cuda<double>& v)
       : val_(arena_matrix_cuda<double>::view(v)),

@@ -393,6 +393,18 @@ int smc_ordered_logistic_lpmf(const smc_matrix* y, int y_scalar,
                               const smc_matrix* lambda, const double* cuts,
                               int64_t ncuts, unsigned flags, double* logp,
                               smc_matrix* d_lambda, double* d_cuts);
+/* The same density with ONE CUT-POINT VECTOR PER OUTCOME (prim/prob/
+ * ordered_logistic_lpmf.hpp L72-200 called with a std::vector of cut vectors;
+ * opencl/prim/ordered_logistic_lpmf.hpp L68-160): `cuts` is a (C-1) x N f64 device
+ * matrix, column i the cut points of outcome i (a (C-1) x 1 matrix is the one-vector
+ * form above with the cut points resident).  SMC_VAR_AUX: the partial of the cut
+ * points is written whole into `d_cuts`, a device matrix with the shape of `cuts`.
+ * Columns that are not strictly increasing or whose first / last cut is not finite
+ * are SMC_ERR_DOMAIN (check_ordered / check_finite, L112-122). */
+int smc_ordered_logistic_lpmf_rows(const smc_matrix* y, int y_scalar,
+                                   const smc_matrix* lambda, const smc_matrix* cuts,
+                                   unsigned flags, double* logp, smc_matrix* d_lambda,
+                                   smc_matrix* d_cuts);
 /* prim/prob/categorical_logit_lpmf.hpp L16-32, one row of log odds per outcome:
  * `lin` is an N x C f64 device matrix and the result is
  * sum_i categorical_logit_lpmf(y_i, lin.row(i)^T) -- what a model that adds terms

@@ -110,6 +110,7 @@ SIGNATURES = {
     "smc_neg_binomial_2_log_lpmf": (_I, [_P, _I, _P, _P, _D, _U, _DP, _P, _DP, _P]),
     "smc_normal_lpdf": (_I, [_P, _D, _P, _D, _D, _U, _DP, _P, _DP, _P, _DP, _DP]),
     "smc_ordered_logistic_lpmf": (_I, [_P, _I, _P, _DP, _I64, _U, _DP, _P, _DP]),
+    "smc_ordered_logistic_lpmf_rows": (_I, [_P, _I, _P, _P, _U, _DP, _P, _P]),
     "smc_categorical_logit_lpmf": (_I, [_P, _I, _P, _U, _DP, _P]),
     "smc_categorical_logit_glm_device": (_I, [_P, _I, _P, _P, _I64, _U, _P, _P]),
     "smc_glm_eval_device": (_I, [_I, _P, _D, _P, _P, _D, _P, _D, _P, _I64, _U, _P,

@@ -16,6 +16,7 @@
 #include <limits>
 #include <vector>
 
+#include "glm_link.cuh"
 #include "smc_internal.h"
 
 using namespace smc;
@@ -438,6 +439,193 @@ int smc_ordered_logistic_lpmf(const smc_matrix* y, int y_scalar,
   *logp = o[SMC_OUT_LOGP];
   if (d_cuts && (flags & SMC_VAR_AUX))
     memcpy(d_cuts, o + SMC_OUT_HEADER, sizeof(double) * ncuts);
+  return SMC_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+// ordered_logistic_lpmf with ONE CUT-POINT VECTOR PER OUTCOME (prim/prob/
+// ordered_logistic_lpmf.hpp L72-200 with a std::vector of cut vectors,
+// opencl/prim/ordered_logistic_lpmf.hpp L68-160 with an (C-1) x N matrix_cl): row i
+// reads column i of `cuts`.  Lane = outcome.  The row's two cut points, the value
+// term and d1 / d2 follow the GLM link (glm_link.cuh, kOrdered) expression by
+// expression, with the class constants evaluated per row; the (C-1) x N partial of the
+// cut points is written whole (two non-zero entries per column, L189-198), so it
+// needs no zero fill.  The column checks of L112-122 (ordered, first and last cut
+// finite) ride along: bit 0 not ordered, bit 1 last cut not finite, bit 2 first.
+constexpr int kOrdThreads = 256;
+constexpr int kCutsUnordered = 1, kCutsLastInf = 2, kCutsFirstInf = 4;
+
+__global__ void __launch_bounds__(kOrdThreads)
+    ordered_rows_kernel(int64_t N, int ncuts, const int* __restrict__ y, int y_scalar,
+                        const double* __restrict__ lambda,
+                        const double* __restrict__ cuts, int64_t ld_cuts,
+                        double* __restrict__ d_lambda, double* __restrict__ d_cuts,
+                        int64_t ld_dcuts, int check_only,
+                        double* __restrict__ block_partials, int* __restrict__ flags_out) {
+  __shared__ double sh[kOrdThreads / 32];
+  double lp = 0.0;
+  int bad = 0;
+  const int C = ncuts + 1;
+  for (int64_t row = blockIdx.x * (int64_t)kOrdThreads + threadIdx.x; row < N;
+       row += (int64_t)gridDim.x * kOrdThreads) {
+    const double* col = cuts + row * ld_cuts;
+    double prev = col[0];
+    if (!isfinite(prev)) bad |= kCutsFirstInf;
+    if (prev != prev) bad |= kCutsUnordered;  // check_ordered rejects a NaN
+    for (int j = 1; j < ncuts; ++j) {
+      const double cur = col[j];
+      if (!(cur > prev)) bad |= kCutsUnordered;
+      prev = cur;
+    }
+    if (C > 2 && !isfinite(prev)) bad |= kCutsLastInf;
+    if (check_only) continue;
+    const int c = y ? y[row] : y_scalar;
+    double ce[4];
+    ordered_class_entry(col, ncuts, c, ce);
+    const double loc = lambda[row];
+    const double cut2 = loc - ce[1], cut1 = loc - ce[0];
+    const double e1 = exp_nonpos(-fabs(cut1)), e2 = exp_nonpos(-fabs(cut2));
+    const double d1 = div_or_zero(cut2 > 0.0 ? e2 : 1.0, 1.0 + e2) - ce[2];
+    const double d2 = ce[3] - div_or_zero(cut1 > 0.0 ? e1 : 1.0, 1.0 + e1);
+    if (d_lambda) d_lambda[row] = d1 - d2;
+    if (d_cuts) {
+      double* dc = d_cuts + row * ld_dcuts;
+      for (int j = 0; j < ncuts; ++j) dc[j] = j == c - 1 ? d2 : (j == c - 2 ? -d1 : 0.0);
+    }
+    const double A = (cut1 > 0.0 ? -cut1 : 0.0) - log1p_or_zero(e1);
+    const double B = (cut2 <= 0.0 ? cut2 : 0.0) - log1p_or_zero(e2);
+    if (c == 1)
+      lp += A;
+    else if (c == C)
+      lp += B;
+    else
+      lp += B + log1m_exp(cut1 - cut2) + A;
+  }
+  // fixed-order block sum: butterfly inside the warp, warp totals in index order
+#pragma unroll
+  for (int o = 16; o; o >>= 1) lp += __shfl_xor_sync(0xffffffffu, lp, o);
+  bad = __reduce_or_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0) {
+    sh[threadIdx.x >> 5] = lp;
+    if (bad) atomicOr(flags_out, bad);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kOrdThreads / 32; ++w) t += sh[w];
+    block_partials[blockIdx.x] = t;
+  }
+}
+
+__global__ void ordered_rows_final_kernel(const double* __restrict__ block_partials,
+                                          int nblocks, double* __restrict__ out) {
+  double v = 0.0;
+  for (int b = 0; b < nblocks; ++b) v += block_partials[b];
+  *out = v;
+}
+
+}  // namespace
+
+extern "C" {
+
+int smc_ordered_logistic_lpmf_rows(const smc_matrix* y, int y_scalar,
+                                   const smc_matrix* lambda, const smc_matrix* cuts,
+                                   unsigned flags, double* logp, smc_matrix* d_lambda,
+                                   smc_matrix* d_cuts) {
+  static const char* fn = "ordered_logistic_lpmf";
+  if (int rc = ensure_ctx()) return rc;
+  int64_t N;
+  if (int rc = theta_shapes(fn, lambda, y, nullptr, d_lambda, nullptr, &N)) return rc;
+  if (!logp || !cuts || cuts->dtype != SMC_F64)
+    return fail(SMC_ERR_INVALID_ARGUMENT, "%s: cuts must be an f64 device matrix", fn);
+  for (const smc_matrix* m : {y, lambda, cuts, (const smc_matrix*)d_lambda,
+                              (const smc_matrix*)d_cuts})
+    if (is_sharded(m))
+      return fail(SMC_ERR_UNSUPPORTED, "%s: per-outcome cut points are not sharded", fn);
+  const int64_t ncuts = cuts->rows, M = cuts->cols;
+  const bool var_cuts = flags & SMC_VAR_AUX;
+  if (var_cuts
+      && (!d_cuts || d_cuts->dtype != SMC_F64 || d_cuts->rows != ncuts || d_cuts->cols != M))
+    return fail(SMC_ERR_INVALID_ARGUMENT, "%s: d_cuts must have the shape of cuts", fn);
+  *logp = 0.0;
+  if (M > 1 && M != N)  // L102-105
+    return fail(SMC_ERR_INVALID_ARGUMENT,
+                "%s: Length of location variables (%lld) does not match the number of "
+                "cutpoint vectors (%lld)",
+                fn, (long long)N, (long long)M);
+  if (M <= 1 || ncuts == 0 || N == 0) {
+    // one cut-point vector for every outcome (or nothing to index): the host-cuts
+    // entry point, C - 1 doubles each way
+    std::vector<double> c_host((size_t)(ncuts > 0 ? ncuts : 1)), dc_host(c_host.size());
+    if (M == 1 && ncuts > 0)
+      if (int rc = smc_matrix_download(cuts, c_host.data(), ncuts)) return rc;
+    if (M == 0) {  // no cut-point vector at all: L107-109 after the finiteness check
+      if (N > 0) {
+        int ok = 1;
+        if (int rc = smc_matrix_all_finite(lambda, &ok)) return rc;
+        if (!ok) return fail(SMC_ERR_DOMAIN, "%s: Location parameter is not finite", fn);
+      }
+      return SMC_OK;
+    }
+    if (int rc = smc_ordered_logistic_lpmf(y, y_scalar, lambda, c_host.data(), ncuts, flags,
+                                           logp, d_lambda, dc_host.data()))
+      return rc;
+    if (var_cuts && ncuts > 0 && M > 0) {
+      if (M == 1) {
+        if (int rc = smc_matrix_upload(d_cuts, dc_host.data(), ncuts)) return rc;
+      } else {
+        if (int rc = smc_matrix_zero(d_cuts)) return rc;
+      }
+    }
+    return SMC_OK;
+  }
+  {  // check_finite(lambda), L106
+    int ok = 1;
+    if (int rc = smc_matrix_all_finite(lambda, &ok)) return rc;
+    if (!ok) return fail(SMC_ERR_DOMAIN, "%s: Location parameter is not finite", fn);
+  }
+  const int64_t C = ncuts + 1;
+  if (int rc = int_bounds(fn, y, y_scalar, 1, (int)C, true)) return rc;  // L111
+  for (const smc_matrix* m : {y, lambda, cuts})
+    if (int rc = realize(m)) return rc;
+  Context& cx = ctx();
+  const bool skip = (flags & SMC_PROPTO) && !(flags & (SMC_VAR_ALPHA | SMC_VAR_AUX));
+  int grid = (int)((N + kOrdThreads - 1) / kOrdThreads);
+  if (grid > cx.sm_count * 8) grid = cx.sm_count * 8;
+  if (int rc = ensure_scratch(sizeof(double) * (size_t)grid)) return rc;
+  if (int rc = ensure_out(4096)) return rc;
+  int* fl = reinterpret_cast<int*>(cx.out_host + 1);
+  *fl = 0;
+  cx.out_host[0] = 0.0;
+  double* dl = (flags & SMC_VAR_ALPHA) && d_lambda ? static_cast<double*>(d_lambda->data)
+                                                   : nullptr;
+  double* dc = var_cuts ? static_cast<double*>(d_cuts->data) : nullptr;
+  if (dl) {
+    d_lambda->zero_pending = false;
+    d_lambda->version++;
+  }
+  if (dc) {
+    d_cuts->zero_pending = false;
+    d_cuts->version++;
+  }
+  ordered_rows_kernel<<<grid, kOrdThreads, 0, cx.stream>>>(
+      N, (int)ncuts, y ? static_cast<const int*>(y->data) : nullptr, y_scalar,
+      static_cast<const double*>(lambda->data), static_cast<const double*>(cuts->data),
+      cuts->ld, dl, dc, dc ? d_cuts->ld : 0, skip ? 1 : 0, cx.scratch, fl);
+  SMC_CUDA(cudaGetLastError());
+  ordered_rows_final_kernel<<<1, 1, 0, cx.stream>>>(cx.scratch, grid, cx.out_host);
+  SMC_CUDA(cudaGetLastError());
+  cx.launches += 2;
+  SMC_CUDA(cudaStreamSynchronize(cx.stream));
+  const int bad = *fl;
+  if (bad & kCutsUnordered)  // L115
+    return fail(SMC_ERR_DOMAIN, "%s: Cut-points are not a valid ordered vector", fn);
+  if (bad & kCutsLastInf) return fail(SMC_ERR_DOMAIN, "%s: Final cut-point is not finite", fn);
+  if (bad & kCutsFirstInf) return fail(SMC_ERR_DOMAIN, "%s: First cut-point is not finite", fn);
+  if (!skip) *logp = cx.out_host[0];
   return SMC_OK;
 }
 

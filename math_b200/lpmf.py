@@ -142,6 +142,20 @@ def ordered_logistic_lpmf(y, lam, cuts, propto=False, theta_var=True, cuts_var=T
     return LpmfResult(logp.value, d, d_cuts if cuts_var else None)
 
 
+def ordered_logistic_lpmf_rows(y, lam, cuts, propto=False, theta_var=True, cuts_var=True):
+    """prim/prob/ordered_logistic_lpmf.hpp L72-200 with one cut-point vector per outcome:
+    ``cuts`` is a (C-1) x N (or (C-1) x 1) f64 MatrixCuda, column i the cut points of
+    outcome i; ``d_aux`` is the device partial with the shape of ``cuts``."""
+    yv, ys = _split(y, int, "y")
+    flags = _flags(propto, theta_var, cuts_var)
+    d = MatrixCuda(lam.size(), 1, np.float64) if theta_var else None
+    d_cuts = MatrixCuda(cuts.rows, cuts.cols, np.float64) if cuts_var else None
+    logp = C.c_double()
+    check(lib().smc_ordered_logistic_lpmf_rows(_h(yv), ys, lam.handle, cuts.handle, flags,
+                                               C.byref(logp), _h(d), _h(d_cuts)))
+    return LpmfResult(logp.value, d, d_cuts)
+
+
 def categorical_logit_lpmf(y, lin, propto=False, lin_var=True):
     """sum_i categorical_logit_lpmf(y_i | lin[i, :]) for an N x C device matrix of log
     odds (prim/prob/categorical_logit_lpmf.hpp L16-32, one row per outcome);
