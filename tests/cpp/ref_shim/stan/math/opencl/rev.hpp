@@ -35,6 +35,18 @@ inline auto from_matrix_cl(const T& x) {
   return from_matrix_cuda<T_dst>(x);
 }
 
+/** from_matrix_cl(x) without a destination type (opencl/copy.hpp L233-237,
+ * opencl/rev/copy.hpp L208-211). */
+template <typename T>
+inline auto from_matrix_cl(const T& x) {
+  return from_matrix_cuda(x);
+}
+/** opencl/kernel_generator/constant.hpp L110-114 (the one kernel-generator expression
+ * test/unit/math/opencl/rev/copy_test.cpp uses, to seed a device adjoint) */
+inline matrix_cuda<double> constant(double v, int rows, int cols) {
+  return matrix_cuda<double>(Eigen::MatrixXd::Constant(rows, cols, v));
+}
+
 }  // namespace math
 }  // namespace stan
 #endif

@@ -31,7 +31,9 @@ REF_TESTS = ["ref_bernoulli_logit_glm_lpmf_test", "ref_poisson_log_glm_lpmf_test
              "ref_bernoulli_logit_lpmf_test", "ref_poisson_log_lpmf_test",
              "ref_neg_binomial_2_log_lpmf_test", "ref_normal_lpdf_test",
              # incl. one cut-point vector per outcome (a (C-1) x N device matrix)
-             "ref_ordered_logistic_lpmf_test"]
+             "ref_ordered_logistic_lpmf_test",
+             # test/unit/math/opencl/rev/copy_test.cpp: host <-> device copies of every var form
+             "ref_copy_test"]
 
 
 @pytest.mark.gpu
