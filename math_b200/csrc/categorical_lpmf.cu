@@ -15,9 +15,11 @@
 // static row -> thread schedule, fixed-order block and grid sums, no atomics.
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <limits>
 
 #include "smc_internal.h"
+#include "tma_utils.cuh"
 
 using namespace smc;
 
@@ -202,6 +204,151 @@ __global__ void __launch_bounds__(kCatThreads)
   }
 }
 
+// The derivative-writing sweep as a TMA pipeline (sm_100a): every WARP owns a small
+// ring of shared-memory slots and streams its own row blocks through it -- no CTA-wide
+// barrier anywhere.  A slot holds a warp tile of RW = 32 / L consecutive rows by all C
+// classes, dense column-major as the tensor map delivers it (element (r, c) at
+// c * RW + r: the lanes of a warp read one contiguous 256-byte run per instruction,
+// conflict-free for L = 1, 2, 4).  Per tile: lane 0 has requested it `stages - 1`
+// iterations ago (cp.async.bulk.tensor, completion on the slot's mbarrier); the warp
+// takes the row max, overwrites the slot with exp(v - max), then with the partial
+// one-hot - softmax, and hands the slot to ONE bulk tensor store (rows >= N clipped
+// by the map); the slot of the previous tile, whose store has finished reading by
+// then, is refilled.  No per-element global address arithmetic, no LSU traffic to
+// HBM; lin is read once and d_lin written once.  L lanes share a row (class c
+// belongs to lane part c mod L), combined with shuffles as in the multilane kernel.
+// Same arithmetic per element as the kernels above: identical results.
+template <int L>
+__global__ void __launch_bounds__(512, 1)
+    cat_lpmf_tma_kernel(const __grid_constant__ CUtensorMap tm_in,
+                        const __grid_constant__ CUtensorMap tm_out, int64_t N, int C,
+                        int stages, int slot_doubles, const int* __restrict__ y,
+                        int y_scalar, double* __restrict__ partials) {
+  extern __shared__ __align__(128) unsigned char cat_tma_raw[];
+  constexpr int RW = 32 / L;
+  const int nwarps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = lane / RW, rl = lane - q * RW;
+  // [nwarps * stages] mbarriers, then the slots (128-byte aligned)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cat_tma_raw);
+  const int bar_bytes = ((nwarps * stages * 8) + 127) & ~127;
+  double* ring = reinterpret_cast<double*>(cat_tma_raw + bar_bytes)
+                 + (size_t)warp * stages * slot_doubles;
+  uint64_t* mybar = bars + warp * stages;
+  __shared__ double s_lp[16], s_bad[16];
+  if (lane == 0) {
+    for (int s = 0; s < stages; ++s) mbar_init(mybar + s, 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  const uint32_t tile_bytes = (uint32_t)(RW * C * 8);
+  const int64_t ntiles = (N + RW - 1) / RW;
+  const int64_t t0 = (int64_t)blockIdx.x * nwarps + warp;
+  const int64_t tstride = (int64_t)gridDim.x * nwarps;
+  const int64_t mine = t0 < ntiles ? (ntiles - t0 + tstride - 1) / tstride : 0;
+  const uint64_t pol = policy_evict_first();
+  if (lane == 0) {
+    for (int k = 0; k < stages - 1 && k < mine; ++k) {
+      mbar_expect_tx(mybar + k, tile_bytes);
+      tma_load_2d(ring + (size_t)k * slot_doubles, &tm_in,
+                  (int)((t0 + k * tstride) * RW), 0, mybar + k, pol);
+    }
+  }
+  double lp = 0.0, bad = 0.0;
+  int slot = 0;
+  uint32_t phase = 0;
+  // the outcome of the NEXT tile's row is requested one iteration ahead (its latency
+  // would otherwise sit in front of every tile's first pass)
+  const auto load_y = [&](int64_t k) {
+    const int64_t i = (t0 + k * tstride) * RW + rl;
+    return k < mine && i < N ? (y ? y[i] : y_scalar) - 1 : 0;
+  };
+  int yi_next = load_y(0);
+  for (int64_t k = 0; k < mine; ++k) {
+    const int64_t row0 = (t0 + k * tstride) * RW;
+    const int64_t i = row0 + rl;
+    const bool live = i < N;
+    const int yi = yi_next;
+    yi_next = load_y(k + 1);
+    double* tile = ring + (size_t)slot * slot_doubles + rl;
+    mbar_wait(mybar + slot, phase);
+    double m = -INFINITY, vy = 0.0, s = 0.0;
+    bool finite = true;
+#pragma unroll 8
+    for (int c = q; c < C; c += L) {
+      const double v = tile[c * RW];
+      finite = finite && isfinite(v);
+      m = fmax(m, v);
+      vy = c == yi ? v : vy;
+    }
+    if constexpr (L > 1) {
+#pragma unroll
+      for (int o = RW; o < 32; o <<= 1) {
+        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        vy += __shfl_xor_sync(0xffffffffu, vy, o);
+        finite = __shfl_xor_sync(0xffffffffu, (int)finite, o) && finite;
+      }
+    }
+#pragma unroll 4
+    for (int c = q; c < C; c += L) {
+      const double e = exp(tile[c * RW] - m);
+      tile[c * RW] = e;
+      s += e;
+    }
+    if constexpr (L > 1) {
+#pragma unroll
+      for (int o = RW; o < 32; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    }
+    const double inv = 1.0 / s;
+#pragma unroll 4
+    for (int c = q; c < C; c += L)
+      tile[c * RW] = (c == yi ? 1.0 : 0.0) - tile[c * RW] * inv;
+    if (live && q == 0) {
+      if (finite) lp += vy - (m + log(s));
+      else bad += 1.0;
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(&tm_out, (int)row0, 0, ring + (size_t)slot * slot_doubles, pol);
+      bulk_commit();
+      // the slot of tile k - 1 (read by its store, committed one iteration ago) takes
+      // tile k + stages - 1
+      const int64_t kn = k + stages - 1;
+      if (kn < mine) {
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        const int sn = slot == 0 ? stages - 1 : slot - 1;
+        mbar_expect_tx(mybar + sn, tile_bytes);
+        tma_load_2d(ring + (size_t)sn * slot_doubles, &tm_in,
+                    (int)((t0 + kn * tstride) * RW), 0, mybar + sn, pol);
+      }
+    }
+    __syncwarp();
+    if (++slot == stages) {
+      slot = 0;
+      phase ^= 1;
+    }
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  for (int o = 16; o; o >>= 1) {
+    lp += __shfl_xor_sync(0xffffffffu, lp, o);
+    bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if (lane == 0) {
+    s_lp[warp] = lp;
+    s_bad[warp] = bad;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < nwarps; ++w) {  // fixed order
+      lp += s_lp[w];
+      bad += s_bad[w];
+    }
+    partials[2 * (size_t)blockIdx.x] = lp;
+    partials[2 * (size_t)blockIdx.x + 1] = bad;
+  }
+}
+
 // out[0] = sum of the per-CTA log densities, out[1] = number of rows with a
 // non-finite entry; one warp, lane-strided partial sums combined in lane order.
 __global__ void cat_lpmf_final_kernel(const double* __restrict__ partials, int nblocks,
@@ -282,7 +429,57 @@ extern "C" int smc_categorical_logit_lpmf(const smc_matrix* y, int y_scalar,
   if (int rc = realize(y)) return rc;
   const double* l = static_cast<const double*>(lin->data);
   const int* yp = y ? static_cast<const int*>(y->data) : nullptr;
-  if (lanes) {
+  // With the derivative wanted and a layout TMA can address (16-byte aligned base and
+  // column stride, at most 128 classes): the per-warp TMA pipeline.
+  const auto tma_ok = [](const smc_matrix* m) {
+    return (reinterpret_cast<uintptr_t>(m->data) & 15) == 0 && (m->ld & 1) == 0;
+  };
+  static const int knob_mode = [] {
+    const char* e = getenv("SMC_CATL_TMA");  // A/B: 0 = the LSU kernels
+    return e ? atoi(e) : 1;
+  }();
+  if (lin_var && C <= 128 && knob_mode && N < (1ll << 31) - 64 && tma_ok(lin)
+      && tma_ok(d_lin) && get_encode()) {
+    // Lanes per row, warps and ring depth, measured on B200 (profiles/r02/
+    // r02_time_categorical_lpmf_tma.txt): the sweep is co-limited by the FP64 exp, so
+    // resident warps matter more than ring depth -- 12 warps x 2 slots beat 8 x 3 at
+    // C = 32 (1.03 vs 1.17 ms at N = 1e7); rows wider than 32 classes take two lanes
+    // per row (16-row tiles: 128-byte box rows; four lanes -- 64-byte box rows -- halve
+    // the TMA rate).  SMC_CATL_L / _W / _S override for A/B.
+    static const int knob_l = [] { const char* e = getenv("SMC_CATL_L"); return e ? atoi(e) : 0; }();
+    static const int knob_w = [] { const char* e = getenv("SMC_CATL_W"); return e ? atoi(e) : 0; }();
+    static const int knob_s = [] { const char* e = getenv("SMC_CATL_S"); return e ? atoi(e) : 0; }();
+    const int L = knob_l ? knob_l : C <= 32 ? 1 : 2;
+    const int RW = 32 / L;
+    const int slot_doubles = (int)(((size_t)RW * C * 8 + 127) / 128 * 16);
+    const size_t slot_bytes = (size_t)slot_doubles * 8, budget = 200 * 1024;
+    int S = knob_s ? knob_s : L == 1 ? (slot_bytes > 4096 ? 2 : 4) : 3;
+    int W = knob_w ? knob_w : L == 1 && slot_bytes > 4096 ? 12 : 16;
+    while (W > 1 && (size_t)W * S * slot_bytes > budget) --W;
+    const size_t smem_tma = (((size_t)W * S * 8 + 127) & ~(size_t)127)
+                            + (size_t)W * S * slot_doubles * 8;
+    CUtensorMap tm_in, tm_out;
+    if (encode_tmap_f64(&tm_in, lin->data, N, C, lin->ld, RW, (int)C) != CUDA_SUCCESS
+        || encode_tmap_f64(&tm_out, d_lin->data, N, C, d_lin->ld, RW, (int)C) != CUDA_SUCCESS)
+      return fail(SMC_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed", fn);
+    const int64_t ntiles = (N + RW - 1) / RW;
+    int g = (int)((ntiles + W - 1) / W);
+    if (g > c.sm_count) g = c.sm_count;
+    if (int rc = ensure_partials(sizeof(double) * 2 * (size_t)g)) return rc;
+    auto launch = [&](auto kern) -> int {
+      SMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem_tma));
+      kern<<<g, W * 32, smem_tma, c.stream>>>(tm_in, tm_out, N, (int)C, S, slot_doubles, yp,
+                                              y_scalar, c.partials);
+      return SMC_OK;
+    };
+    int rc = L == 1   ? launch(cat_lpmf_tma_kernel<1>)
+             : L == 2 ? launch(cat_lpmf_tma_kernel<2>)
+                      : launch(cat_lpmf_tma_kernel<4>);
+    if (rc) return rc;
+    SMC_CUDA(cudaGetLastError());
+    grid = g;
+  } else if (lanes) {
     static std::atomic<bool> attr_set[16];
     if (!attr_set[c.device & 15]) {
       SMC_CUDA(cudaFuncSetAttribute(cat_lpmf_kernel<true>,
