@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kCatThreads)
 // HBM; lin is read once and d_lin written once.  L lanes share a row (class c
 // belongs to lane part c mod L), combined with shuffles as in the multilane kernel.
 // Same arithmetic per element as the kernels above: identical results.
-template <int L>
+template <int L, bool kStore>
 __global__ void __launch_bounds__(512, 1)
     cat_lpmf_tma_kernel(const __grid_constant__ CUtensorMap tm_in,
                         const __grid_constant__ CUtensorMap tm_out, int64_t N, int C,
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(512, 1)
   const int64_t mine = t0 < ntiles ? (ntiles - t0 + tstride - 1) / tstride : 0;
   const uint64_t pol = policy_evict_first();
   if (lane == 0) {
-    for (int k = 0; k < stages - 1 && k < mine; ++k) {
+    for (int k = 0; k < stages - (kStore ? 1 : 0) && k < mine; ++k) {
       mbar_expect_tx(mybar + k, tile_bytes);
       tma_load_2d(ring + (size_t)k * slot_doubles, &tm_in,
                   (int)((t0 + k * tstride) * RW), 0, mybar + k, pol);
@@ -292,32 +292,37 @@ __global__ void __launch_bounds__(512, 1)
 #pragma unroll 4
     for (int c = q; c < C; c += L) {
       const double e = exp(tile[c * RW] - m);
-      tile[c * RW] = e;
+      if constexpr (kStore) tile[c * RW] = e;
       s += e;
     }
     if constexpr (L > 1) {
 #pragma unroll
       for (int o = RW; o < 32; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     }
-    const double inv = 1.0 / s;
+    if constexpr (kStore) {
+      const double inv = 1.0 / s;
 #pragma unroll 4
-    for (int c = q; c < C; c += L)
-      tile[c * RW] = (c == yi ? 1.0 : 0.0) - tile[c * RW] * inv;
+      for (int c = q; c < C; c += L)
+        tile[c * RW] = (c == yi ? 1.0 : 0.0) - tile[c * RW] * inv;
+    }
     if (live && q == 0) {
       if (finite) lp += vy - (m + log(s));
       else bad += 1.0;
     }
-    fence_proxy_async_smem();
+    if constexpr (kStore) fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      tma_store_2d(&tm_out, (int)row0, 0, ring + (size_t)slot * slot_doubles, pol);
-      bulk_commit();
-      // the slot of tile k - 1 (read by its store, committed one iteration ago) takes
-      // tile k + stages - 1
-      const int64_t kn = k + stages - 1;
+      if constexpr (kStore) {
+        tma_store_2d(&tm_out, (int)row0, 0, ring + (size_t)slot * slot_doubles, pol);
+        bulk_commit();
+      }
+      // kStore: the slot of tile k - 1 (read by its store, committed one iteration ago)
+      // takes tile k + stages - 1; data log odds (no store): this tile's own slot is free
+      // again and takes tile k + stages
+      const int64_t kn = kStore ? k + stages - 1 : k + stages;
       if (kn < mine) {
-        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        const int sn = slot == 0 ? stages - 1 : slot - 1;
+        if constexpr (kStore) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        const int sn = !kStore ? slot : slot == 0 ? stages - 1 : slot - 1;
         mbar_expect_tx(mybar + sn, tile_bytes);
         tma_load_2d(ring + (size_t)sn * slot_doubles, &tm_in,
                     (int)((t0 + kn * tstride) * RW), 0, mybar + sn, pol);
@@ -329,7 +334,7 @@ __global__ void __launch_bounds__(512, 1)
       phase ^= 1;
     }
   }
-  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (kStore && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   for (int o = 16; o; o >>= 1) {
     lp += __shfl_xor_sync(0xffffffffu, lp, o);
     bad += __shfl_xor_sync(0xffffffffu, bad, o);
@@ -402,13 +407,14 @@ extern "C" int smc_categorical_logit_lpmf(const smc_matrix* y, int y_scalar,
                   (long long)C);
   }
   Context& c = ctx();
-  // C <= 32: lane = row, C doubles of shared memory per thread (64 KB per CTA at
-  // C = 32, three CTAs per SM).  C <= 64 with the derivative wanted: two lanes per
-  // row, at most 32 doubles per thread again (N=4e6, C=64: 1.44 -> 1.12 ms).
-  // Everything else re-reads through L1/L2: without a derivative pass (data log
-  // odds) exp is evaluated once per entry anyway and staging is pure overhead
-  // (N=1e7, C=32: 0.80 vs 0.93 ms; N=4e6, C=64: 0.65 vs 0.81 ms), and four lanes per
-  // row (C <= 128) lose to it either way (1.76 vs 2.03 ms).
+  // The LSU kernels, for what the TMA pipeline below cannot take (a layout TMA cannot
+  // address, more than 128 classes).  C <= 32: lane = row, C doubles of shared memory
+  // per thread (64 KB per CTA at C = 32, three CTAs per SM).  C <= 64 with the
+  // derivative wanted: two lanes per row, at most 32 doubles per thread again (N=4e6,
+  // C=64: 1.44 -> 1.12 ms).  Everything else re-reads through L1/L2: without a
+  // derivative pass (data log odds) exp is evaluated once per entry anyway and staging
+  // is pure overhead (N=1e7, C=32: 0.80 vs 0.93 ms; N=4e6, C=64: 0.65 vs 0.81 ms), and
+  // four lanes per row (C <= 128) lose to it either way (1.76 vs 2.03 ms).
   const int lanes = !lin_var ? 0 : C <= 32 ? 1 : C <= 64 ? 2 : 0;
   const int threads = kCatThreads;
   const int64_t rows_per_cta = lanes ? threads / lanes : threads;
@@ -429,8 +435,9 @@ extern "C" int smc_categorical_logit_lpmf(const smc_matrix* y, int y_scalar,
   if (int rc = realize(y)) return rc;
   const double* l = static_cast<const double*>(lin->data);
   const int* yp = y ? static_cast<const int*>(y->data) : nullptr;
-  // With the derivative wanted and a layout TMA can address (16-byte aligned base and
-  // column stride, at most 128 classes): the per-warp TMA pipeline.
+  // A layout TMA can address (16-byte aligned base and column stride) and at most 128
+  // classes: the per-warp TMA pipeline, with the in-place store stream when the
+  // derivative is wanted.
   const auto tma_ok = [](const smc_matrix* m) {
     return (reinterpret_cast<uintptr_t>(m->data) & 15) == 0 && (m->ld & 1) == 0;
   };
@@ -438,8 +445,11 @@ extern "C" int smc_categorical_logit_lpmf(const smc_matrix* y, int y_scalar,
     const char* e = getenv("SMC_CATL_TMA");  // A/B: 0 = the LSU kernels
     return e ? atoi(e) : 1;
   }();
-  if (lin_var && C <= 128 && knob_mode && N < (1ll << 31) - 64 && tma_ok(lin)
-      && tma_ok(d_lin) && get_encode()) {
+  // (data log odds: only 16 <= C <= 32 gains, N=1e7 C=32 0.80 -> 0.76 ms; narrower and
+  // wider rows are faster through the re-reading LSU kernel,
+  // profiles/r02/r02_time_categorical_lpmf_tma4.txt)
+  if (C <= 128 && knob_mode && N < (1ll << 31) - 64 && tma_ok(lin)
+      && (lin_var ? tma_ok(d_lin) : (C >= 16 && C <= 32)) && get_encode()) {
     // Lanes per row, warps and ring depth, measured on B200 (profiles/r02/
     // r02_time_categorical_lpmf_tma.txt): the sweep is co-limited by the FP64 exp, so
     // resident warps matter more than ring depth -- 12 warps x 2 slots beat 8 x 3 at
@@ -460,8 +470,11 @@ extern "C" int smc_categorical_logit_lpmf(const smc_matrix* y, int y_scalar,
                             + (size_t)W * S * slot_doubles * 8;
     CUtensorMap tm_in, tm_out;
     if (encode_tmap_f64(&tm_in, lin->data, N, C, lin->ld, RW, (int)C) != CUDA_SUCCESS
-        || encode_tmap_f64(&tm_out, d_lin->data, N, C, d_lin->ld, RW, (int)C) != CUDA_SUCCESS)
+        || (lin_var
+            && encode_tmap_f64(&tm_out, d_lin->data, N, C, d_lin->ld, RW, (int)C)
+                   != CUDA_SUCCESS))
       return fail(SMC_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed", fn);
+    if (!lin_var) tm_out = tm_in;  // unused
     const int64_t ntiles = (N + RW - 1) / RW;
     int g = (int)((ntiles + W - 1) / W);
     if (g > c.sm_count) g = c.sm_count;
@@ -473,9 +486,12 @@ extern "C" int smc_categorical_logit_lpmf(const smc_matrix* y, int y_scalar,
                                               y_scalar, c.partials);
       return SMC_OK;
     };
-    int rc = L == 1   ? launch(cat_lpmf_tma_kernel<1>)
-             : L == 2 ? launch(cat_lpmf_tma_kernel<2>)
-                      : launch(cat_lpmf_tma_kernel<4>);
+    int rc = lin_var ? (L == 1   ? launch(cat_lpmf_tma_kernel<1, true>)
+                        : L == 2 ? launch(cat_lpmf_tma_kernel<2, true>)
+                                 : launch(cat_lpmf_tma_kernel<4, true>))
+                     : (L == 1   ? launch(cat_lpmf_tma_kernel<1, false>)
+                        : L == 2 ? launch(cat_lpmf_tma_kernel<2, false>)
+                                 : launch(cat_lpmf_tma_kernel<4, false>));
     if (rc) return rc;
     SMC_CUDA(cudaGetLastError());
     grid = g;

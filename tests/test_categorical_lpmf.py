@@ -132,6 +132,33 @@ def test_gpu_matches_oracle(gpu, N, C):
 
 
 @pytest.mark.gpu
+def test_gpu_lsu_kernels_still_match_oracle(gpu):
+    """The LSU kernels behind the TMA pipeline (layouts TMA cannot address) stay covered:
+    the same comparison in a fresh process with SMC_CATL_TMA=0."""
+    import subprocess, sys, os
+    code = r"""
+import sys
+sys.path.insert(0, %r)
+import numpy as np, math_b200 as mb
+from oracle import pyoracle as po
+mb.runtime.set_device(0)
+for N, C in ((4099, 9), (50021, 32), (2049, 64), (513, 128)):
+    rng = np.random.default_rng(N + C)
+    lin = np.asfortranarray(rng.standard_normal((N, C)) * 4.0)
+    y = rng.integers(1, C + 1, N).astype(np.int32)
+    o = po.categorical_logit_lpmf(y, lin)
+    r = mb.lpmf.categorical_logit_lpmf(mb.to_matrix_cuda(y), mb.to_matrix_cuda(lin))
+    assert abs(r.logp - o["logp"]) <= 1e-10 * abs(o["logp"]), (N, C)
+    d = mb.from_matrix_cuda(r.d_theta)
+    assert np.allclose(d, o["d_lin"], rtol=1e-9, atol=1e-13), (N, C)
+print("ok")
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, SMC_CATL_TMA="0"))
+    assert p.returncode == 0 and "ok" in p.stdout, p.stdout + p.stderr
+
+
+@pytest.mark.gpu
 def test_gpu_error_contract(gpu):
     mb = gpu
     lin = np.asfortranarray(np.random.default_rng(0).standard_normal((6, 3)))
