@@ -23,6 +23,11 @@
 
 using namespace smc;
 
+#ifndef SMC_CATL_UNROLL
+#define SMC_CATL_UNROLL 4
+#endif
+constexpr int kCatlUnroll = SMC_CATL_UNROLL;  // exp / partial loops of the TMA pipeline
+
 namespace {
 
 constexpr int kCatThreads = 256;
@@ -289,7 +294,7 @@ __global__ void __launch_bounds__(512, 1)
         finite = __shfl_xor_sync(0xffffffffu, (int)finite, o) && finite;
       }
     }
-#pragma unroll 4
+#pragma unroll kCatlUnroll
     for (int c = q; c < C; c += L) {
       const double e = exp(tile[c * RW] - m);
       if constexpr (kStore) tile[c * RW] = e;
@@ -301,7 +306,7 @@ __global__ void __launch_bounds__(512, 1)
     }
     if constexpr (kStore) {
       const double inv = 1.0 / s;
-#pragma unroll 4
+#pragma unroll kCatlUnroll
       for (int c = q; c < C; c += L)
         tile[c * RW] = (c == yi ? 1.0 : 0.0) - tile[c * RW] * inv;
     }

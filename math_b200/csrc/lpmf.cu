@@ -541,11 +541,14 @@ int smc_ordered_logistic_lpmf_rows(const smc_matrix* y, int y_scalar,
   if (int rc = theta_shapes(fn, lambda, y, nullptr, d_lambda, nullptr, &N)) return rc;
   if (!logp || !cuts || cuts->dtype != SMC_F64)
     return fail(SMC_ERR_INVALID_ARGUMENT, "%s: cuts must be an f64 device matrix", fn);
-  for (const smc_matrix* m : {y, lambda, cuts, (const smc_matrix*)d_lambda,
-                              (const smc_matrix*)d_cuts})
-    if (is_sharded(m))
-      return fail(SMC_ERR_UNSUPPORTED, "%s: per-outcome cut points are not sharded", fn);
+  if (is_sharded(cuts) || is_sharded(d_cuts))
+    return fail(SMC_ERR_UNSUPPORTED, "%s: the cut points are not sharded", fn);
   const int64_t ncuts = cuts->rows, M = cuts->cols;
+  if (M > 1 && ncuts > 0)  // (the one-vector form below takes a sharded lambda)
+    for (const smc_matrix* m : {y, lambda, (const smc_matrix*)d_lambda})
+      if (is_sharded(m))
+        return fail(SMC_ERR_UNSUPPORTED,
+                    "%s: per-outcome cut points with a sharded location vector", fn);
   const bool var_cuts = flags & SMC_VAR_AUX;
   if (var_cuts
       && (!d_cuts || d_cuts->dtype != SMC_F64 || d_cuts->rows != ncuts || d_cuts->cols != M))
