@@ -28,13 +28,8 @@ if ROOT not in sys.path:
 SEED = 12345
 
 
-def main():
-    G = int(sys.argv[1])
-    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-    warmup = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-    import math_b200 as mb
+def measure(mb, G, steps, warmup):
     rt = mb.runtime
-    rt.set_device(0)
     n = rt.shard_init(G)
     out = {"n_shards": n, "reduce": rt.shard_reduce_mode()}
 
@@ -98,6 +93,36 @@ def main():
                      "logp_per_row": r.logp / NS}
     del xs, ys
     rt.shard_shutdown()
+    return out
+
+
+def main():
+    G = int(sys.argv[1])
+    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+    warmup = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    child = len(sys.argv) > 4 and sys.argv[4] == "--only"
+    import math_b200 as mb
+    mb.runtime.set_device(0)
+    if child:  # one mode (whatever SMC_SHARD_REDUCE says), nothing else
+        print(json.dumps(measure(mb, G, steps, warmup)), flush=True)
+        return
+    # the default reduction (small results: every shard's kernel stores its packed result and
+    # a completion flag straight into pinned host memory, the host adds the G slots in shard
+    # order -- no collective on the evaluation path) ...
+    os.environ.pop("SMC_SHARD_REDUCE", None)
+    out = measure(mb, G, steps, warmup)
+    # ... then the same evaluations in a fresh process with SMC_SHARD_REDUCE=nccl: the packed
+    # result all-reduced in place over NCCL on the compute streams, one read-back
+    import subprocess
+    try:
+        p = subprocess.run([sys.executable, os.path.abspath(__file__), str(G), str(steps),
+                            str(warmup), "--only"], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, SMC_SHARD_REDUCE="nccl"))
+        lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+        out["nccl_all_reduce"] = json.loads(lines[-1]) if lines else {
+            "error": f"rc={p.returncode} " + (p.stderr or "")[-300:]}
+    except Exception as e:  # noqa: BLE001 -- the default mode's record stands on its own
+        out["nccl_all_reduce"] = {"error": repr(e)[:300]}
     print(json.dumps(out), flush=True)
 
 

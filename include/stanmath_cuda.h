@@ -179,9 +179,12 @@ int smc_matrix_fill_synthetic(smc_matrix* m, uint64_t seed, int64_t row0,
  * fill_synthetic, free) take a plain one, provided x and every per-row operand of a
  * call are sharded alike (smc_matrix_create_like).  One evaluation launches the fused
  * kernel on every GPU (small parameters travel as kernel arguments: that is the
- * broadcast), all-reduces the packed K + O(1) result in place over NCCL on the
- * compute streams, and reads it back once; N-vector partials and the N x K adjoint
- * of an autodiff x stay sharded.  This is the reference's scatter-once / broadcast-
+ * broadcast) and sums the packed results: K + O(1) doubles per GPU go straight from
+ * every kernel into its slot of one pinned host buffer, a completion flag behind them,
+ * and are added in shard order by the calling thread ("direct": no collective, no copy,
+ * no stream synchronise; bit-reproducible); larger results (the categorical K x C
+ * gradient) are all-reduced in place over NCCL on the compute streams and read back
+ * once.  N-vector partials and the N x K adjoint of an autodiff x stay sharded.  This is the reference's scatter-once / broadcast-
  * parameters / reduce pattern (prim/functor/mpi_parallel_call.hpp L332-392,
  * L408-449) in one process, beyond the one device of the OpenCL backend
  * (opencl/opencl_context.hpp L75-76).  Entry points without a sharded form
@@ -192,7 +195,9 @@ int smc_matrix_fill_synthetic(smc_matrix* m, uint64_t seed, int64_t row0,
  * or NULL for 0, 1, ...  NCCL is loaded at run time (libnccl.so.2).  If it is
  * missing, if SMC_SHARD_REDUCE=host is set, or if several shards share a GPU
  * (single-GPU tests of the sharded logic), the packed results are read back per
- * shard and summed on the host in shard order instead.  Re-initialising invalidates
+ * shard and summed on the host in shard order instead.  SMC_SHARD_REDUCE=nccl sends
+ * the small results through the NCCL all-reduce too (smc_shard_reduce_mode() tells:
+ * "direct+nccl", "direct+host", "nccl", "host").  Re-initialising invalidates
  * existing sharded matrices.  One sharded evaluation runs at a time per process. */
 int smc_shard_init(int n_shards, const int* devices);
 int smc_shard_count(int* n_shards);

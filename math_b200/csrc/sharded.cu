@@ -27,6 +27,7 @@
 #include <nccl.h>
 
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -83,6 +84,10 @@ struct Shard {
   ncclComm_t comm = nullptr;    // this shard's rank of the communicator
   double* out_dev = nullptr;    // packed result of the shard (all-reduced in place)
   size_t out_bytes = 0;
+  // "direct" reduction: where this shard's kernel stores its completion flag (mapped
+  // host memory, behind the shard's slot of the packed results) and the value to store
+  unsigned long long* done_flag = nullptr;
+  unsigned long long done_val = 0;
 };
 
 struct ShardComm {
@@ -90,7 +95,9 @@ struct ShardComm {
   std::vector<Shard*> shards;
   NcclApi nccl;
   bool use_nccl = false;
-  std::string reduce_mode;  // "nccl" | "host"
+  bool direct = false;      // small results: zero-copy slots + completion flags
+  std::string reduce_mode;  // "nccl" | "host" | "direct"
+  unsigned long long seq = 0;
   double* host_out = nullptr;  // pinned read-back buffer of the reduced result
   size_t host_bytes = 0;
   std::vector<double> host_sum;
@@ -221,9 +228,19 @@ int shards_timer_stop(double* ms_max, bool* any) {
 // G results are then summed -- NCCL all-reduce in place on those streams and one
 // read-back from shard 0, or (host mode) G results in mapped host memory added in
 // shard order -- and *out points at the reduced vector in host memory.
+// Direct mode (the default for results of at most kDirectMaxOut doubles, i.e. the
+// memory-bound families; SMC_SHARD_REDUCE=nccl / host force the collective / the copies):
+// the exchange is K + O(1) doubles per GPU, so instead of a collective every shard's
+// kernel stores its packed result STRAIGHT into its slot of one
+// pinned, mapped host buffer and its completion flag behind it (the mechanism of the
+// one-GPU synchronous call, capi.cu run_sync); the host polls the G flags and adds the
+// G slots in shard order -- bit-reproducible, no all-reduce, no copy, no stream
+// synchronise on the evaluation path.
+constexpr int kDirectMaxOut = 4096;
+
 static int run_over_shards(const smc_matrix* x, int n_out,
                            const std::function<int(int, Shard*, double*)>& launch,
-                           const double** out) {
+                           const double** out, bool allow_direct = false) {
   ShardComm& sc = comm();
   const int G = (int)x->shards.size();
   if ((int)sc.shards.size() != G)
@@ -232,6 +249,68 @@ static int run_over_shards(const smc_matrix* x, int n_out,
   std::lock_guard<std::mutex> lock(sc.mu);
   const size_t bytes = sizeof(double) * (size_t)n_out;
   int64_t launches = 0;
+  if (allow_direct && sc.direct && n_out <= kDirectMaxOut) {
+    const size_t stride = (size_t)n_out + 1;  // packed result + completion flag
+    const size_t need = sizeof(double) * stride * (size_t)(G + 1);
+    if (sc.host_bytes < need) {
+      if (int rc = synchronize_shards()) return rc;
+      if (sc.host_out) SMC_CUDA(cudaFreeHost(sc.host_out));
+      sc.host_out = nullptr;
+      const size_t want = need < 4096 ? 4096 : need;
+      SMC_CUDA(cudaHostAlloc(&sc.host_out, want, cudaHostAllocPortable | cudaHostAllocMapped));
+      sc.host_bytes = want;
+    }
+    const unsigned long long seq = ++sc.seq;
+    for (int g = 0; g < G; ++g) {
+      Shard* s = sc.shards[g];
+      ShardScope scope(s);
+      double* slot = sc.host_out + (size_t)(g + 1) * stride;
+      volatile unsigned long long* flag
+          = reinterpret_cast<volatile unsigned long long*>(slot + n_out);
+      *flag = 0;
+      s->done_flag = const_cast<unsigned long long*>(flag);
+      s->done_val = seq;
+      s->ctx.flag_armed = false;
+      const int64_t before = s->ctx.launches;
+      if (x->shards[g]->rows == 0) {  // more shards than rows: contributes zeros
+        memset(slot, 0, bytes);
+        *flag = seq;
+        s->ctx.flag_armed = true;
+      } else if (int rc = launch(g, s, slot)) {
+        s->done_flag = nullptr;
+        return rc;
+      }
+      s->done_flag = nullptr;
+      launches += s->ctx.launches - before;
+    }
+    // shard 0 finishes first more often than not (it was launched first): poll in order
+    // (the driver's own stream synchronise spins on the host too); a kernel that runs for
+    // longer than the spin budget is waited for on its stream
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int g = 0; g < G; ++g) {
+      Shard* s = sc.shards[g];
+      volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(
+          sc.host_out + (size_t)(g + 1) * stride + n_out);
+      bool done = false;
+      if (s->ctx.flag_armed) {
+        for (int spin = 0; !done; ++spin) {
+          done = *flag == seq;
+          if (!done && (spin & 63) == 63
+              && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(20))
+            break;
+        }
+      }
+      if (!done) SMC_CUDA(cudaStreamSynchronize(s->ctx.stream));
+    }
+    for (int j = 0; j < n_out; ++j) {
+      double v = 0.0;
+      for (int g = 0; g < G; ++g) v += sc.host_out[(size_t)(g + 1) * stride + j];
+      sc.host_out[j] = v;
+    }
+    own_ctx().launches += launches;
+    *out = sc.host_out;
+    return SMC_OK;
+  }
   const bool host_reduce = !sc.use_nccl;
   for (int g = 0; g < G; ++g) {
     Shard* s = sc.shards[g];
@@ -258,7 +337,7 @@ static int run_over_shards(const smc_matrix* x, int n_out,
     if (sc.host_out) SMC_CUDA(cudaFreeHost(sc.host_out));
     sc.host_out = nullptr;
     const size_t want = host_need < 4096 ? 4096 : host_need;
-    SMC_CUDA(cudaHostAlloc(&sc.host_out, want, cudaHostAllocPortable));
+    SMC_CUDA(cudaHostAlloc(&sc.host_out, want, cudaHostAllocPortable | cudaHostAllocMapped));
     sc.host_bytes = want;
   }
   if (host_reduce) {
@@ -314,7 +393,7 @@ int run_sharded(GlmCall& c, int n_out, const double** out) {
   if (int rc = check_partition(c.x, {c.y, c.alpha_vec, c.aux_vec, c.d_alpha_vec, c.d_aux_vec,
                                      c.d_y_vec, c.d_x}))
     return rc;
-  return run_over_shards(c.x, n_out, [&](int g, Shard*, double* out_g) {
+  return run_over_shards(c.x, n_out, [&](int g, Shard* sh, double* out_g) {
     GlmCall cg = c;
     auto pick = [g](const smc_matrix* m) {
       return m ? const_cast<smc_matrix*>(m->shards[g]) : nullptr;
@@ -327,11 +406,12 @@ int run_sharded(GlmCall& c, int n_out, const double** out) {
     cg.d_aux_vec = pick(c.d_aux_vec);
     cg.d_y_vec = pick(c.d_y_vec);
     cg.d_x = pick(c.d_x);
-    cg.done_flag = nullptr;
+    cg.done_flag = sh->done_flag;  // direct mode only, else NULL
+    cg.done_val = sh->done_val;
     cg.once_terms = g == 0;  // terms the reference adds once per call, not per row
     cg.out = out_g;
     return launch_glm(cg);
-  }, out);
+  }, out, /*allow_direct=*/true);
 }
 
 // The categorical GLM over the shards of x: beta (K x C) and alpha (C) are copied to
@@ -403,7 +483,11 @@ int smc_shard_init(int n_shards, const int* devices) {
                 distinct ? "libnccl.so.2 could not be loaded"
                          : "several shards share one GPU");
   }
-  sc.reduce_mode = sc.use_nccl ? "nccl" : "host";
+  // small results (the memory-bound families: K + O(1) doubles) go through the direct
+  // slots unless a mode is forced; larger ones (the categorical K x C gradient) through
+  // NCCL, or through the host when there is no NCCL
+  sc.direct = !mode || strcmp(mode, "direct") == 0;
+  sc.reduce_mode = std::string(sc.direct ? "direct+" : "") + (sc.use_nccl ? "nccl" : "host");
   Context& cur = ctx();
   if (cur.inited) cudaSetDevice(cur.device);
   return SMC_OK;

@@ -12,12 +12,24 @@ from tests.util import assert_grad, assert_logp, make_inputs
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[[0, 0, 0], None], ids=["3-shards-on-gpu0", "one-shard-per-gpu"])
-def shard_set(gpu, request):
-    devices = request.param
+@pytest.fixture(params=[([0, 0, 0], None), (None, None), ([0, 0, 0], "host"), (None, "nccl")],
+                ids=["3-shards-on-gpu0", "one-shard-per-gpu", "3-shards-on-gpu0-host-copies",
+                     "one-shard-per-gpu-nccl-only"])
+def shard_set(gpu, request, monkeypatch):
+    """Default: small results through the direct slots (every shard's kernel stores its packed
+    result and a completion flag straight into pinned host memory, the host adds the slots in
+    shard order), large ones through NCCL / the host; SMC_SHARD_REDUCE=host / nccl force the
+    read-back copies / the NCCL all-reduce for everything."""
+    devices, mode = request.param
     if devices is None and gpu.runtime.device_count() < 2:
         pytest.skip("one shard per GPU needs at least two GPUs")
+    if mode:
+        monkeypatch.setenv("SMC_SHARD_REDUCE", mode)
+    else:
+        monkeypatch.delenv("SMC_SHARD_REDUCE", raising=False)
     n = gpu.runtime.shard_init(devices=devices) if devices else gpu.runtime.shard_init(0)
+    got = gpu.runtime.shard_reduce_mode()
+    assert got == mode if mode else got.startswith("direct+")
     yield n
     gpu.runtime.shard_shutdown()
 
