@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 namespace smc {
 
@@ -150,10 +151,18 @@ inline CUresult encode_tmap_f64(CUtensorMap* map, const void* base, int64_t rows
   if (cols == 1) gstr[0] = (cuuint64_t)((rows + 1) & ~1ll) * 8;
   cuuint32_t box[2] = {(cuuint32_t)box_rows, (cuuint32_t)box_cols};
   cuuint32_t estr[2] = {1, 1};
+  // (A/B switch, read once: SMC_TMAP_L2PROMO = 0 none, 1 64 B, 2 128 B, 3 256 B -- default)
+  static const int promo = [] {
+    const char* e = getenv("SMC_TMAP_L2PROMO");
+    return e ? atoi(e) : 3;
+  }();
+  const CUtensorMapL2promotion pr = promo == 0   ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                    : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                    : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                 : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(base), gdim,
              gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+             CU_TENSOR_MAP_SWIZZLE_NONE, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
 }  // namespace smc
