@@ -4,6 +4,7 @@
 // lazy finiteness checks, and unpacking of the packed device result.
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -73,6 +74,14 @@ int check_dx(const char* fn, unsigned flags, const smc_matrix* x,
 }  // namespace
 
 namespace smc {
+int64_t spin_budget_us() {
+  static const int64_t us = [] {
+    const char* e = getenv("SMC_SPIN_US");
+    return e ? (int64_t)atoll(e) : (int64_t)60;
+  }();
+  return us;
+}
+
 // Runs the call with the packed result in pinned host memory; returns it.
 int run_sync(GlmCall& c, int n_out, const double** out) {
   if (is_sharded(c.x)) return run_sharded(c, n_out, out);
@@ -89,7 +98,9 @@ int run_sync(GlmCall& c, int n_out, const double** out) {
   // polling it for a short while saves the wake-up latency of a stream
   // synchronise, which is most of the call for small N (a whole evaluation of
   // N = 1e4, K = 100 takes ~10 us on the GPU).  Long kernels fall through to the
-  // blocking synchronise, so a waiting chain does not burn a core for milliseconds.
+  // blocking synchronise, so a waiting chain does not burn a core for milliseconds
+  // (SMC_SPIN_US, default 60; polling for the whole of a 2.9 ms evaluation was measured
+  // and buys nothing, profiles/r02/r02_spin_budget.txt).
   volatile unsigned long long* flag
       = reinterpret_cast<volatile unsigned long long*>(cx.out_host + n_out);
   const unsigned long long seq = ++cx.sync_seq;
@@ -104,7 +115,7 @@ int run_sync(GlmCall& c, int n_out, const double** out) {
     for (int spin = 0; !done; ++spin) {
       done = *flag == seq;
       if (!done && (spin & 63) == 63
-          && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(60))
+          && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(spin_budget_us()))
         break;
     }
   }

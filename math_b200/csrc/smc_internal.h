@@ -167,6 +167,9 @@ struct Knobs {
   int cat_ks;
 };
 const Knobs& knobs();
+// How long a synchronous call polls its completion flag before it blocks on the stream
+// (SMC_SPIN_US, default 60 us).
+int64_t spin_budget_us();
 uint64_t next_matrix_id();
 
 // ---- row-sharded matrices (sharded.cu) ------------------------------------------
