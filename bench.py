@@ -494,7 +494,7 @@ def run_ours(args):
                     "kernel on every rank -> NCCL all-reduce of the packed K+8 doubles -> "
                     "pinned host memory on rank 0, stream sync; x shards resident; "
                     "wall-clock timed, max over ranks")
-    for _ in range(2):
+    for _ in range(max(3, args.warmup)):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
