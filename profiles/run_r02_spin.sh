@@ -1,3 +1,5 @@
+#!/bin/bash
+# gpurun (1 GPU): poll budget of the synchronous call (SMC_SPIN_US 60 vs 5000) -> profiles/r02/r02_spin_budget.txt
 mkdir -p gpurun_out; out=gpurun_out/r02_spin_budget.txt; : > $out
 for i in 1 2; do for us in 60 5000; do for c in 2 4b 5b; do
   echo -n "SMC_SPIN_US=$us cfg=$c " | tee -a $out
