@@ -23,10 +23,6 @@
 
 using namespace smc;
 
-#ifndef SMC_CATL_UNROLL
-#define SMC_CATL_UNROLL 4
-#endif
-constexpr int kCatlUnroll = SMC_CATL_UNROLL;  // exp / partial loops of the TMA pipeline
 
 namespace {
 
@@ -231,6 +227,10 @@ __global__ void __launch_bounds__(512, 1)
                         int y_scalar, double* __restrict__ partials) {
   extern __shared__ __align__(128) unsigned char cat_tma_raw[];
   constexpr int RW = 32 / L;
+  // unroll of the exp / partial loops: 8 amortises the rematerialised polynomial
+  // constants over more elements (C=32: 1.035 -> 1.022 ms, C=8: 0.330 -> 0.324) but costs
+  // the two-lane form registers it needs elsewhere (C=128: 1.20 -> 1.25 ms)
+  constexpr int kCatlUnroll = L == 1 ? 8 : 4;
   const int nwarps = blockDim.x >> 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = lane / RW, rl = lane - q * RW;
